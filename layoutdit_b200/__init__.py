@@ -1,0 +1,11 @@
+"""B200-native DiT backbone forward (drop-in for LayoutDiT's ``DiTBackbone``)."""
+from .config import DiTConfig, dit_base, dit_large, flops_per_image  # noqa: F401
+
+__all__ = ["DiTConfig", "dit_base", "dit_large", "flops_per_image", "DiTBackbone"]
+
+
+def __getattr__(name):
+    if name == "DiTBackbone":
+        from .dit_backbone import DiTBackbone
+        return DiTBackbone
+    raise AttributeError(name)
