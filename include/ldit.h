@@ -1,0 +1,102 @@
+/* libldit_b200 -- C ABI of the B200-native DiT backbone kernels.
+ *
+ * The reference (matteociccozzi/LayoutDiT) has no FFI of its own: its hot path is the Python
+ * call `self.dit(x).hidden_states` (src/layoutdit/modeling/dit_backbone.py:47) into
+ * HuggingFace `BeitModel`, which dispatches one ATen/cuBLAS/cuDNN library kernel per op.
+ * Each entry point below replaces the library call(s) named beside it
+ * (HF = transformers/models/beit/modeling_beit.py, transformers 5.5.0;
+ *  R  = src/layoutdit/modeling/dit_backbone.py of the reference).
+ *
+ * Conventions
+ *  - All pointers are DEVICE pointers into memory owned by the caller (PyTorch in the shipped
+ *    host code).  The library never allocates, frees or retains device memory.
+ *  - `stream` is a cudaStream_t passed as void*.  Every call only enqueues work on it: no
+ *    synchronisation, no use of the default stream, safe to capture into a CUDA graph.
+ *  - Return value: 0 = OK; negative = argument / alignment error (LDIT_E_*); positive = a
+ *    cudaError_t (or 10000 + CUresult from the tensor-map encoder).  No C++ exception crosses
+ *    the ABI.  ldit_error_string() describes any code.
+ *  - Alignment: base pointers 16-byte aligned; row pitches multiples of 16 bytes.
+ *  - bf16 = __nv_bfloat16 (2 bytes); f32 = float.
+ */
+#ifndef LDIT_H_
+#define LDIT_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define LDIT_OK 0
+#define LDIT_E_NULL (-1)       /* required pointer is NULL */
+#define LDIT_E_SHAPE (-2)      /* unsupported dimension */
+#define LDIT_E_ALIGN (-3)      /* pointer / pitch alignment */
+#define LDIT_E_DTYPE (-4)      /* unknown dtype code */
+#define LDIT_E_NO_DRIVER (-5)  /* cuTensorMapEncodeTiled not resolvable (no CUDA driver) */
+
+#define LDIT_DTYPE_F32 0
+#define LDIT_DTYPE_F16 1
+#define LDIT_DTYPE_BF16 2
+
+int ldit_version(void);
+const char* ldit_error_string(int code);
+
+/* nn.LayerNorm(D, eps) -- HF:458,460 (called at HF:478,495); ATen native_layer_norm.
+ * x f32 [rows, D] -> y bf16 [rows, D].  D must be a multiple of 128, D <= 2048. */
+int ldit_layernorm(const void* x, const void* gamma, const void* beta, void* y, int rows, int D, float eps, void* stream);
+
+/* nn.Linear with fused bias -- query/key/value at HF:324-338 run as ONE GEMM over the
+ * concatenated [3D, D] weight (key has no bias: pass zeros in that third of `bias`).
+ * out bf16 [M, N] = A bf16 [M, K] x W bf16 [N, K]^T + bias f32 [N] (bias may be NULL). */
+int ldit_gemm_bias(const void* A, const void* W, const void* bias, void* out, int M, int N, int K, void* stream);
+
+/* BeitIntermediate, HF:428-432: out bf16 [M, N] = gelu_erf(A x W^T + bias). */
+int ldit_gemm_bias_gelu(const void* A, const void* W, const void* bias, void* out, int M, int N, int K, void* stream);
+
+/* BeitSelfOutput + layer-scale + residual (HF:383, 488-492) and BeitOutput + layer-scale +
+ * residual (HF:442, 500-504):  x f32 [M, N] <- x + scale (.) (A x W^T + bias), in place.
+ * scale may be NULL (layer_scale_init_value <= 0, HF:462-467). */
+int ldit_gemm_bias_scale_residual(const void* A, const void* W, const void* bias, const void* scale, void* x, int M, int N,
+                                  int K, void* stream);
+
+/* BeitEmbeddings.forward, HF:161-184 (Conv2d k16 s16 HF:218 + flatten/transpose HF:220 +
+ * cat(cls) HF:176-177 + position add HF:179-180), as an im2col GEMM.
+ *  pixels   [B, 3, H, W] of dtype `pixel_dtype` (LDIT_DTYPE_*), contiguous NCHW
+ *  w        bf16 [D, 768]  flattened conv weight
+ *  pos_bias f32 [P, D]     position rows 1..P (already resized to Gh x Gw) + conv bias
+ *  cls_pos  f32 [D]        cls_token + position row 0
+ *  scratch  bf16 [B*P, 768] workspace for the im2col operand
+ *  x        f32 [B, P+1, D] residual stream (output)
+ * H, W multiples of 16; P = (H/16)(W/16). */
+int ldit_patch_embed(const void* pixels, int pixel_dtype, const void* w, const void* pos_bias, const void* cls_pos,
+                     void* scratch, void* x, int B, int H, int W, int D, void* stream);
+
+/* BeitSelfAttention core, HF:275-298 / F.scaled_dot_product_attention at HF:356-364, plus the
+ * head merge HF:365-367.  qkv bf16 [B*N, 3D] (Q | K | V, heads contiguous, head_dim 64) ->
+ * ctx bf16 [B*N, D].  bias_table: NULL, or f32 [heads, T] with T = (2Gh-1)(2Gw-1)+3 -- the
+ * relative_position_bias_table resized to this window (HF:556-571), transposed; the kernel
+ * gathers it in-tile with the index rule of HF:522-544 instead of materialising [heads,N,N]. */
+int ldit_attention(const void* qkv, void* ctx, const void* bias_table, int B, int N, int heads, int Gh, int Gw, void* stream);
+
+/* Tap extraction + F.interpolate(bilinear, align_corners=False), R:50-61.
+ *  x f32 [B, 1+Gh*Gw, D] (hidden state incl. CLS) -> out bf16, channels-last memory
+ *  [B, oh, ow, D] with oh = floor(Gh*scale), ow = floor(Gw*scale); scale in {4, 2, 1, 0.5}
+ *  (any positive scale is accepted). */
+int ldit_resample_taps(const void* x, void* out, int B, int Gh, int Gw, int D, float scale, void* stream);
+
+/* Bytes of the im2col scratch ldit_patch_embed needs. */
+size_t ldit_patch_embed_scratch_bytes(int B, int H, int W);
+
+/* Tuning knob: force the GEMM tile width (128, 192 or 256); 0 restores the automatic choice
+ * (fewest persistent-schedule rounds x tile width).  Also settable with LDIT_GEMM_BN. */
+void ldit_set_gemm_tile_n(int bn);
+
+/* Number of kernels the library has enqueued since load / last reset (for gpu_launches). */
+unsigned long long ldit_launch_count(void);
+void ldit_reset_launch_count(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* LDIT_H_ */

@@ -1,0 +1,59 @@
+"""ctypes binding of libldit_b200.so (include/ldit.h).  There is no fallback: if the
+library is missing or a call fails, the caller gets an exception."""
+from __future__ import annotations
+
+import ctypes
+import os
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libldit_b200.so")
+
+_c = ctypes
+_vp, _i, _f = _c.c_void_p, _c.c_int, _c.c_float
+
+# name -> (restype, argtypes); mirrors include/ldit.h one to one
+SIGNATURES = {
+    "ldit_version": (_i, []),
+    "ldit_error_string": (_c.c_char_p, [_i]),
+    "ldit_layernorm": (_i, [_vp, _vp, _vp, _vp, _i, _i, _f, _vp]),
+    "ldit_gemm_bias": (_i, [_vp, _vp, _vp, _vp, _i, _i, _i, _vp]),
+    "ldit_gemm_bias_gelu": (_i, [_vp, _vp, _vp, _vp, _i, _i, _i, _vp]),
+    "ldit_gemm_bias_scale_residual": (_i, [_vp, _vp, _vp, _vp, _vp, _i, _i, _i, _vp]),
+    "ldit_patch_embed": (_i, [_vp, _i, _vp, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _vp]),
+    "ldit_attention": (_i, [_vp, _vp, _vp, _i, _i, _i, _i, _i, _vp]),
+    "ldit_resample_taps": (_i, [_vp, _vp, _i, _i, _i, _i, _f, _vp]),
+    "ldit_patch_embed_scratch_bytes": (_c.c_size_t, [_i, _i, _i]),
+    "ldit_set_gemm_tile_n": (None, [_i]),
+    "ldit_launch_count": (_c.c_ulonglong, []),
+    "ldit_reset_launch_count": (None, []),
+}
+
+DTYPE_F32, DTYPE_F16, DTYPE_BF16 = 0, 1, 2
+
+_lib = None
+
+
+class LditError(RuntimeError):
+    pass
+
+
+def load():
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        raise LditError(f"{LIB_PATH} is missing: run `python -m layoutdit_b200.build` "
+                        "(or __graft_entry__.build()). There is no CPU or eager fallback.")
+    lib = ctypes.CDLL(LIB_PATH)
+    for name, (res, args) in SIGNATURES.items():
+        fn = getattr(lib, name)  # AttributeError if the ABI and the header drifted apart
+        fn.restype = res
+        fn.argtypes = args
+    _lib = lib
+    return lib
+
+
+def check(rc: int, what: str):
+    if rc != 0:
+        msg = load().ldit_error_string(rc).decode()
+        raise LditError(f"{what} failed: {msg} (code {rc})")

@@ -1,0 +1,287 @@
+// extern "C" boundary of libldit_b200.so -- see include/ldit.h for the contract.
+// Host code here only validates arguments, builds TMA tensor maps and enqueues kernels.
+#include <atomic>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+
+#include "../../include/ldit.h"
+#include "attention_mma.cuh"
+#include "gemm.cuh"
+#include "rowwise.cuh"
+
+using namespace ldit;
+
+namespace {
+
+std::atomic<unsigned long long> g_launches{0};
+
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                  const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+EncodeTiledFn encode_fn() {
+  static EncodeTiledFn fn = [] {
+    void* p = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) != cudaSuccess ||
+        q != cudaDriverEntryPointSuccess)
+      p = nullptr;
+    (void)cudaGetLastError();
+    return reinterpret_cast<EncodeTiledFn>(p);
+  }();
+  return fn;
+}
+
+// 2-D bf16 tensor [rows, cols] row-major, box [box_rows, 64 cols], 128-byte swizzle,
+// out-of-bounds elements read as zero.
+int make_tmap_bf16_2d(CUtensorMap* tm, const void* ptr, uint64_t rows, uint64_t cols, uint32_t box_rows) {
+  EncodeTiledFn fn = encode_fn();
+  if (!fn) return LDIT_E_NO_DRIVER;
+  cuuint64_t dims[2] = {cols, rows};
+  cuuint64_t strides[1] = {cols * 2};
+  cuuint32_t box[2] = {64, box_rows};
+  cuuint32_t estr[2] = {1, 1};
+  CUresult r = fn(tm, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(ptr), dims, strides, box, estr,
+                  CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                  CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  return r == CUDA_SUCCESS ? 0 : 10000 + static_cast<int>(r);
+}
+
+int num_sms() {
+  static int sms = [] {
+    int dev = 0, n = 148;
+    if (cudaGetDevice(&dev) == cudaSuccess) cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev);
+    return n > 0 ? n : 148;
+  }();
+  return sms;
+}
+
+inline bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15) == 0; }
+
+inline int check_launch() {
+  g_launches.fetch_add(1, std::memory_order_relaxed);
+  return static_cast<int>(cudaGetLastError());
+}
+
+// Tile width: minimise (rounds of the persistent schedule) x (tile width); ties go to the
+// wider tile (fewer re-reads of A).  LDIT_GEMM_BN overrides for experiments.
+std::atomic<int> g_forced_bn{-1};
+
+int pick_bn(int M, int N) {
+  int forced = g_forced_bn.load(std::memory_order_relaxed);
+  if (forced < 0) {
+    const char* e = getenv("LDIT_GEMM_BN");
+    forced = e ? atoi(e) : 0;
+    g_forced_bn.store(forced);
+  }
+  if (forced == 128 || forced == 192 || forced == 256) return forced;
+  const int sms = num_sms();
+  const int mb = (M + kBM - 1) / kBM;
+  int best = 256;
+  long best_cost = -1;
+  const int cands[3] = {256, 192, 128};
+  for (int bn : cands) {
+    const long tiles = static_cast<long>(mb) * ((N + bn - 1) / bn);
+    const long rounds = (tiles + sms - 1) / sms;
+    const long cost = rounds * (bn + 16);  // +16: per-tile fixed overhead in "column" units
+    if (best_cost < 0 || cost < best_cost) { best_cost = cost; best = bn; }
+  }
+  return best;
+}
+
+template <int BN, int EPI>
+int launch_gemm_t(const void* A, const void* W, GemmArgs g, cudaStream_t st) {
+  using Cfg = GemmCfg<BN>;
+  static bool attr_set = false;
+  if (!attr_set) {
+    cudaError_t e = cudaFuncSetAttribute(gemm_tcgen05_kernel<BN, EPI>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES);
+    if (e != cudaSuccess) return static_cast<int>(e);
+    attr_set = true;
+  }
+  CUtensorMap tmA, tmB;
+  int rc = make_tmap_bf16_2d(&tmA, A, g.M, g.K, kBM);
+  if (rc) return rc;
+  rc = make_tmap_bf16_2d(&tmB, W, g.N, g.K, BN);
+  if (rc) return rc;
+  g.num_m_blocks = (g.M + kBM - 1) / kBM;
+  g.num_n_blocks = (g.N + BN - 1) / BN;
+  const int tiles = g.num_m_blocks * g.num_n_blocks;
+  const int grid = tiles < num_sms() ? tiles : num_sms();
+  gemm_tcgen05_kernel<BN, EPI><<<grid, kGemmThreads, Cfg::SMEM_BYTES, st>>>(tmA, tmB, g);
+  return check_launch();
+}
+
+template <int EPI>
+int launch_gemm(const void* A, const void* W, GemmArgs g, cudaStream_t st) {
+  if (!A || !W || !g.out) return LDIT_E_NULL;
+  if (g.M <= 0 || g.N <= 0 || g.K <= 0 || (g.N % 32) || (g.K % 8)) return LDIT_E_SHAPE;
+  if (!aligned16(A) || !aligned16(W) || !aligned16(g.out) || !aligned16(g.bias) || !aligned16(g.scale) ||
+      !aligned16(g.resid) || !aligned16(g.posb))
+    return LDIT_E_ALIGN;
+  switch (pick_bn(g.M, g.N)) {
+    case 128: return launch_gemm_t<128, EPI>(A, W, g, st);
+    case 192: return launch_gemm_t<192, EPI>(A, W, g, st);
+    default: return launch_gemm_t<256, EPI>(A, W, g, st);
+  }
+}
+
+}  // namespace
+
+extern "C" {
+
+int ldit_version(void) { return 100; }
+
+const char* ldit_error_string(int code) {
+  static thread_local char buf[128];
+  switch (code) {
+    case LDIT_OK: return "ok";
+    case LDIT_E_NULL: return "required pointer is NULL";
+    case LDIT_E_SHAPE: return "unsupported shape";
+    case LDIT_E_ALIGN: return "pointer or pitch not 16-byte aligned";
+    case LDIT_E_DTYPE: return "unknown dtype code";
+    case LDIT_E_NO_DRIVER: return "cuTensorMapEncodeTiled unavailable (no CUDA driver)";
+    default: break;
+  }
+  if (code >= 10000) {
+    snprintf(buf, sizeof(buf), "cuTensorMapEncodeTiled failed with CUresult %d", code - 10000);
+    return buf;
+  }
+  if (code > 0) return cudaGetErrorString(static_cast<cudaError_t>(code));
+  return "unknown error";
+}
+
+void ldit_set_gemm_tile_n(int bn) { g_forced_bn.store((bn == 128 || bn == 192 || bn == 256) ? bn : 0); }
+
+unsigned long long ldit_launch_count(void) { return g_launches.load(); }
+void ldit_reset_launch_count(void) { g_launches.store(0); }
+
+int ldit_layernorm(const void* x, const void* gamma, const void* beta, void* y, int rows, int D, float eps, void* stream) {
+  if (!x || !gamma || !beta || !y) return LDIT_E_NULL;
+  if (rows <= 0 || D <= 0 || (D % 128) || D > 2048) return LDIT_E_SHAPE;
+  if (!aligned16(x) || !aligned16(gamma) || !aligned16(beta) || !aligned16(y)) return LDIT_E_ALIGN;
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  const int blocks = (rows + 7) / 8;
+  const float* xf = static_cast<const float*>(x);
+  const float* gf = static_cast<const float*>(gamma);
+  const float* bf = static_cast<const float*>(beta);
+  __nv_bfloat16* yb = static_cast<__nv_bfloat16*>(y);
+#define LDIT_LN_CASE(V) \
+  case V: layernorm_kernel<V><<<blocks, 256, 0, st>>>(xf, gf, bf, yb, rows, eps); break;
+  switch (D / 128) {
+    LDIT_LN_CASE(1) LDIT_LN_CASE(2) LDIT_LN_CASE(3) LDIT_LN_CASE(4) LDIT_LN_CASE(5) LDIT_LN_CASE(6) LDIT_LN_CASE(7)
+    LDIT_LN_CASE(8) LDIT_LN_CASE(9) LDIT_LN_CASE(10) LDIT_LN_CASE(11) LDIT_LN_CASE(12) LDIT_LN_CASE(13)
+    LDIT_LN_CASE(14) LDIT_LN_CASE(15) LDIT_LN_CASE(16)
+    default: return LDIT_E_SHAPE;
+  }
+#undef LDIT_LN_CASE
+  return check_launch();
+}
+
+int ldit_gemm_bias(const void* A, const void* W, const void* bias, void* out, int M, int N, int K, void* stream) {
+  GemmArgs g{};
+  g.M = M; g.N = N; g.K = K;
+  g.bias = static_cast<const float*>(bias);
+  g.out = out; g.ldo = N;
+  return launch_gemm<EPI_BIAS>(A, W, g, static_cast<cudaStream_t>(stream));
+}
+
+int ldit_gemm_bias_gelu(const void* A, const void* W, const void* bias, void* out, int M, int N, int K, void* stream) {
+  GemmArgs g{};
+  g.M = M; g.N = N; g.K = K;
+  g.bias = static_cast<const float*>(bias);
+  g.out = out; g.ldo = N;
+  return launch_gemm<EPI_BIAS_GELU>(A, W, g, static_cast<cudaStream_t>(stream));
+}
+
+int ldit_gemm_bias_scale_residual(const void* A, const void* W, const void* bias, const void* scale, void* x, int M, int N,
+                                  int K, void* stream) {
+  GemmArgs g{};
+  g.M = M; g.N = N; g.K = K;
+  g.bias = static_cast<const float*>(bias);
+  g.scale = static_cast<const float*>(scale);
+  g.resid = static_cast<const float*>(x);
+  g.out = x; g.ldo = N;
+  return launch_gemm<EPI_SCALE_RESID>(A, W, g, static_cast<cudaStream_t>(stream));
+}
+
+size_t ldit_patch_embed_scratch_bytes(int B, int H, int W) {
+  if (B <= 0 || H < 16 || W < 16) return 0;
+  return static_cast<size_t>(B) * (H / 16) * (W / 16) * 768 * 2;
+}
+
+int ldit_patch_embed(const void* pixels, int pixel_dtype, const void* w, const void* pos_bias, const void* cls_pos,
+                     void* scratch, void* x, int B, int H, int W, int D, void* stream) {
+  if (!pixels || !w || !pos_bias || !cls_pos || !scratch || !x) return LDIT_E_NULL;
+  if (B <= 0 || H < 16 || W < 16 || (H % 16) || (W % 16) || D <= 0 || (D % 32)) return LDIT_E_SHAPE;
+  if (!aligned16(pixels) || !aligned16(scratch) || !aligned16(x) || !aligned16(cls_pos)) return LDIT_E_ALIGN;
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  const int Gh = H / 16, Gw = W / 16, P = Gh * Gw;
+  const size_t threads = static_cast<size_t>(B) * 3 * H * (W / 8);
+  const unsigned blocks = static_cast<unsigned>((threads + 255) / 256);
+  __nv_bfloat16* a = static_cast<__nv_bfloat16*>(scratch);
+  switch (pixel_dtype) {
+    case LDIT_DTYPE_F32: im2col_kernel<float><<<blocks, 256, 0, st>>>(static_cast<const float*>(pixels), a, B, H, W, Gh, Gw); break;
+    case LDIT_DTYPE_F16: im2col_kernel<__half><<<blocks, 256, 0, st>>>(static_cast<const __half*>(pixels), a, B, H, W, Gh, Gw); break;
+    case LDIT_DTYPE_BF16:
+      im2col_kernel<__nv_bfloat16><<<blocks, 256, 0, st>>>(static_cast<const __nv_bfloat16*>(pixels), a, B, H, W, Gh, Gw);
+      break;
+    default: return LDIT_E_DTYPE;
+  }
+  int rc = check_launch();
+  if (rc) return rc;
+  cls_rows_kernel<<<(B * (D / 4) + 255) / 256, 256, 0, st>>>(static_cast<const float*>(cls_pos), static_cast<float*>(x), B, P + 1, D);
+  rc = check_launch();
+  if (rc) return rc;
+  GemmArgs g{};
+  g.M = B * P; g.N = D; g.K = 768;
+  g.out = x; g.ldo = D;
+  g.P = P;
+  g.posb = static_cast<const float*>(pos_bias);
+  return launch_gemm<EPI_PATCH>(scratch, w, g, st);
+}
+
+int ldit_attention(const void* qkv, void* ctx, const void* bias_table, int B, int N, int heads, int Gh, int Gw, void* stream) {
+  if (!qkv || !ctx) return LDIT_E_NULL;
+  if (B <= 0 || heads <= 0 || Gh <= 0 || Gw <= 0 || N != Gh * Gw + 1) return LDIT_E_SHAPE;
+  if (!aligned16(qkv) || !aligned16(ctx) || !aligned16(bias_table)) return LDIT_E_ALIGN;
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  AttnArgs a{};
+  a.qkv = static_cast<const __nv_bfloat16*>(qkv);
+  a.ctx = static_cast<__nv_bfloat16*>(ctx);
+  a.bias_table = static_cast<const float*>(bias_table);
+  a.B = B; a.N = N; a.heads = heads; a.D = heads * kAttDh;
+  a.Gh = Gh; a.Gw = Gw; a.T = (2 * Gh - 1) * (2 * Gw - 1) + 3;
+  a.scale_log2e = 0.125f * 1.4426950408889634f;
+  dim3 grid((N + kAttBQ - 1) / kAttBQ, heads, B);
+  size_t smem = 8192 + 32768;
+  if (bias_table) {
+    smem += static_cast<size_t>(a.T) * 4 + static_cast<size_t>(N) * 4;
+    if (smem > 227 * 1024) return LDIT_E_SHAPE;
+    static size_t max_set = 0;
+    if (smem > max_set) {
+      cudaError_t e = cudaFuncSetAttribute(attention_mma_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem));
+      if (e != cudaSuccess) return static_cast<int>(e);
+      max_set = smem;
+    }
+    attention_mma_kernel<true><<<grid, 128, smem, st>>>(a);
+  } else {
+    attention_mma_kernel<false><<<grid, 128, smem, st>>>(a);
+  }
+  return check_launch();
+}
+
+int ldit_resample_taps(const void* x, void* out, int B, int Gh, int Gw, int D, float scale, void* stream) {
+  if (!x || !out) return LDIT_E_NULL;
+  if (B <= 0 || Gh <= 0 || Gw <= 0 || D <= 0 || (D % 8) || !(scale > 0.f)) return LDIT_E_SHAPE;
+  if (!aligned16(x) || !aligned16(out)) return LDIT_E_ALIGN;
+  const int oh = static_cast<int>(floorf(Gh * scale)), ow = static_cast<int>(floorf(Gw * scale));
+  if (oh <= 0 || ow <= 0) return LDIT_E_SHAPE;
+  const size_t total = static_cast<size_t>(B) * oh * ow * (D / 8);
+  const unsigned blocks = static_cast<unsigned>((total + 255) / 256);
+  resample_taps_kernel<<<blocks, 256, 0, static_cast<cudaStream_t>(stream)>>>(
+      static_cast<const float*>(x), static_cast<__nv_bfloat16*>(out), B, Gh * Gw + 1, D, Gh, Gw, oh, ow, 1.0f / scale);
+  return check_launch();
+}
+
+}  // extern "C"

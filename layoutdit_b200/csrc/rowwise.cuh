@@ -1,0 +1,168 @@
+// HBM-bound row-wise kernels: LayerNorm, im2col (+cast), CLS rows, tap resampling.
+// None of these has data reuse worth staging in shared memory; they are written for
+// coalesced 128-bit accesses, one pass over their bytes, and enough bytes in flight.
+#pragma once
+
+#include "ptx.cuh"
+
+namespace ldit {
+
+// ------------------------------------------------------------------------------ LayerNorm
+// nn.LayerNorm(D, eps=1e-12) at HF:458,460 (called HF:478,495).  One warp per row, the row
+// lives in registers: mean, then the centred second moment (eps is ~0, so the one-pass
+// E[x^2]-E[x]^2 form is not safe), all in fp32.  fp32 residual stream in, bf16 out
+// (the next kernel is a bf16 GEMM).
+template <int VPL>  // float4 per lane: D = 128 * VPL
+__global__ void __launch_bounds__(256)
+layernorm_kernel(const float* __restrict__ x, const float* __restrict__ gamma, const float* __restrict__ beta,
+                 __nv_bfloat16* __restrict__ y, int rows, float eps) {
+  constexpr int D = 128 * VPL;
+  const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const int lane = threadIdx.x & 31;
+  if (warp >= rows) return;
+  const float4* xr = reinterpret_cast<const float4*>(x + static_cast<size_t>(warp) * D);
+  float4 v[VPL];
+  float sum = 0.f;
+#pragma unroll
+  for (int i = 0; i < VPL; ++i) {
+    v[i] = xr[lane + 32 * i];
+    sum += (v[i].x + v[i].y) + (v[i].z + v[i].w);
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, o);
+  const float mean = sum * (1.0f / D);
+  float sq = 0.f;
+#pragma unroll
+  for (int i = 0; i < VPL; ++i) {
+    v[i].x -= mean; v[i].y -= mean; v[i].z -= mean; v[i].w -= mean;
+    sq += (v[i].x * v[i].x + v[i].y * v[i].y) + (v[i].z * v[i].z + v[i].w * v[i].w);
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) sq += __shfl_xor_sync(0xffffffffu, sq, o);
+  const float rstd = rsqrtf(sq * (1.0f / D) + eps);
+  uint2* yr = reinterpret_cast<uint2*>(y + static_cast<size_t>(warp) * D);
+  const float4* g4 = reinterpret_cast<const float4*>(gamma);
+  const float4* b4 = reinterpret_cast<const float4*>(beta);
+#pragma unroll
+  for (int i = 0; i < VPL; ++i) {
+    const float4 g = __ldg(g4 + lane + 32 * i);
+    const float4 b = __ldg(b4 + lane + 32 * i);
+    uint2 o;
+    o.x = pack_bf16x2(fmaf(v[i].x * rstd, g.x, b.x), fmaf(v[i].y * rstd, g.y, b.y));
+    o.y = pack_bf16x2(fmaf(v[i].z * rstd, g.z, b.z), fmaf(v[i].w * rstd, g.w, b.w));
+    yr[lane + 32 * i] = o;
+  }
+}
+
+// ------------------------------------------------------------------------- im2col (+cast)
+// Conv2d(3, D, k=16, s=16) at HF:209,218 is a GEMM over 16x16 patches.  This pass rewrites
+// the NCHW page batch as the GEMM's A operand [B*P, 768] bf16 with column order (c, py, px)
+// -- the order of the flattened conv weight -- casting from the caller's dtype on the way
+// (the reference feeds fp32 on CPU and fp16 under autocast, R:trainer.py:155,168).
+template <typename T>
+__device__ __forceinline__ void load8(const T* p, float (&v)[8]);
+template <>
+__device__ __forceinline__ void load8<float>(const float* p, float (&v)[8]) {
+  const float4 a = __ldg(reinterpret_cast<const float4*>(p));
+  const float4 b = __ldg(reinterpret_cast<const float4*>(p) + 1);
+  v[0] = a.x; v[1] = a.y; v[2] = a.z; v[3] = a.w; v[4] = b.x; v[5] = b.y; v[6] = b.z; v[7] = b.w;
+}
+template <>
+__device__ __forceinline__ void load8<__nv_bfloat16>(const __nv_bfloat16* p, float (&v)[8]) {
+  const uint4 a = __ldg(reinterpret_cast<const uint4*>(p));
+  const __nv_bfloat162* h = reinterpret_cast<const __nv_bfloat162*>(&a);
+#pragma unroll
+  for (int i = 0; i < 4; ++i) { const float2 f = __bfloat1622float2(h[i]); v[2 * i] = f.x; v[2 * i + 1] = f.y; }
+}
+template <>
+__device__ __forceinline__ void load8<__half>(const __half* p, float (&v)[8]) {
+  const uint4 a = __ldg(reinterpret_cast<const uint4*>(p));
+  const __half2* h = reinterpret_cast<const __half2*>(&a);
+#pragma unroll
+  for (int i = 0; i < 4; ++i) { const float2 f = __half22float2(h[i]); v[2 * i] = f.x; v[2 * i + 1] = f.y; }
+}
+
+template <typename T>
+__global__ void __launch_bounds__(256)
+im2col_kernel(const T* __restrict__ x, __nv_bfloat16* __restrict__ a, int B, int H, int W, int Gh, int Gw) {
+  // one thread = 8 consecutive pixels of one image row (half a patch row)
+  const int wchunks = (Gw * 16) / 8;
+  const size_t total = static_cast<size_t>(B) * 3 * (Gh * 16) * wchunks;
+  const size_t idx = static_cast<size_t>(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (idx >= total) return;
+  const int xc = static_cast<int>(idx % wchunks);
+  size_t t = idx / wchunks;
+  const int yy = static_cast<int>(t % (Gh * 16)); t /= (Gh * 16);
+  const int c = static_cast<int>(t % 3);
+  const int b = static_cast<int>(t / 3);
+  float v[8];
+  load8<T>(x + ((static_cast<size_t>(b) * 3 + c) * H + yy) * W + xc * 8, v);
+  const int gy = yy >> 4, py = yy & 15, gx = xc >> 1, px = (xc & 1) * 8;
+  const size_t row = (static_cast<size_t>(b) * Gh + gy) * Gw + gx;
+  uint4 o;
+  o.x = pack_bf16x2(v[0], v[1]); o.y = pack_bf16x2(v[2], v[3]);
+  o.z = pack_bf16x2(v[4], v[5]); o.w = pack_bf16x2(v[6], v[7]);
+  *reinterpret_cast<uint4*>(a + row * 768 + c * 256 + py * 16 + px) = o;
+}
+
+// Token row 0 of every image: cls_token + position row 0 (HF:176-180); cls_pos = their sum.
+__global__ void __launch_bounds__(256)
+cls_rows_kernel(const float* __restrict__ cls_pos, float* __restrict__ xres, int B, int N, int D) {
+  const int idx = blockIdx.x * blockDim.x + threadIdx.x;  // float4 index
+  const int d4 = D / 4;
+  if (idx >= B * d4) return;
+  const int b = idx / d4, j = idx - b * d4;
+  reinterpret_cast<float4*>(xres + static_cast<size_t>(b) * N * D)[j] = __ldg(reinterpret_cast<const float4*>(cls_pos) + j);
+}
+
+// ------------------------------------------------------------------------ tap resampling
+// R:dit_backbone.py:50-61: drop CLS, view tokens as a Gh x Gw grid and resample with
+// F.interpolate(scale_factor=s, mode="bilinear", align_corners=False), s in {4, 2, 1, .5}.
+// Output is written channels-last ([B, oh, ow, D] in memory, handed to the caller as a
+// [B, D, oh, ow] view) -- the same strides the reference's interpolate outputs have on the
+// NHWC-strided view it is given, and the layout in which both the token reads and the
+// (dominant) tap writes are fully coalesced.  ATen's source-index rule for a given
+// scale_factor: src = max((dst + .5) / s - .5, 0); i0 = min(floor(src), in-1); i1 = min(i0+1, in-1).
+__global__ void __launch_bounds__(256)
+resample_taps_kernel(const float* __restrict__ xres, __nv_bfloat16* __restrict__ out, int B, int N, int D, int Gh, int Gw,
+                     int oh, int ow, float inv_scale) {
+  const int d8 = D / 8;
+  const size_t total = static_cast<size_t>(B) * oh * ow * d8;
+  const size_t idx = static_cast<size_t>(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (idx >= total) return;
+  const int j = static_cast<int>(idx % d8);
+  size_t t = idx / d8;
+  const int ox = static_cast<int>(t % ow); t /= ow;
+  const int oy = static_cast<int>(t % oh);
+  const int b = static_cast<int>(t / oh);
+  const float sy = fmaxf((oy + 0.5f) * inv_scale - 0.5f, 0.f);
+  const float sx = fmaxf((ox + 0.5f) * inv_scale - 0.5f, 0.f);
+  const int y0 = min(static_cast<int>(sy), Gh - 1), x0 = min(static_cast<int>(sx), Gw - 1);
+  const int y1 = min(y0 + 1, Gh - 1), x1 = min(x0 + 1, Gw - 1);
+  const float ly = sy - y0, lx = sx - x0;
+  const float w00 = (1.f - ly) * (1.f - lx), w01 = (1.f - ly) * lx, w10 = ly * (1.f - lx), w11 = ly * lx;
+  const float* base = xres + (static_cast<size_t>(b) * N + 1) * D + j * 8;
+  const float* p00 = base + static_cast<size_t>(y0 * Gw + x0) * D;
+  const float* p01 = base + static_cast<size_t>(y0 * Gw + x1) * D;
+  const float* p10 = base + static_cast<size_t>(y1 * Gw + x0) * D;
+  const float* p11 = base + static_cast<size_t>(y1 * Gw + x1) * D;
+  float acc[8];
+#pragma unroll
+  for (int h = 0; h < 2; ++h) {
+    const float4 a = __ldg(reinterpret_cast<const float4*>(p00) + h);
+    const float4 bq = __ldg(reinterpret_cast<const float4*>(p01) + h);
+    const float4 c = __ldg(reinterpret_cast<const float4*>(p10) + h);
+    const float4 d = __ldg(reinterpret_cast<const float4*>(p11) + h);
+    // same association order as ATen: w00*a + w01*b + w10*c + w11*d
+    acc[4 * h + 0] = w00 * a.x + w01 * bq.x + w10 * c.x + w11 * d.x;
+    acc[4 * h + 1] = w00 * a.y + w01 * bq.y + w10 * c.y + w11 * d.y;
+    acc[4 * h + 2] = w00 * a.z + w01 * bq.z + w10 * c.z + w11 * d.z;
+    acc[4 * h + 3] = w00 * a.w + w01 * bq.w + w10 * c.w + w11 * d.w;
+  }
+  uint4 o;
+  o.x = pack_bf16x2(acc[0], acc[1]); o.y = pack_bf16x2(acc[2], acc[3]);
+  o.z = pack_bf16x2(acc[4], acc[5]); o.w = pack_bf16x2(acc[6], acc[7]);
+  reinterpret_cast<uint4*>(out)[idx] = o;
+}
+
+}  // namespace ldit

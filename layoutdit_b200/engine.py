@@ -1,0 +1,311 @@
+"""Host-side orchestration of the backbone forward: weight packing, per-geometry
+workspaces, and the launch sequence over the C ABI (include/ldit.h).
+
+PyTorch is used here for device memory, streams and CUDA-graph capture only; every
+arithmetic step of the forward is a kernel in libldit_b200.so.  The two places a torch op
+touches numbers are weight-preparation steps executed once per (weights, H, W), never per
+forward: resizing the position table (HF:138-159) and the relative-position bias tables
+(HF:556-571) to the current patch grid.
+"""
+from __future__ import annotations
+
+import math
+from collections import OrderedDict
+from dataclasses import dataclass, field
+
+import torch
+import torch.nn.functional as F
+
+from . import _lib
+from .config import DiTConfig
+from .dit_params import DiTParameters
+
+_DTYPE_CODE = {torch.float32: _lib.DTYPE_F32, torch.float16: _lib.DTYPE_F16, torch.bfloat16: _lib.DTYPE_BF16}
+TAP_SCALES = (4.0, 2.0, 1.0, 0.5)  # R:dit_backbone.py:35
+
+
+def tap_layer_indices(num_layers: int):
+    d = num_layers
+    return [d // 3, d // 2, 2 * d // 3, d]  # R:dit_backbone.py:33-34
+
+
+def _ptr(t):
+    return None if t is None else t.data_ptr()
+
+
+@dataclass
+class _LayerPack:
+    ln1_w: torch.Tensor
+    ln1_b: torch.Tensor
+    wqkv: torch.Tensor      # bf16 [3D, D]
+    bqkv: torch.Tensor      # f32 [3D]  (key third is zero, HF:240)
+    wo: torch.Tensor        # bf16 [D, D]
+    bo: torch.Tensor
+    lam1: torch.Tensor | None
+    ln2_w: torch.Tensor
+    ln2_b: torch.Tensor
+    w1: torch.Tensor        # bf16 [I, D]
+    b1: torch.Tensor
+    w2: torch.Tensor        # bf16 [D, I]
+    b2: torch.Tensor
+    lam2: torch.Tensor | None
+    rel_table: torch.Tensor | None   # f32 [T0, heads] native-window table (per-layer), or None
+
+
+@dataclass
+class _Geometry:
+    """Everything that depends on (B, H, W): workspaces and resized tables."""
+    B: int
+    H: int
+    W: int
+    Gh: int
+    Gw: int
+    N: int
+    M: int
+    x: torch.Tensor          # f32 [M, D] residual stream
+    a: torch.Tensor          # bf16 [M, D] LayerNorm output / attention context
+    big: torch.Tensor        # bf16 [M, max(3D, I)] QKV, MLP hidden and im2col scratch (disjoint lifetimes)
+    pos_bias: torch.Tensor   # f32 [P, D]
+    cls_pos: torch.Tensor    # f32 [D]
+    bias_tables: list        # per layer: f32 [heads, T] or None
+    graph: object = None
+    graph_in: torch.Tensor | None = None
+    graph_out: OrderedDict | None = None
+    launches: int = 0
+    extra: dict = field(default_factory=dict)
+
+
+class Engine:
+    def __init__(self, params: DiTParameters, cfg: DiTConfig):
+        self.params = params
+        self.cfg = cfg
+        self.lib = _lib.load()
+        self._pack_key = None
+        self._layers: list[_LayerPack] = []
+        self._geoms: dict = {}
+        self.tap_idx = tap_layer_indices(cfg.num_hidden_layers)
+
+    # ------------------------------------------------------------------ weight packing
+    def _weights_key(self):
+        return tuple((p.data_ptr(), p._version) for p in self.params.parameters())
+
+    def refresh_weights(self, force: bool = False):
+        key = self._weights_key()
+        if not force and key == self._pack_key:
+            return
+        cfg, P = self.cfg, self.params
+        dev = P.embeddings.cls_token.device
+        if dev.type != "cuda":
+            raise _lib.LditError("DiTBackbone parameters must live on a CUDA device (there is no CPU path)")
+        f32 = lambda t: t.detach().to(dev, torch.float32).contiguous()
+        bf16 = lambda t: t.detach().to(dev, torch.bfloat16).contiguous()
+        with torch.no_grad():
+            e = P.embeddings
+            D = cfg.hidden_size
+            self.w_patch = bf16(e.patch_embeddings.projection.weight.reshape(D, -1))
+            self.b_patch = f32(e.patch_embeddings.projection.bias)
+            self.cls = f32(e.cls_token.reshape(D))
+            self.pos = None if e.position_embeddings is None else f32(e.position_embeddings)
+            enc = P.encoder
+            self.shared_table = (f32(enc.relative_position_bias.relative_position_bias_table)
+                                 if cfg.use_shared_relative_position_bias else None)
+            layers = []
+            for L in enc.layer:
+                at = L.attention.attention
+                wqkv = torch.cat([at.query.weight, at.key.weight, at.value.weight], dim=0)
+                bqkv = torch.cat([at.query.bias, torch.zeros_like(at.query.bias), at.value.bias], dim=0)
+                layers.append(_LayerPack(
+                    ln1_w=f32(L.layernorm_before.weight), ln1_b=f32(L.layernorm_before.bias),
+                    wqkv=bf16(wqkv), bqkv=f32(bqkv),
+                    wo=bf16(L.attention.output.dense.weight), bo=f32(L.attention.output.dense.bias),
+                    lam1=None if L.lambda_1 is None else f32(L.lambda_1),
+                    ln2_w=f32(L.layernorm_after.weight), ln2_b=f32(L.layernorm_after.bias),
+                    w1=bf16(L.intermediate.dense.weight), b1=f32(L.intermediate.dense.bias),
+                    w2=bf16(L.output.dense.weight), b2=f32(L.output.dense.bias),
+                    lam2=None if L.lambda_2 is None else f32(L.lambda_2),
+                    rel_table=(f32(at.relative_position_bias.relative_position_bias_table)
+                               if cfg.use_relative_position_bias else None)))
+            self._layers = layers
+        self._pack_key = key
+        self._geoms.clear()  # resized tables and captured graphs hold the old weights
+        self.device = dev
+
+    # --------------------------------------------------------------- per-geometry state
+    def _resized_pos(self, Gh, Gw, H, W):
+        """HF ``interpolate_pos_encoding`` (HF:121-159): weight preparation, once per (H, W)."""
+        pos, g = self.pos, self.cfg.grid
+        if Gh * Gw == g * g and H == W:
+            return pos[0]
+        D = pos.shape[-1]
+        grid = pos[0, 1:].reshape(1, g, g, D).permute(0, 3, 1, 2)
+        grid = F.interpolate(grid, size=(Gh, Gw), mode="bicubic", align_corners=False)
+        return torch.cat([pos[0, :1], grid.permute(0, 2, 3, 1).reshape(Gh * Gw, D)], dim=0)
+
+    def _resized_table(self, table, Gh, Gw):
+        """First half of ``BeitRelativePositionBias.forward`` (HF:550-571), once per (H, W):
+        -> f32 [heads, (2Gh-1)(2Gw-1)+3]; the gather by index (HF:573-581) happens in-tile."""
+        g = self.cfg.grid
+        old = 2 * g - 1
+        nh, nw = 2 * Gh - 1, 2 * Gw - 1
+        sub = table[: old * old].reshape(1, old, old, -1).permute(0, 3, 1, 2)
+        new = F.interpolate(sub, size=(nh, nw), mode="bilinear")
+        new = new.permute(0, 2, 3, 1).reshape(nh * nw, -1)
+        return torch.cat([new, table[old * old:]], dim=0).t().contiguous()
+
+    def _geometry(self, B, H, W) -> _Geometry:
+        key = (B, H, W)
+        geo = self._geoms.get(key)
+        if geo is not None:
+            return geo
+        cfg, dev = self.cfg, self.device
+        D, I = cfg.hidden_size, cfg.intermediate_size
+        Gh, Gw = H // 16, W // 16
+        P = Gh * Gw
+        N = P + 1
+        M = B * N
+        with torch.no_grad():
+            if self.pos is not None:
+                pos = self._resized_pos(Gh, Gw, H, W)
+                pos_bias = (pos[1:] + self.b_patch).contiguous()
+                cls_pos = (self.cls + pos[0]).contiguous()
+            else:
+                pos_bias = self.b_patch.expand(P, D).contiguous()
+                cls_pos = self.cls.clone()
+            tables = []
+            shared = None if self.shared_table is None else self._resized_table(self.shared_table, Gh, Gw)
+            for L in self._layers:
+                t = None if L.rel_table is None else self._resized_table(L.rel_table, Gh, Gw)
+                tables.append(t if t is not None else shared)
+        wide = max(3 * D, I)
+        geo = _Geometry(B=B, H=H, W=W, Gh=Gh, Gw=Gw, N=N, M=M,
+                        x=torch.empty(M, D, device=dev, dtype=torch.float32),
+                        a=torch.empty(M, D, device=dev, dtype=torch.bfloat16),
+                        big=torch.empty(M * wide, device=dev, dtype=torch.bfloat16),
+                        pos_bias=pos_bias, cls_pos=cls_pos, bias_tables=tables)
+        self._geoms[key] = geo
+        return geo
+
+    # -------------------------------------------------------------------- launch sequence
+    def _alloc_outputs(self, geo: _Geometry):
+        D = self.cfg.hidden_size
+        outs = []
+        for s in TAP_SCALES:
+            oh, ow = int(math.floor(geo.Gh * s)), int(math.floor(geo.Gw * s))
+            outs.append(torch.empty(geo.B, oh, ow, D, device=self.device, dtype=torch.bfloat16))
+        return outs
+
+    def _enqueue(self, geo: _Geometry, x: torch.Tensor, outs, stream: int):
+        """Enqueue the whole forward on ``stream``.  Returns the number of kernels launched."""
+        lib, cfg, chk = self.lib, self.cfg, _lib.check
+        D, I, heads = cfg.hidden_size, cfg.intermediate_size, cfg.num_attention_heads
+        M, N, B = geo.M, geo.N, geo.B
+        xr, a, big = geo.x.data_ptr(), geo.a.data_ptr(), geo.big.data_ptr()
+        eps = float(cfg.layer_norm_eps)
+        n0 = lib.ldit_launch_count()
+        chk(lib.ldit_patch_embed(x.data_ptr(), _DTYPE_CODE[x.dtype], self.w_patch.data_ptr(), geo.pos_bias.data_ptr(),
+                                 geo.cls_pos.data_ptr(), big, xr, B, geo.H, geo.W, D, stream), "ldit_patch_embed")
+
+        def emit_tap(layer_no):
+            # hidden_states[layer_no] is the residual stream right now (HF:628-630, 654-655)
+            for idx, slot in zip(self.tap_idx, range(4)):
+                if idx == layer_no:
+                    chk(lib.ldit_resample_taps(xr, outs[slot].data_ptr(), B, geo.Gh, geo.Gw, D, TAP_SCALES[slot], stream),
+                        "ldit_resample_taps")
+
+        emit_tap(0)
+        for i, L in enumerate(self._layers):
+            chk(lib.ldit_layernorm(xr, L.ln1_w.data_ptr(), L.ln1_b.data_ptr(), a, M, D, eps, stream), "ldit_layernorm")
+            chk(lib.ldit_gemm_bias(a, L.wqkv.data_ptr(), L.bqkv.data_ptr(), big, M, 3 * D, D, stream), "ldit_gemm_bias")
+            chk(lib.ldit_attention(big, a, _ptr(geo.bias_tables[i]), B, N, heads, geo.Gh, geo.Gw, stream), "ldit_attention")
+            chk(lib.ldit_gemm_bias_scale_residual(a, L.wo.data_ptr(), L.bo.data_ptr(), _ptr(L.lam1), xr, M, D, D, stream),
+                "ldit_gemm_bias_scale_residual")
+            chk(lib.ldit_layernorm(xr, L.ln2_w.data_ptr(), L.ln2_b.data_ptr(), a, M, D, eps, stream), "ldit_layernorm")
+            chk(lib.ldit_gemm_bias_gelu(a, L.w1.data_ptr(), L.b1.data_ptr(), big, M, I, D, stream), "ldit_gemm_bias_gelu")
+            chk(lib.ldit_gemm_bias_scale_residual(big, L.w2.data_ptr(), L.b2.data_ptr(), _ptr(L.lam2), xr, M, D, I, stream),
+                "ldit_gemm_bias_scale_residual")
+            emit_tap(i + 1)
+        return int(lib.ldit_launch_count() - n0)
+
+    @staticmethod
+    def _as_feats(outs):
+        feats = OrderedDict()
+        for i, o in enumerate(outs, start=2):
+            feats[f"p{i}"] = o.permute(0, 3, 1, 2)  # [B, D, oh, ow] view of channels-last memory
+        return feats
+
+    def prepare_input(self, x: torch.Tensor) -> torch.Tensor:
+        if x.dim() != 4:
+            raise ValueError(f"expected pixel_values of shape [B, 3, H, W], got {tuple(x.shape)}")
+        if x.shape[1] != self.cfg.num_channels:
+            raise ValueError("Make sure that the channel dimension of the pixel values match with the one set in the configuration.")
+        if not x.is_cuda:
+            raise _lib.LditError("DiTBackbone.forward needs a CUDA tensor (there is no CPU path)")
+        if x.dtype not in _DTYPE_CODE:
+            x = x.float()
+        H, W = x.shape[2], x.shape[3]
+        if H < 16 or W < 16:
+            raise ValueError("image smaller than one 16x16 patch")
+        if H % 16 or W % 16:  # Conv2d(k16, s16) ignores the ragged border (HF:218)
+            x = x[:, :, : H // 16 * 16, : W // 16 * 16]
+        return x.contiguous()
+
+    def forward(self, x: torch.Tensor):
+        self.refresh_weights()
+        H0, W0 = x.shape[2], x.shape[3]
+        x = self.prepare_input(x)
+        geo = self._geometry(x.shape[0], H0, W0) if (H0 % 16 == 0 and W0 % 16 == 0) else self._geometry_ragged(x, H0, W0)
+        outs = self._alloc_outputs(geo)
+        geo.launches = self._enqueue(geo, x, outs, torch.cuda.current_stream(self.device).cuda_stream)
+        return self._as_feats(outs)
+
+    def _geometry_ragged(self, x, H0, W0):
+        # the position-table rule looks at the ORIGINAL height/width (HF:135), the conv at the cropped ones
+        key = (x.shape[0], H0, W0)
+        geo = self._geoms.get(key)
+        if geo is None:
+            geo = self._geometry(x.shape[0], H0, W0)
+            geo.H, geo.W = x.shape[2], x.shape[3]
+        return geo
+
+    # ----------------------------------------------------------------------- CUDA graphs
+    def forward_graphed(self, x: torch.Tensor):
+        """Replay a captured CUDA graph of the whole forward for this (B, H, W, dtype).
+        Outputs are STATIC buffers overwritten by the next call with the same geometry."""
+        self.refresh_weights()
+        if x.shape[2] % 16 or x.shape[3] % 16:
+            return self.forward(x)
+        x = self.prepare_input(x)
+        geo = self._geometry(x.shape[0], x.shape[2], x.shape[3])
+        if geo.graph is None or geo.graph_in.dtype != x.dtype:
+            geo.graph_in = torch.empty_like(x)
+            geo.graph_in.copy_(x)
+            outs = self._alloc_outputs(geo)
+            side = torch.cuda.Stream(self.device)
+            side.wait_stream(torch.cuda.current_stream(self.device))
+            with torch.cuda.stream(side):  # warm-up outside capture: sets func attributes, loads modules
+                self._enqueue(geo, geo.graph_in, outs, side.cuda_stream)
+            torch.cuda.current_stream(self.device).wait_stream(side)
+            torch.cuda.synchronize(self.device)
+            graph = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(graph):
+                geo.launches = self._enqueue(geo, geo.graph_in, outs, torch.cuda.current_stream(self.device).cuda_stream)
+            geo.graph, geo.graph_out = graph, self._as_feats(outs)
+        if x.data_ptr() != geo.graph_in.data_ptr():
+            geo.graph_in.copy_(x, non_blocking=True)
+        geo.graph.replay()
+        return geo.graph_out
+
+    def graph_input_buffer(self, B, H, W, dtype=torch.float32):
+        """The static input tensor of the captured graph for this geometry: writing pixels
+        straight into it (e.g. the H2D copy) skips the staging copy in ``forward_graphed``."""
+        self.refresh_weights()
+        geo = self._geometry(B, H, W)
+        if geo.graph_in is None or geo.graph_in.dtype != dtype:
+            geo.graph = None
+            geo.graph_in = torch.zeros(B, 3, H, W, device=self.device, dtype=dtype)
+            self.forward_graphed(geo.graph_in)
+        return geo.graph_in
+
+    def last_launches(self, B, H, W) -> int:
+        geo = self._geoms.get((B, H, W))
+        return 0 if geo is None else geo.launches

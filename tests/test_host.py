@@ -1,0 +1,107 @@
+"""CPU: host-side logic and the C-ABI surface (no kernel is launched)."""
+import ctypes
+import os
+import re
+
+import pytest
+import torch
+
+from conftest import ROOT
+from layoutdit_b200 import _lib
+from layoutdit_b200.config import DiTConfig, dit_base, dit_large, flops_per_image
+from layoutdit_b200.dit_params import DiTParameters
+from layoutdit_b200.synth import make_state_dict, state_dict_keys, synthetic_pages
+from oracle import hf_reference
+
+
+def _declared_symbols():
+    text = open(os.path.join(ROOT, "include", "ldit.h")).read()
+    text = re.sub(r"/\*.*?\*/", "", text, flags=re.S)
+    return sorted(set(re.findall(r"\b(ldit_[a-z_0-9]+)\s*\(", text)))
+
+
+def test_library_builds_and_exports_every_declared_symbol():
+    from layoutdit_b200 import build
+    path = build.build()
+    lib = ctypes.CDLL(path)
+    declared = _declared_symbols()
+    assert len(declared) >= 10
+    for name in declared:
+        assert hasattr(lib, name), f"{name} declared in include/ldit.h but not exported"
+    assert sorted(_lib.SIGNATURES) == declared, "ctypes table and header drifted apart"
+    assert lib.ldit_version() >= 100
+
+
+def test_argument_validation_without_gpu():
+    lib = _lib.load()
+    assert lib.ldit_layernorm(None, None, None, None, 4, 768, 1e-12, None) == -1
+    buf = ctypes.create_string_buffer(64)
+    p = ctypes.addressof(buf)
+    p16 = (p + 15) & ~15
+    assert lib.ldit_layernorm(p16, p16, p16, p16, 4, 100, 1e-12, None) == -2      # D not a multiple of 128
+    assert lib.ldit_gemm_bias(p16, p16, None, p16 + 2, 128, 768, 768, None) == -3   # misaligned output
+    assert lib.ldit_attention(p16, p16, None, 1, 100, 12, 14, 14, None) == -2       # N != Gh*Gw+1
+    assert lib.ldit_patch_embed(p16, 7, p16, p16, p16, p16, p16, 1, 32, 32, 768, None) == -4
+    assert lib.ldit_error_string(-3).decode().startswith("pointer")
+    assert lib.ldit_patch_embed_scratch_bytes(64, 224, 224) == 64 * 196 * 768 * 2
+
+
+@pytest.mark.parametrize("cfg", [dit_base(), dit_large(),
+                                 DiTConfig(use_relative_position_bias=True, use_absolute_position_embeddings=False),
+                                 DiTConfig(use_shared_relative_position_bias=True, use_mask_token=False,
+                                           layer_scale_init_value=0.0)])
+def test_parameter_tree_matches_hf_state_dict(cfg):
+    ours = DiTParameters(cfg).state_dict()
+    hf = hf_reference.build(cfg.to_dict()).dit.state_dict()
+    assert list(ours) == list(hf)
+    assert all(ours[k].shape == hf[k].shape for k in hf)
+    assert dict(state_dict_keys(cfg)) == {k: tuple(v.shape) for k, v in hf.items()}
+
+
+def test_state_dict_roundtrip_and_legacy_buffers_ignored():
+    cfg = DiTConfig(hidden_size=128, num_hidden_layers=3, num_attention_heads=2, intermediate_size=256, image_size=64,
+                    use_relative_position_bias=True)
+    sd = make_state_dict(cfg, 3, True)
+    sd["encoder.layer.0.attention.attention.relative_position_bias.relative_position_index"] = torch.zeros(17, 17)
+    p = DiTParameters(cfg)
+    res = p.load_state_dict(sd, strict=True)
+    assert not res.missing_keys and not res.unexpected_keys
+    for k, v in p.state_dict().items():
+        assert torch.equal(v, sd[k])
+
+
+def test_hf_init_statistics():
+    p = DiTParameters(dit_base())
+    sd = p.state_dict()
+    assert float(sd["embeddings.cls_token"].abs().max()) == 0.0
+    assert float(sd["embeddings.position_embeddings"].abs().max()) == 0.0
+    assert abs(float(sd["encoder.layer.3.intermediate.dense.weight"].std()) - 0.02) < 1e-3
+    assert float(sd["encoder.layer.3.lambda_1"].mean()) == pytest.approx(0.1)
+    assert float(sd["encoder.layer.0.layernorm_before.weight"].mean()) == 1.0
+
+
+def test_config_rules_and_flops():
+    with pytest.raises(ValueError):
+        DiTConfig(hidden_size=100)
+    with pytest.raises(ValueError):
+        DiTConfig(hidden_size=768, num_attention_heads=8)
+    assert flops_per_image(dit_base(), 224, 224) / 1e9 == pytest.approx(35.126, abs=2e-3)
+    assert flops_per_image(dit_base(), 512, 512) / 1e9 == pytest.approx(214.054, abs=2e-3)
+    assert flops_per_image(dit_large(), 224, 224) / 1e9 == pytest.approx(123.107, abs=2e-3)
+
+
+def test_backbone_boundary_attributes_and_cpu_refusal():
+    from layoutdit_b200 import DiTBackbone
+    m = DiTBackbone(pretrained=False)
+    assert m.hidden_size == 768 and m.layer_idxs == [4, 6, 8, 12] and m.scales == [4.0, 2.0, 1.0, 0.5]
+    assert isinstance(m.dit, torch.nn.Module)
+    res = m.dit.load_state_dict({"embeddings.cls_token": torch.ones(1, 1, 768)}, strict=False)
+    assert "embeddings.cls_token" not in res.missing_keys
+    with pytest.raises(_lib.LditError):   # no CPU fallback: fails loudly
+        m.eval()(torch.zeros(1, 3, 224, 224))
+
+
+def test_synthetic_pages_are_deterministic_and_in_range():
+    a, b = synthetic_pages(2, 64, 96, 7), synthetic_pages(2, 64, 96, 7)
+    assert torch.equal(a, b) and a.shape == (2, 3, 64, 96)
+    assert float(a.min()) >= -1.0 and float(a.max()) <= 1.0

@@ -1,0 +1,188 @@
+"""GPU: every C-ABI entry point against a plain fp32 PyTorch statement of the same op on the
+same (bf16-rounded) inputs.  All calls go through ctypes -> libldit_b200.so."""
+import math
+
+import pytest
+import torch
+import torch.nn.functional as F
+
+from layoutdit_b200 import _lib
+
+pytestmark = pytest.mark.gpu
+
+
+def _stream():
+    return torch.cuda.current_stream().cuda_stream
+
+
+def _rel_fro(got, ref):
+    return float((got.double() - ref.double()).norm() / ref.double().norm().clamp_min(1e-30))
+
+
+@pytest.fixture(scope="module")
+def lib(cuda_device):
+    lib = _lib.load()
+    yield lib
+    lib.ldit_set_gemm_tile_n(0)
+
+
+# ----------------------------------------------------------------------------- LayerNorm
+@pytest.mark.parametrize("rows,D", [(1, 128), (1001, 768), (1576, 1024), (12608, 768)])
+def test_layernorm(lib, rows, D):
+    g = torch.Generator(device="cuda").manual_seed(rows + D)
+    x = torch.randn(rows, D, device="cuda", generator=g) * 3 + 0.7
+    x[0, :] = 5.0                                   # constant row: variance 0, eps=1e-12 must not blow up to NaN
+    w = torch.randn(D, device="cuda", generator=g)
+    b = torch.randn(D, device="cuda", generator=g)
+    y = torch.empty(rows, D, device="cuda", dtype=torch.bfloat16)
+    _lib.check(lib.ldit_layernorm(x.data_ptr(), w.data_ptr(), b.data_ptr(), y.data_ptr(), rows, D, 1e-12, _stream()), "ln")
+    ref = F.layer_norm(x, (D,), w, b, 1e-12)
+    assert torch.isfinite(y.float()).all()
+    torch.testing.assert_close(y.float()[1:], ref[1:], rtol=2 ** -7, atol=2e-2)
+    assert _rel_fro(y.float()[1:], ref[1:]) < 3e-3
+
+
+# ---------------------------------------------------------------------------------- GEMMs
+GEMM_SHAPES = [(128, 128, 64), (200, 256, 128), (333, 768, 768), (1000, 2304, 768), (520, 3072, 768),
+               (257, 768, 3072), (130, 1024, 1024), (4100, 768, 768)]
+
+
+def _gemm_inputs(M, N, K, seed):
+    g = torch.Generator(device="cuda").manual_seed(seed)
+    A = (torch.randn(M, K, device="cuda", generator=g)).to(torch.bfloat16)
+    W = (torch.randn(N, K, device="cuda", generator=g) * 0.05).to(torch.bfloat16)
+    bias = torch.randn(N, device="cuda", generator=g)
+    return A, W, bias
+
+
+@pytest.mark.parametrize("bn", [0, 128, 192, 256])
+@pytest.mark.parametrize("M,N,K", GEMM_SHAPES)
+def test_gemm_bias(lib, M, N, K, bn):
+    lib.ldit_set_gemm_tile_n(bn)
+    A, W, bias = _gemm_inputs(M, N, K, M + N + K)
+    out = torch.full((M, N), float("nan"), device="cuda", dtype=torch.bfloat16)
+    _lib.check(lib.ldit_gemm_bias(A.data_ptr(), W.data_ptr(), bias.data_ptr(), out.data_ptr(), M, N, K, _stream()), "gemm")
+    ref = A.float() @ W.float().t() + bias
+    assert torch.isfinite(out.float()).all()
+    assert _rel_fro(out.float(), ref) < 4e-3
+    torch.testing.assert_close(out.float(), ref, rtol=2 ** -7, atol=2e-2)
+
+
+@pytest.mark.parametrize("M,N,K", [(333, 3072, 768), (12608, 3072, 768)])
+def test_gemm_bias_gelu(lib, M, N, K):
+    lib.ldit_set_gemm_tile_n(0)
+    A, W, bias = _gemm_inputs(M, N, K, 7)
+    out = torch.empty(M, N, device="cuda", dtype=torch.bfloat16)
+    _lib.check(lib.ldit_gemm_bias_gelu(A.data_ptr(), W.data_ptr(), bias.data_ptr(), out.data_ptr(), M, N, K, _stream()), "gemm")
+    ref = F.gelu(A.float() @ W.float().t() + bias)          # exact erf GELU
+    assert _rel_fro(out.float(), ref) < 4e-3
+    torch.testing.assert_close(out.float(), ref, rtol=2 ** -7, atol=2e-2)
+
+
+@pytest.mark.parametrize("with_scale", [True, False])
+@pytest.mark.parametrize("M,N,K", [(333, 768, 768), (12608, 768, 3072), (197, 1024, 4096)])
+def test_gemm_bias_scale_residual(lib, M, N, K, with_scale):
+    lib.ldit_set_gemm_tile_n(0)
+    A, W, bias = _gemm_inputs(M, N, K, 11)
+    g = torch.Generator(device="cuda").manual_seed(5)
+    x = torch.randn(M, N, device="cuda", generator=g)
+    scale = torch.rand(N, device="cuda", generator=g) + 0.05 if with_scale else None
+    ref = x + (scale if with_scale else 1.0) * (A.float() @ W.float().t() + bias)
+    _lib.check(lib.ldit_gemm_bias_scale_residual(A.data_ptr(), W.data_ptr(), bias.data_ptr(),
+                                                 scale.data_ptr() if with_scale else None, x.data_ptr(), M, N, K, _stream()),
+               "gemm")
+    # fp32 output: only accumulation-order noise over K bf16 products
+    torch.testing.assert_close(x, ref, rtol=1e-4, atol=2e-3)
+
+
+def test_gemm_rejects_bad_arguments(lib):
+    A, W, bias = _gemm_inputs(128, 128, 64, 1)
+    out = torch.empty(128, 128, device="cuda", dtype=torch.bfloat16)
+    assert lib.ldit_gemm_bias(A.data_ptr(), W.data_ptr(), bias.data_ptr(), out.data_ptr(), 128, 100, 64, _stream()) == -2
+    assert lib.ldit_gemm_bias(A.data_ptr(), None, bias.data_ptr(), out.data_ptr(), 128, 128, 64, _stream()) == -1
+
+
+# ---------------------------------------------------------------------------- patch embed
+@pytest.mark.parametrize("dtype", [torch.float32, torch.float16, torch.bfloat16])
+@pytest.mark.parametrize("B,H,W,D", [(2, 64, 96, 128), (3, 224, 224, 768)])
+def test_patch_embed(lib, B, H, W, D, dtype):
+    g = torch.Generator(device="cuda").manual_seed(B * H + W)
+    px = (torch.rand(B, 3, H, W, device="cuda", generator=g) * 2 - 1).to(dtype)
+    w = (torch.randn(D, 3, 16, 16, device="cuda", generator=g) * 0.04).to(torch.bfloat16)
+    cb = torch.randn(D, device="cuda", generator=g) * 0.1
+    P = (H // 16) * (W // 16)
+    pos = torch.randn(P + 1, D, device="cuda", generator=g) * 0.2
+    cls = torch.randn(D, device="cuda", generator=g) * 0.2
+    pos_bias = (pos[1:] + cb).contiguous()
+    cls_pos = (cls + pos[0]).contiguous()
+    scratch = torch.empty(lib.ldit_patch_embed_scratch_bytes(B, H, W) // 2, device="cuda", dtype=torch.bfloat16)
+    x = torch.full((B, P + 1, D), float("nan"), device="cuda")
+    _lib.check(lib.ldit_patch_embed(px.data_ptr(), {torch.float32: 0, torch.float16: 1, torch.bfloat16: 2}[dtype],
+                                    w.reshape(D, -1).data_ptr(), pos_bias.data_ptr(), cls_pos.data_ptr(),
+                                    scratch.data_ptr(), x.data_ptr(), B, H, W, D, _stream()), "patch_embed")
+    pxr = px.to(torch.bfloat16).float()                      # the kernel's A operand is bf16
+    tok = F.conv2d(pxr, w.float(), cb, stride=16).flatten(2).transpose(1, 2)
+    ref = torch.cat([cls.expand(B, 1, D), tok], dim=1) + pos
+    torch.testing.assert_close(x, ref, rtol=1e-4, atol=2e-3)
+
+
+# ------------------------------------------------------------------------------ attention
+def _attn_ref(qkv, B, N, heads, bias):
+    D = heads * 64
+    q, k, v = qkv.float().reshape(B, N, 3, heads, 64).permute(2, 0, 3, 1, 4)
+    s = q @ k.transpose(-1, -2) / 8.0
+    if bias is not None:
+        s = s + bias
+    return (torch.softmax(s, dim=-1) @ v).transpose(1, 2).reshape(B * N, D)
+
+
+def _dense_bias(table_t, Gh, Gw):
+    """[heads, T] -> [1, heads, N, N] by the index rule of HF:522-544 (torch statement)."""
+    T = table_t.shape[1]
+    ys, xs = torch.meshgrid(torch.arange(Gh), torch.arange(Gw), indexing="ij")
+    ys, xs = ys.flatten(), xs.flatten()
+    idx = torch.zeros(Gh * Gw + 1, Gh * Gw + 1, dtype=torch.long)
+    idx[1:, 1:] = (ys[:, None] - ys[None, :] + Gh - 1) * (2 * Gw - 1) + (xs[:, None] - xs[None, :] + Gw - 1)
+    idx[0, :] = T - 3
+    idx[:, 0] = T - 2
+    idx[0, 0] = T - 1
+    return table_t[:, idx.to(table_t.device)].unsqueeze(0)
+
+
+@pytest.mark.parametrize("with_bias", [False, True])
+@pytest.mark.parametrize("B,heads,Gh,Gw", [(2, 2, 4, 4), (3, 12, 14, 14), (2, 4, 14, 20), (1, 3, 32, 32), (2, 2, 5, 7)])
+def test_attention(lib, B, heads, Gh, Gw, with_bias):
+    N, D = Gh * Gw + 1, heads * 64
+    g = torch.Generator(device="cuda").manual_seed(N + heads)
+    qkv = (torch.randn(B * N, 3 * D, device="cuda", generator=g) * 1.5).to(torch.bfloat16)
+    table = None
+    bias = None
+    if with_bias:
+        T = (2 * Gh - 1) * (2 * Gw - 1) + 3
+        table = torch.randn(heads, T, device="cuda", generator=g)
+        bias = _dense_bias(table, Gh, Gw)
+    ctx = torch.full((B * N, D), float("nan"), device="cuda", dtype=torch.bfloat16)
+    _lib.check(lib.ldit_attention(qkv.data_ptr(), ctx.data_ptr(), None if table is None else table.data_ptr(),
+                                  B, N, heads, Gh, Gw, _stream()), "attention")
+    ref = _attn_ref(qkv, B, N, heads, bias)
+    assert torch.isfinite(ctx.float()).all()
+    assert _rel_fro(ctx.float(), ref) < 8e-3
+    torch.testing.assert_close(ctx.float(), ref, rtol=2e-2, atol=2e-2)
+
+
+# ----------------------------------------------------------------------------------- taps
+@pytest.mark.parametrize("scale", [4.0, 2.0, 1.0, 0.5])
+@pytest.mark.parametrize("B,Gh,Gw,D", [(2, 4, 4, 128), (2, 5, 7, 128), (3, 14, 14, 768), (1, 20, 14, 1024)])
+def test_resample_taps(lib, B, Gh, Gw, D, scale):
+    g = torch.Generator(device="cuda").manual_seed(Gh * Gw)
+    x = torch.randn(B, Gh * Gw + 1, D, device="cuda", generator=g)
+    oh, ow = int(math.floor(Gh * scale)), int(math.floor(Gw * scale))
+    out = torch.full((B, oh, ow, D), float("nan"), device="cuda", dtype=torch.bfloat16)
+    _lib.check(lib.ldit_resample_taps(x.data_ptr(), out.data_ptr(), B, Gh, Gw, D, scale, _stream()), "taps")
+    t = x[:, 1:, :].permute(0, 2, 1).reshape(B, D, Gh, Gw)
+    ref = t if scale == 1.0 else F.interpolate(t, scale_factor=scale, mode="bilinear", align_corners=False)
+    got = out.permute(0, 3, 1, 2).float()
+    assert got.shape == ref.shape
+    torch.testing.assert_close(got, ref, rtol=2 ** -8, atol=1e-6)
+    # bit-exact against the bf16 rounding of the fp32 reference for the exact-weight scales
+    assert (got == ref.to(torch.bfloat16).float()).float().mean() > 0.999

@@ -1,0 +1,141 @@
+"""GPU parity proper: the drop-in ``DiTBackbone`` (CUDA path through the C ABI) against
+
+* the committed fixtures produced by the reference's own ``DiTBackbone`` (tests/golden/),
+* the CPU oracle (oracle/dit_oracle.py) on the same seeded inputs,
+* size-independent properties at BASELINE.json's full sizes.
+
+Stated tolerance (bf16 tensor-core math with fp32 accumulation and an fp32 residual stream,
+against the fp32 reference; calibration in SURVEY.md section 8c): per tap
+relative-Frobenius error <= 1e-2 and max-abs error <= 5e-2 of the tap's abs-max; and the
+error must not exceed 2x what the same HF module gives in plain torch bf16 on the GPU.
+"""
+import pytest
+import torch
+
+from conftest import build_case, compare_to_golden, golden_index
+from layoutdit_b200 import DiTBackbone
+from layoutdit_b200.config import dit_base
+from layoutdit_b200.synth import make_state_dict, synthetic_pages
+from oracle import dit_oracle, hf_reference
+
+pytestmark = pytest.mark.gpu
+
+REL_FRO = 1e-2
+MAX_ABS_REL = 5e-2
+ALL = sorted(golden_index().keys())
+
+
+def _backbone(cfg, sd, **kw):
+    return DiTBackbone(pretrained=False, config=cfg, state_dict=sd, **kw).cuda().eval()
+
+
+def _rel_fro(got, ref):
+    return float((got.double().cpu() - ref.double().cpu()).norm() / ref.double().cpu().norm().clamp_min(1e-30))
+
+
+@pytest.mark.parametrize("name", ALL)
+def test_matches_reference_fixture(cuda_device, name):
+    cfg, sd, x, gold, meta = build_case(name)
+    feats = _backbone(cfg, sd)(x.cuda())
+    assert list(feats.keys()) == ["p2", "p3", "p4", "p5"]
+    errs = compare_to_golden(feats, gold, meta, rel_fro=REL_FRO, max_abs_rel=MAX_ABS_REL)
+    print(name, {k: (f"{e:.2e}", f"{m:.2e}") for k, (e, m) in errs.items()})
+
+
+@pytest.mark.parametrize("name", ["tiny_abs_native", "tiny_relpos", "base_224_w1"])
+def test_not_worse_than_torch_bf16_eager(cuda_device, name):
+    """Scale-free bar: error vs the fp32 oracle <= 2x the error of the HF module in torch bf16."""
+    cfg, sd, x, _, _ = build_case(name)
+    ref = dit_oracle.dit_backbone_forward(sd, cfg.to_dict(), x)
+    ours = _backbone(cfg, sd)(x.cuda())
+    hf = hf_reference.build(cfg.to_dict(), sd).cuda().to(torch.bfloat16)
+    with torch.no_grad():
+        theirs = hf(x.cuda().to(torch.bfloat16))
+    for k in ref:
+        e_ours, e_hf = _rel_fro(ours[k].float(), ref[k]), _rel_fro(theirs[k].float(), ref[k])
+        print(name, k, f"ours {e_ours:.2e}  torch-bf16 {e_hf:.2e}")
+        assert e_ours <= max(2.0 * e_hf, 2e-3)
+
+
+@pytest.mark.parametrize("dtype", [torch.float16, torch.bfloat16])
+def test_input_dtypes(cuda_device, dtype):
+    cfg, sd, x, gold, meta = build_case("tiny_abs_native")
+    feats = _backbone(cfg, sd)(x.cuda().to(dtype))
+    compare_to_golden(feats, gold, meta, rel_fro=1.5e-2, max_abs_rel=6e-2)
+
+
+def test_graph_replay_equals_eager_and_is_deterministic(cuda_device):
+    cfg, sd, x, _, _ = build_case("tiny_abs_interp")
+    xe = x.cuda()
+    eager = _backbone(cfg, sd)
+    a = {k: v.clone() for k, v in eager(xe).items()}
+    b = eager(xe)
+    graphed = _backbone(cfg, sd, use_cuda_graph=True)
+    c = {k: v.clone() for k, v in graphed(xe).items()}
+    d = graphed(xe)
+    for k in a:
+        assert torch.equal(a[k], b[k]) and torch.equal(a[k], c[k]) and torch.equal(a[k], d[k])
+
+
+def test_weight_update_is_picked_up(cuda_device):
+    cfg, sd, x, _, _ = build_case("tiny_w0")
+    m = _backbone(cfg, sd)
+    a = {k: v.clone() for k, v in m(x.cuda()).items()}
+    with torch.no_grad():
+        m.dit.encoder.layer[0].output.dense.bias.add_(0.5)
+    b = m(x.cuda())
+    assert not torch.equal(a["p5"], b["p5"])
+    sd2 = {k: v.clone() for k, v in sd.items()}
+    sd2["encoder.layer.0.output.dense.bias"] = sd2["encoder.layer.0.output.dense.bias"] + 0.5
+    ref = dit_oracle.dit_backbone_forward(sd2, cfg.to_dict(), x)
+    assert _rel_fro(b["p5"].float(), ref["p5"]) < REL_FRO
+
+
+def test_ragged_and_channel_errors(cuda_device):
+    cfg, sd, x, _, _ = build_case("tiny_abs_native")
+    m = _backbone(cfg, sd)
+    with pytest.raises(ValueError):
+        m(torch.zeros(1, 4, 64, 64, device="cuda"))
+    xr = synthetic_pages(1, 70, 83, 5)          # not multiples of 16: conv floors (HF:218), R:dit_backbone.py:45
+    got = m(xr.cuda())
+    ref = dit_oracle.dit_backbone_forward(sd, cfg.to_dict(), xr)
+    for k in ref:
+        assert got[k].shape == ref[k].shape
+        assert _rel_fro(got[k].float(), ref[k]) < REL_FRO
+
+
+def test_full_size_c2_properties(cuda_device):
+    """BASELINE config 2 (DiT-base, batch 64, 224x224): batch independence, oracle agreement on
+    two images of the batch, finiteness, shapes and strides."""
+    cfg = dit_base()
+    sd = make_state_dict(cfg, 1, True)
+    x = synthetic_pages(64, 224, 224, 1234)
+    m = _backbone(cfg, sd)
+    full = m(x.cuda())
+    shapes = {"p2": (64, 768, 56, 56), "p3": (64, 768, 28, 28), "p4": (64, 768, 14, 14), "p5": (64, 768, 7, 7)}
+    for k, v in full.items():
+        assert tuple(v.shape) == shapes[k] and v.dtype == torch.bfloat16
+        assert v.stride(1) == 1                      # channels-last, like the reference's interpolate outputs
+        assert torch.isfinite(v.float()).all()
+    solo = m(x[37:38].cuda())
+    for k in full:                                    # no cross-image coupling anywhere on the path
+        assert torch.equal(full[k][37:38], solo[k])
+    ref = dit_oracle.dit_backbone_forward(sd, cfg.to_dict(), x[[0, 63]])
+    for k in ref:
+        got = full[k][[0, 63]].float()
+        assert _rel_fro(got, ref[k]) < REL_FRO
+        assert float((got.cpu() - ref[k]).abs().max() / ref[k].abs().max()) < MAX_ABS_REL
+
+
+def test_full_size_c3_512(cuda_device):
+    """BASELINE config 3 geometry (512x512, N=1025, interpolated position table), 2 images vs oracle."""
+    cfg = dit_base()
+    sd = make_state_dict(cfg, 1, True)
+    x = synthetic_pages(2, 512, 512, 99)
+    got = _backbone(cfg, sd)(x.cuda())
+    ref = dit_oracle.dit_backbone_forward(sd, cfg.to_dict(), x)
+    for k in ref:
+        assert got[k].shape == ref[k].shape
+        e = _rel_fro(got[k].float(), ref[k])
+        print("c3", k, f"{e:.2e}")
+        assert e < REL_FRO
