@@ -64,7 +64,7 @@ class _Geometry:
     M: int
     x: torch.Tensor          # f32 [M, D] residual stream
     a: torch.Tensor          # bf16 [M, D] LayerNorm output / attention context
-    big: torch.Tensor        # bf16 [M, max(3D, I)] QKV, MLP hidden and im2col scratch (disjoint lifetimes)
+    big: torch.Tensor        # bf16 [M, max(3D, I, 768)] QKV, MLP hidden and im2col scratch (disjoint lifetimes)
     pos_bias: torch.Tensor   # f32 [P, D]
     cls_pos: torch.Tensor    # f32 [D]
     bias_tables: list        # per layer: f32 [heads, T] or None
@@ -176,7 +176,7 @@ class Engine:
             for L in self._layers:
                 t = None if L.rel_table is None else self._resized_table(L.rel_table, Gh, Gw)
                 tables.append(t if t is not None else shared)
-        wide = max(3 * D, I)
+        wide = max(3 * D, I, 768)  # 768 = im2col row (3*16*16): the patch-embed scratch lives here too
         geo = _Geometry(B=B, H=H, W=W, Gh=Gh, Gw=Gw, N=N, M=M,
                         x=torch.empty(M, D, device=dev, dtype=torch.float32),
                         a=torch.empty(M, D, device=dev, dtype=torch.bfloat16),
@@ -194,37 +194,48 @@ class Engine:
             outs.append(torch.empty(geo.B, oh, ow, D, device=self.device, dtype=torch.bfloat16))
         return outs
 
-    def _enqueue(self, geo: _Geometry, x: torch.Tensor, outs, stream: int):
-        """Enqueue the whole forward on ``stream``.  Returns the number of kernels launched."""
-        lib, cfg, chk = self.lib, self.cfg, _lib.check
+    def _plan(self, geo: _Geometry, x: torch.Tensor, outs, stream: int):
+        """The forward as an ordered list of (name, C-ABI function, args): one entry per
+        library call, in stream order."""
+        lib, cfg = self.lib, self.cfg
         D, I, heads = cfg.hidden_size, cfg.intermediate_size, cfg.num_attention_heads
         M, N, B = geo.M, geo.N, geo.B
         xr, a, big = geo.x.data_ptr(), geo.a.data_ptr(), geo.big.data_ptr()
         eps = float(cfg.layer_norm_eps)
-        n0 = lib.ldit_launch_count()
-        chk(lib.ldit_patch_embed(x.data_ptr(), _DTYPE_CODE[x.dtype], self.w_patch.data_ptr(), geo.pos_bias.data_ptr(),
-                                 geo.cls_pos.data_ptr(), big, xr, B, geo.H, geo.W, D, stream), "ldit_patch_embed")
+        plan = [("ldit_patch_embed", lib.ldit_patch_embed,
+                 (x.data_ptr(), _DTYPE_CODE[x.dtype], self.w_patch.data_ptr(), geo.pos_bias.data_ptr(),
+                  geo.cls_pos.data_ptr(), big, xr, B, geo.H, geo.W, D, stream))]
 
         def emit_tap(layer_no):
             # hidden_states[layer_no] is the residual stream right now (HF:628-630, 654-655)
-            for idx, slot in zip(self.tap_idx, range(4)):
+            for slot, idx in enumerate(self.tap_idx):
                 if idx == layer_no:
-                    chk(lib.ldit_resample_taps(xr, outs[slot].data_ptr(), B, geo.Gh, geo.Gw, D, TAP_SCALES[slot], stream),
-                        "ldit_resample_taps")
+                    plan.append(("ldit_resample_taps", lib.ldit_resample_taps,
+                                 (xr, outs[slot].data_ptr(), B, geo.Gh, geo.Gw, D, TAP_SCALES[slot], stream)))
 
         emit_tap(0)
         for i, L in enumerate(self._layers):
-            chk(lib.ldit_layernorm(xr, L.ln1_w.data_ptr(), L.ln1_b.data_ptr(), a, M, D, eps, stream), "ldit_layernorm")
-            chk(lib.ldit_gemm_bias(a, L.wqkv.data_ptr(), L.bqkv.data_ptr(), big, M, 3 * D, D, stream), "ldit_gemm_bias")
-            chk(lib.ldit_attention(big, a, _ptr(geo.bias_tables[i]), B, N, heads, geo.Gh, geo.Gw, stream), "ldit_attention")
-            chk(lib.ldit_gemm_bias_scale_residual(a, L.wo.data_ptr(), L.bo.data_ptr(), _ptr(L.lam1), xr, M, D, D, stream),
-                "ldit_gemm_bias_scale_residual")
-            chk(lib.ldit_layernorm(xr, L.ln2_w.data_ptr(), L.ln2_b.data_ptr(), a, M, D, eps, stream), "ldit_layernorm")
-            chk(lib.ldit_gemm_bias_gelu(a, L.w1.data_ptr(), L.b1.data_ptr(), big, M, I, D, stream), "ldit_gemm_bias_gelu")
-            chk(lib.ldit_gemm_bias_scale_residual(big, L.w2.data_ptr(), L.b2.data_ptr(), _ptr(L.lam2), xr, M, D, I, stream),
-                "ldit_gemm_bias_scale_residual")
+            plan += [
+                ("ldit_layernorm", lib.ldit_layernorm, (xr, L.ln1_w.data_ptr(), L.ln1_b.data_ptr(), a, M, D, eps, stream)),
+                ("ldit_gemm_bias", lib.ldit_gemm_bias, (a, L.wqkv.data_ptr(), L.bqkv.data_ptr(), big, M, 3 * D, D, stream)),
+                ("ldit_attention", lib.ldit_attention,
+                 (big, a, _ptr(geo.bias_tables[i]), B, N, heads, geo.Gh, geo.Gw, stream)),
+                ("ldit_gemm_bias_scale_residual", lib.ldit_gemm_bias_scale_residual,
+                 (a, L.wo.data_ptr(), L.bo.data_ptr(), _ptr(L.lam1), xr, M, D, D, stream)),
+                ("ldit_layernorm", lib.ldit_layernorm, (xr, L.ln2_w.data_ptr(), L.ln2_b.data_ptr(), a, M, D, eps, stream)),
+                ("ldit_gemm_bias_gelu", lib.ldit_gemm_bias_gelu, (a, L.w1.data_ptr(), L.b1.data_ptr(), big, M, I, D, stream)),
+                ("ldit_gemm_bias_scale_residual", lib.ldit_gemm_bias_scale_residual,
+                 (big, L.w2.data_ptr(), L.b2.data_ptr(), _ptr(L.lam2), xr, M, D, I, stream)),
+            ]
             emit_tap(i + 1)
-        return int(lib.ldit_launch_count() - n0)
+        return plan
+
+    def _enqueue(self, geo: _Geometry, x: torch.Tensor, outs, stream: int, limit: int | None = None):
+        """Enqueue the whole forward on ``stream``.  Returns the number of kernels launched."""
+        n0 = self.lib.ldit_launch_count()
+        for name, fn, args in self._plan(geo, x, outs, stream)[:limit]:
+            _lib.check(fn(*args), name)
+        return int(self.lib.ldit_launch_count() - n0)
 
     @staticmethod
     def _as_feats(outs):
