@@ -91,6 +91,9 @@ size_t ldit_patch_embed_scratch_bytes(int B, int H, int W);
 /* Tuning knob: force the GEMM tile width (128, 192 or 256); 0 restores the automatic choice
  * (fewest persistent-schedule rounds x tile width).  Also settable with LDIT_GEMM_BN. */
 void ldit_set_gemm_tile_n(int bn);
+/* Tuning knob: 2 (default) = CTA pairs with tcgen05.mma.cta_group::2 (256 x BN tile per pair);
+ * 1 = independent CTAs (128 x BN tile).  Also settable with LDIT_GEMM_CTAS. */
+void ldit_set_gemm_cta_pair(int ctas);
 
 /* Number of kernels the library has enqueued since load / last reset (for gpu_launches). */
 unsigned long long ldit_launch_count(void);

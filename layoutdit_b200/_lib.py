@@ -24,6 +24,7 @@ SIGNATURES = {
     "ldit_resample_taps": (_i, [_vp, _vp, _i, _i, _i, _i, _f, _vp]),
     "ldit_patch_embed_scratch_bytes": (_c.c_size_t, [_i, _i, _i]),
     "ldit_set_gemm_tile_n": (None, [_i]),
+    "ldit_set_gemm_cta_pair": (None, [_i]),
     "ldit_launch_count": (_c.c_ulonglong, []),
     "ldit_reset_launch_count": (None, []),
 }

@@ -3,13 +3,23 @@
 // fp32 accumulation in TMEM, fused epilogues.  Both operands are K-major, so the natural
 // PyTorch layouts are consumed as they are, with no transposes anywhere.
 //
-// CTA = 128 + 256 threads, one CTA per SM, static round-robin tile scheduler:
-//   warp 0    TMA producer   (one lane): cp.async.bulk.tensor A/B tiles -> 128B-swizzled smem ring
-//   warp 1    MMA issuer     (one lane): tcgen05.mma 128 x BN x 16, accumulators double-buffered in TMEM
+// CTAS = 2 (default): a CTA pair on one TPC computes a 256 x BN tile with
+// tcgen05.mma.cta_group::2 -- each CTA stages its own 128 rows of A and HALF of the BN rows of
+// W, so the pair pulls (256 + BN) x K operand bytes from L2 for 256 x BN x K MACs (1.5x fewer
+// bytes per FLOP than two independent 128 x BN tiles; this GEMM is L2->SM-bandwidth-bound
+// otherwise) and each SM's shared-memory operand traffic halves.  CTAS = 1 is the single-CTA
+// 128 x BN variant of the same code.
+//
+// CTA = 128 + 256 threads, one CTA per SM, static round-robin tile scheduler over clusters:
+//   warp 0    TMA producer   (one lane, both CTAs): A/B tiles -> 128B-swizzled smem ring; all
+//             completion bytes are credited to the LEADER CTA's "full" barrier
+//   warp 1    MMA issuer     (one lane, leader CTA only): tcgen05.mma, accumulators
+//             double-buffered in TMEM; tcgen05.commit multicasts "slot free" / "accumulator ready"
+//             to both CTAs
 //   warp 2    TMEM allocator
-//   warps 4-11 epilogue: tcgen05.ld -> registers -> bias / erf-GELU / layer-scale + residual -> global
-// Pipelines: smem full/empty mbarriers (TMA <-> MMA) and TMEM full/empty mbarriers
-// (MMA <-> epilogue), so the epilogue of tile i overlaps the main loop of tile i+1.
+//   warps 4-11 epilogue (both CTAs, own 128 rows): tcgen05.ld -> registers -> bias / erf-GELU /
+//             layer-scale + residual -> swizzled smem staging -> TMA store (the residual tile
+//             arrives by TMA load into the same staging buffer, prefetched one chunk ahead)
 //
 // Replaces the cuBLAS calls behind nn.Linear at HF:324-338 (QKV), HF:383 (+HF:488-492),
 // HF:429-430 and HF:442 (+HF:500-504), and the conv at HF:218 (as an im2col GEMM).
@@ -31,48 +41,87 @@ struct GemmArgs {
   int P;               // EPI_PATCH: patches per image; GEMM row b*P+p -> token row b*(P+1)+1+p
   const float* posb;   // EPI_PATCH: [P, N] fp32 = position rows 1..P + conv bias
   int num_m_blocks, num_n_blocks;
+  int dbg;             // experiments only (LDIT_GEMM_DBG): bit 0 = epilogue drains TMEM but stores nothing
 };
 
-constexpr int kBM = 128;
-constexpr int kBK = 64;  // 64 bf16 = one 128-byte swizzle row
+constexpr int kBM = 128;  // rows per CTA
+constexpr int kBK = 64;   // 64 bf16 = one 128-byte swizzle row
 constexpr int kUmmaK = 16;
 constexpr int kGemmEpiWarps = 8;
 constexpr int kGemmThreads = 128 + kGemmEpiWarps * 32;
 constexpr int kAccStride = 256;  // TMEM columns between the two accumulator stages
 constexpr int kTmemCols = 512;
+constexpr int kMaxSmem = 232448;  // 227 KB opt-in limit per CTA
 
-template <int BN>
+template <int BN, int EPI, int CTAS>
 struct GemmCfg {
   static_assert(BN == 128 || BN == 192 || BN == 256, "BN");
+  static_assert(CTAS == 1 || CTAS == 2, "CTAS");
+  static constexpr bool OUT_F32 = (EPI == EPI_SCALE_RESID || EPI == EPI_PATCH);
+  static constexpr bool STAGED = (EPI != EPI_PATCH);  // patch rows are re-indexed per image: direct stores
+  static constexpr int TILE_M = kBM * CTAS;
   static constexpr int A_BYTES = kBM * kBK * 2;
-  static constexpr int B_BYTES = BN * kBK * 2;
+  static constexpr int B_ROWS = BN / CTAS;            // rows of W staged by each CTA
+  static constexpr int B_BYTES = B_ROWS * kBK * 2;
   static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
-  static constexpr int STAGES = BN == 256 ? 4 : (BN == 192 ? 5 : 6);
-  static constexpr int BAR_BYTES = 256;
-  static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + BAR_BYTES + 1024;  // + alignment slack
+  // epilogue staging: per warp two buffers of 32 rows x 32 columns
+  static constexpr int CHUNK_BYTES = 32 * 32 * (OUT_F32 ? 4 : 2);
+  static constexpr int STAGING_BYTES = STAGED ? kGemmEpiWarps * 2 * CHUNK_BYTES : 0;
+  static constexpr int BAR_BYTES = 512;
+  static constexpr int STAGES_FIT = (kMaxSmem - 1024 - BAR_BYTES - STAGING_BYTES) / STAGE_BYTES;
+  static constexpr int STAGES = STAGES_FIT > 8 ? 8 : STAGES_FIT;
+  static_assert(STAGES >= 3, "pipeline too shallow");
+  static_assert(A_BYTES % 1024 == 0 && B_BYTES % 1024 == 0, "swizzle-128B tiles must stay 1 KB aligned");
+  static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + STAGING_BYTES + BAR_BYTES + 1024;  // + alignment slack
 };
 
-template <int BN, int EPI>
+// exact-erf GELU (HF:430, ACT2FN["gelu"]) evaluated as x * Phi(x) with
+// Phi(x) = 0.5 erfc(-x / sqrt 2) from the Abramowitz-Stegun 7.1.26 rational form (|erf error|
+// < 1.5e-7, i.e. far below the bf16 rounding of the result): ~13 FMA-pipe ops + 2 MUFU, so
+// the epilogue stays under the MMA time of its tile -- erff() costs ~2x that.
+__device__ __forceinline__ float gelu_erf_fast(float x) {
+  const float z = fabsf(x) * 0.70710678118654752f;
+  float t;
+  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(t) : "f"(fmaf(0.3275911f, z, 1.0f)));
+  float p = fmaf(t, 0.5f * 1.061405429f, 0.5f * -1.453152027f);
+  p = fmaf(p, t, 0.5f * 1.421413741f);
+  p = fmaf(p, t, 0.5f * -0.284496736f);
+  p = fmaf(p, t, 0.5f * 0.254829592f);
+  p *= t;
+  float e;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e) : "f"(z * z * -1.4426950408889634f));
+  const float h = p * e;  // 0.5 * erfc(|x| / sqrt 2)
+  return x * (x >= 0.f ? 1.0f - h : h);
+}
+
+template <int BN, int EPI, int CTAS>
 __global__ void __launch_bounds__(kGemmThreads, 1)
-gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const GemmArgs g) {
-  using Cfg = GemmCfg<BN>;
+gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
+                    const __grid_constant__ CUtensorMap tmC, const GemmArgs g) {
+  using Cfg = GemmCfg<BN, EPI, CTAS>;
   constexpr int S = Cfg::STAGES;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   uint8_t* sA = smem;
   uint8_t* sB = smem + S * Cfg::A_BYTES;
-  uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + S * Cfg::STAGE_BYTES);
+  uint8_t* sStage = smem + S * Cfg::STAGE_BYTES;  // 1 KB aligned: every tile size is a multiple of 1 KB
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(sStage + Cfg::STAGING_BYTES);
   uint64_t* empty_bar = full_bar + S;
   uint64_t* tfull_bar = empty_bar + S;
   uint64_t* tempty_bar = tfull_bar + 2;
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty_bar + 2);
+  uint64_t* resid_bar = tempty_bar + 2;  // [kGemmEpiWarps][2]
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(resid_bar + 2 * kGemmEpiWarps);
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
+  const uint32_t rank = CTAS == 2 ? cluster_ctarank() : 0u;  // 0 = leader of the pair
+  const int cluster_id = blockIdx.x / CTAS;
+  const int num_clusters = gridDim.x / CTAS;
 
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&tmA);
     tma_prefetch_desc(&tmB);
+    if constexpr (Cfg::STAGED) tma_prefetch_desc(&tmC);
   }
   if (warp == 1 && lane == 0) {
     for (int i = 0; i < S; ++i) {
@@ -81,17 +130,23 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
     }
     for (int i = 0; i < 2; ++i) {
       mbar_init(&tfull_bar[i], 1);
-      mbar_init(&tempty_bar[i], kGemmEpiWarps);
+      mbar_init(&tempty_bar[i], kGemmEpiWarps * CTAS);
     }
+    for (int i = 0; i < 2 * kGemmEpiWarps; ++i) mbar_init(&resid_bar[i], 1);
     fence_barrier_init();
     fence_proxy_async_smem();
   }
   if (warp == 2) {
-    tmem_alloc(tmem_slot, kTmemCols);
-    tmem_relinquish();
+    if constexpr (CTAS == 2) {
+      tmem_alloc_cg2(tmem_slot, kTmemCols);
+      tmem_relinquish_cg2();
+    } else {
+      tmem_alloc(tmem_slot, kTmemCols);
+      tmem_relinquish();
+    }
   }
   tcgen05_fence_before();
-  __syncthreads();
+  if constexpr (CTAS == 2) cluster_sync_all(); else __syncthreads();
   tcgen05_fence_after();
   const uint32_t tmem_base = *tmem_slot;
 
@@ -102,26 +157,33 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
     if (lane == 0) {
       int stage = 0;
       uint32_t phase = 0;
-      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
-        const int m0 = (tile / g.num_n_blocks) * kBM;
-        const int n0 = (tile % g.num_n_blocks) * BN;
+      for (int tile = cluster_id; tile < num_tiles; tile += num_clusters) {
+        const int m0 = (tile / g.num_n_blocks) * Cfg::TILE_M + static_cast<int>(rank) * kBM;
+        const int n0 = (tile % g.num_n_blocks) * BN + static_cast<int>(rank) * Cfg::B_ROWS;
         for (int kb = 0; kb < nkb; ++kb) {
           mbar_wait(&empty_bar[stage], phase ^ 1);
-          mbar_arrive_expect_tx(&full_bar[stage], Cfg::STAGE_BYTES);
-          tma_load_2d(sA + stage * Cfg::A_BYTES, &tmA, &full_bar[stage], kb * kBK, m0);
-          tma_load_2d(sB + stage * Cfg::B_BYTES, &tmB, &full_bar[stage], kb * kBK, n0);
+          if constexpr (CTAS == 2) {
+            if (rank == 0) mbar_arrive_expect_tx(&full_bar[stage], Cfg::STAGE_BYTES * 2);
+            const uint32_t leader_full = mapa_shared(smem_u32(&full_bar[stage]), 0);
+            tma_load_2d_cg2(sA + stage * Cfg::A_BYTES, &tmA, leader_full, kb * kBK, m0);
+            tma_load_2d_cg2(sB + stage * Cfg::B_BYTES, &tmB, leader_full, kb * kBK, n0);
+          } else {
+            mbar_arrive_expect_tx(&full_bar[stage], Cfg::STAGE_BYTES);
+            tma_load_2d(sA + stage * Cfg::A_BYTES, &tmA, &full_bar[stage], kb * kBK, m0);
+            tma_load_2d(sB + stage * Cfg::B_BYTES, &tmB, &full_bar[stage], kb * kBK, n0);
+          }
           if (++stage == S) { stage = 0; phase ^= 1; }
         }
       }
     }
   } else if (warp == 1) {
-    if (lane == 0) {
-      constexpr uint32_t idesc = umma_idesc_bf16(kBM, BN, 0, 0);
+    if (lane == 0 && rank == 0) {
+      constexpr uint32_t idesc = umma_idesc_bf16(Cfg::TILE_M, BN, 0, 0);
       int stage = 0;
       uint32_t phase = 0;
       int acc = 0;
       uint32_t acc_phase = 0;
-      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+      for (int tile = cluster_id; tile < num_tiles; tile += num_clusters) {
         mbar_wait(&tempty_bar[acc], acc_phase ^ 1);
         tcgen05_fence_after();
         const uint32_t d_tmem = tmem_base + acc * kAccStride;
@@ -132,112 +194,186 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
           const uint64_t bdesc = umma_desc_kmajor_sw128(smem_u32(sB + stage * Cfg::B_BYTES));
 #pragma unroll
           for (int k = 0; k < kBK / kUmmaK; ++k) {
-            umma_bf16_ss(d_tmem, adesc + 2 * k, bdesc + 2 * k, idesc, (kb | k) != 0);
+            if constexpr (CTAS == 2) umma_bf16_ss_cg2(d_tmem, adesc + 2 * k, bdesc + 2 * k, idesc, (kb | k) != 0);
+            else umma_bf16_ss(d_tmem, adesc + 2 * k, bdesc + 2 * k, idesc, (kb | k) != 0);
           }
-          tcgen05_commit(&empty_bar[stage]);  // smem slot reusable once these MMAs have read it
+          // smem slot reusable (in both CTAs) once these MMAs have read it
+          if constexpr (CTAS == 2) tcgen05_commit_cg2(&empty_bar[stage], 3); else tcgen05_commit(&empty_bar[stage]);
           if (++stage == S) { stage = 0; phase ^= 1; }
         }
-        tcgen05_commit(&tfull_bar[acc]);  // accumulator complete
+        // accumulator complete (both CTAs' epilogues)
+        if constexpr (CTAS == 2) tcgen05_commit_cg2(&tfull_bar[acc], 3); else tcgen05_commit(&tfull_bar[acc]);
         acc ^= 1;
         if (acc == 0) acc_phase ^= 1;
       }
     }
   } else if (warp >= 4) {
-    const int quarter = warp & 3;              // TMEM lane quarter this warp may access
-    const int half = (warp - 4) >> 2;          // which half of the BN columns
+    const int ew = warp - 4;
+    const int quarter = warp & 3;   // TMEM lane quarter this warp may access
+    const int half = ew >> 2;       // which half of the BN columns
     constexpr int kChunks = BN / 2 / 32;
     int acc = 0;
     uint32_t acc_phase = 0;
-    for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
-      const int m0 = (tile / g.num_n_blocks) * kBM;
-      const int n0 = (tile % g.num_n_blocks) * BN;
-      const int row = m0 + quarter * 32 + lane;
-      const bool row_ok = row < g.M;
-      mbar_wait(&tfull_bar[acc], acc_phase);
-      tcgen05_fence_after();
-      const uint32_t taddr = tmem_base + acc * kAccStride + half * (BN / 2) + (static_cast<uint32_t>(quarter * 32) << 16);
+    const int row_in_tile = static_cast<int>(rank) * kBM + quarter * 32;
 
-      size_t orow = static_cast<size_t>(row);
-      const float* posb_row = nullptr;
-      if constexpr (EPI == EPI_PATCH) {
-        const int b = row / g.P, p = row - b * g.P;
-        orow = static_cast<size_t>(b) * (g.P + 1) + 1 + p;
-        posb_row = g.posb + static_cast<size_t>(p) * g.N;
+    auto release_accumulator = [&](int a) {
+      // all TMEM reads of this accumulator are done: hand it back to the (leader's) MMA warp
+      tcgen05_fence_before();
+      __syncwarp();
+      if (lane == 0) {
+        if constexpr (CTAS == 2) mbar_arrive_cluster(mapa_shared(smem_u32(&tempty_bar[a]), 0));
+        else mbar_arrive(&tempty_bar[a]);
       }
-#pragma unroll 1
-      for (int c = 0; c < kChunks; ++c) {
-        uint32_t r[32];
-        tmem_ld_32x32b_x32(taddr + c * 32, r);
-        tcgen05_wait_ld();
-        if (c == kChunks - 1) {
-          // all TMEM reads of this accumulator are done: hand it back to the MMA warp
-          tcgen05_fence_before();
-          __syncwarp();
-          if (lane == 0) mbar_arrive(&tempty_bar[acc]);
+    };
+
+    if constexpr (Cfg::STAGED) {
+      uint8_t* my_stage = sStage + ew * 2 * Cfg::CHUNK_BYTES;
+      uint64_t* my_bar = resid_bar + ew * 2;
+      uint32_t gc = 0;  // chunks processed by this warp so far: buffer = gc & 1, residual phase = (gc >> 1) & 1
+      if constexpr (EPI == EPI_SCALE_RESID) {
+        if (lane == 0 && cluster_id < num_tiles) {  // residual of the very first chunk
+          const int tile = cluster_id;
+          mbar_arrive_expect_tx(&my_bar[0], Cfg::CHUNK_BYTES);
+          tma_load_2d(my_stage, &tmC, &my_bar[0], (tile % g.num_n_blocks) * BN + half * (BN / 2),
+                      (tile / g.num_n_blocks) * Cfg::TILE_M + row_in_tile);
         }
-        const int col = n0 + half * (BN / 2) + c * 32;
-        if (row_ok && col < g.N) {
-#pragma unroll
-          for (int j = 0; j < 32; j += 8) {
-            float v[8];
-#pragma unroll
-            for (int e = 0; e < 8; ++e) v[e] = __uint_as_float(r[j + e]);
-            if (g.bias != nullptr) {
-              const float4 b0 = __ldg(reinterpret_cast<const float4*>(g.bias + col + j));
-              const float4 b1 = __ldg(reinterpret_cast<const float4*>(g.bias + col + j + 4));
-              v[0] += b0.x; v[1] += b0.y; v[2] += b0.z; v[3] += b0.w;
-              v[4] += b1.x; v[5] += b1.y; v[6] += b1.z; v[7] += b1.w;
+      }
+      for (int tile = cluster_id; tile < num_tiles; tile += num_clusters) {
+        const int row0 = (tile / g.num_n_blocks) * Cfg::TILE_M + row_in_tile;
+        const int col0 = (tile % g.num_n_blocks) * BN + half * (BN / 2);
+        mbar_wait(&tfull_bar[acc], acc_phase);
+        tcgen05_fence_after();
+        const uint32_t taddr = tmem_base + acc * kAccStride + half * (BN / 2) + (static_cast<uint32_t>(quarter * 32) << 16);
+#pragma unroll 1
+        for (int c = 0; c < kChunks; ++c, ++gc) {
+          uint8_t* buf = my_stage + (gc & 1) * Cfg::CHUNK_BYTES;
+          uint8_t* nbuf = my_stage + ((gc + 1) & 1) * Cfg::CHUNK_BYTES;
+          if (lane == 0) {
+            if constexpr (EPI == EPI_SCALE_RESID) {
+              // the other buffer was last read by the store of chunk gc-1: it must have drained
+              // before the next residual chunk is prefetched into it
+              tma_store_wait_read<0>();
+              int ntile = tile, nc = c + 1;
+              if (nc == kChunks) { ntile = tile + num_clusters; nc = 0; }
+              if (ntile < num_tiles) {
+                mbar_arrive_expect_tx(&my_bar[(gc + 1) & 1], Cfg::CHUNK_BYTES);
+                tma_load_2d(nbuf, &tmC, &my_bar[(gc + 1) & 1], (ntile % g.num_n_blocks) * BN + half * (BN / 2) + nc * 32,
+                            (ntile / g.num_n_blocks) * Cfg::TILE_M + row_in_tile);
+              }
+            } else {
+              tma_store_wait_read<1>();  // only the store of chunk gc-2 (this chunk's buffer) must have drained
             }
-            if constexpr (EPI == EPI_BIAS || EPI == EPI_BIAS_GELU) {
+          }
+          uint32_t r[32];
+          tmem_ld_32x32b_x32(taddr + c * 32, r);
+          tcgen05_wait_ld();
+          if (c == kChunks - 1) release_accumulator(acc);
+          if (g.dbg & 1) continue;
+          __syncwarp();  // lane 0's wait_group.read above covers the whole warp's writes into buf
+          const int col = col0 + c * 32;
+          const bool col_ok = col < g.N;
+          if constexpr (EPI == EPI_SCALE_RESID) {
+            mbar_wait(&my_bar[gc & 1], (gc >> 1) & 1);
+            // fp32 rows of 128 B, 128B swizzle: 16-byte chunk j of row `lane` sits at j ^ (lane & 7)
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+              float4* p = reinterpret_cast<float4*>(buf + lane * 128 + ((j ^ (lane & 7)) << 4));
+              float4 x = *p;
+              float v0 = __uint_as_float(r[4 * j]), v1 = __uint_as_float(r[4 * j + 1]);
+              float v2 = __uint_as_float(r[4 * j + 2]), v3 = __uint_as_float(r[4 * j + 3]);
+              if (g.bias != nullptr && col_ok) {
+                const float4 b = __ldg(reinterpret_cast<const float4*>(g.bias + col) + j);
+                v0 += b.x; v1 += b.y; v2 += b.z; v3 += b.w;
+              }
+              if (g.scale != nullptr && col_ok) {
+                const float4 s = __ldg(reinterpret_cast<const float4*>(g.scale + col) + j);
+                x.x = fmaf(s.x, v0, x.x); x.y = fmaf(s.y, v1, x.y); x.z = fmaf(s.z, v2, x.z); x.w = fmaf(s.w, v3, x.w);
+              } else {
+                x.x += v0; x.y += v1; x.z += v2; x.w += v3;
+              }
+              *p = x;
+            }
+          } else {
+            // bf16 rows of 64 B, 64B swizzle: 16-byte chunk j of row `lane` sits at j ^ ((lane >> 1) & 3)
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+              float v[8];
+#pragma unroll
+              for (int e = 0; e < 8; ++e) v[e] = __uint_as_float(r[8 * j + e]);
+              if (g.bias != nullptr && col_ok) {
+                const float4 b0 = __ldg(reinterpret_cast<const float4*>(g.bias + col) + 2 * j);
+                const float4 b1 = __ldg(reinterpret_cast<const float4*>(g.bias + col) + 2 * j + 1);
+                v[0] += b0.x; v[1] += b0.y; v[2] += b0.z; v[3] += b0.w;
+                v[4] += b1.x; v[5] += b1.y; v[6] += b1.z; v[7] += b1.w;
+              }
               if constexpr (EPI == EPI_BIAS_GELU) {
 #pragma unroll
-                for (int e = 0; e < 8; ++e) v[e] = gelu_erf(v[e]);
+                for (int e = 0; e < 8; ++e) v[e] = gelu_erf_fast(v[e]);
               }
               uint4 o;
               o.x = pack_bf16x2(v[0], v[1]);
               o.y = pack_bf16x2(v[2], v[3]);
               o.z = pack_bf16x2(v[4], v[5]);
               o.w = pack_bf16x2(v[6], v[7]);
-              __nv_bfloat16* op = reinterpret_cast<__nv_bfloat16*>(g.out) + orow * g.ldo + col + j;
-              *reinterpret_cast<uint4*>(op) = o;
-            } else if constexpr (EPI == EPI_SCALE_RESID) {
-              const float* rp = g.resid + orow * g.ldo + col + j;
-              float4 x0 = *reinterpret_cast<const float4*>(rp);
-              float4 x1 = *reinterpret_cast<const float4*>(rp + 4);
-              if (g.scale != nullptr) {
-                const float4 s0 = __ldg(reinterpret_cast<const float4*>(g.scale + col + j));
-                const float4 s1 = __ldg(reinterpret_cast<const float4*>(g.scale + col + j + 4));
-                x0.x = fmaf(s0.x, v[0], x0.x); x0.y = fmaf(s0.y, v[1], x0.y);
-                x0.z = fmaf(s0.z, v[2], x0.z); x0.w = fmaf(s0.w, v[3], x0.w);
-                x1.x = fmaf(s1.x, v[4], x1.x); x1.y = fmaf(s1.y, v[5], x1.y);
-                x1.z = fmaf(s1.z, v[6], x1.z); x1.w = fmaf(s1.w, v[7], x1.w);
-              } else {
-                x0.x += v[0]; x0.y += v[1]; x0.z += v[2]; x0.w += v[3];
-                x1.x += v[4]; x1.y += v[5]; x1.z += v[6]; x1.w += v[7];
-              }
-              float* op = reinterpret_cast<float*>(g.out) + orow * g.ldo + col + j;
-              *reinterpret_cast<float4*>(op) = x0;
-              *reinterpret_cast<float4*>(op + 4) = x1;
-            } else {  // EPI_PATCH
-              const float4 p0 = __ldg(reinterpret_cast<const float4*>(posb_row + col + j));
-              const float4 p1 = __ldg(reinterpret_cast<const float4*>(posb_row + col + j + 4));
-              float4 x0 = make_float4(v[0] + p0.x, v[1] + p0.y, v[2] + p0.z, v[3] + p0.w);
-              float4 x1 = make_float4(v[4] + p1.x, v[5] + p1.y, v[6] + p1.z, v[7] + p1.w);
-              float* op = reinterpret_cast<float*>(g.out) + orow * g.ldo + col + j;
-              *reinterpret_cast<float4*>(op) = x0;
-              *reinterpret_cast<float4*>(op + 4) = x1;
+              *reinterpret_cast<uint4*>(buf + lane * 64 + ((j ^ ((lane >> 1) & 3)) << 4)) = o;
+            }
+          }
+          fence_proxy_async_smem();  // generic-proxy smem writes -> visible to the TMA engine
+          __syncwarp();
+          if (lane == 0 && col_ok) {
+            tma_store_2d(&tmC, buf, col, row0);
+            tma_store_commit();
+          }
+        }
+        acc ^= 1;
+        if (acc == 0) acc_phase ^= 1;
+      }
+      if (lane == 0) tma_store_wait<0>();  // smem must stay valid until the last stores have read it
+    } else {
+      // EPI_PATCH: GEMM row b*P+p lands on token row b*(P+1)+1+p, plus position/conv-bias row p
+      for (int tile = cluster_id; tile < num_tiles; tile += num_clusters) {
+        const int n0 = (tile % g.num_n_blocks) * BN;
+        const int row = (tile / g.num_n_blocks) * Cfg::TILE_M + row_in_tile + lane;
+        const bool row_ok = row < g.M;
+        mbar_wait(&tfull_bar[acc], acc_phase);
+        tcgen05_fence_after();
+        const uint32_t taddr = tmem_base + acc * kAccStride + half * (BN / 2) + (static_cast<uint32_t>(quarter * 32) << 16);
+        const int b = row / g.P, p = row - b * g.P;
+        const size_t orow = static_cast<size_t>(b) * (g.P + 1) + 1 + p;
+        const float* posb_row = g.posb + static_cast<size_t>(p) * g.N;
+#pragma unroll 1
+        for (int c = 0; c < kChunks; ++c) {
+          uint32_t r[32];
+          tmem_ld_32x32b_x32(taddr + c * 32, r);
+          tcgen05_wait_ld();
+          if (c == kChunks - 1) release_accumulator(acc);
+          const int col = n0 + half * (BN / 2) + c * 32;
+          if (row_ok && col < g.N) {
+            float* op = reinterpret_cast<float*>(g.out) + orow * g.ldo + col;
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+              const float4 pb = __ldg(reinterpret_cast<const float4*>(posb_row + col) + j);
+              float4 x = make_float4(__uint_as_float(r[4 * j]) + pb.x, __uint_as_float(r[4 * j + 1]) + pb.y,
+                                     __uint_as_float(r[4 * j + 2]) + pb.z, __uint_as_float(r[4 * j + 3]) + pb.w);
+              reinterpret_cast<float4*>(op)[j] = x;
             }
           }
         }
+        acc ^= 1;
+        if (acc == 0) acc_phase ^= 1;
       }
-      acc ^= 1;
-      if (acc == 0) acc_phase ^= 1;
     }
   }
 
+  __syncwarp();  // warps 0/1 ran single-lane loops: reconverge before the .aligned barriers
   tcgen05_fence_before();
-  __syncthreads();
-  if (warp == 2) tmem_dealloc(tmem_base, kTmemCols);
+  if constexpr (CTAS == 2) {
+    cluster_sync_all();  // the peer may still be signalling this CTA's barriers / reading its smem
+    if (warp == 2) tmem_dealloc_cg2(tmem_base, kTmemCols);
+  } else {
+    __syncthreads();
+    if (warp == 2) tmem_dealloc(tmem_base, kTmemCols);
+  }
 }
 
 }  // namespace ldit

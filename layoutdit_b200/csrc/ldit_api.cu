@@ -33,19 +33,24 @@ EncodeTiledFn encode_fn() {
   return fn;
 }
 
-// 2-D bf16 tensor [rows, cols] row-major, box [box_rows, 64 cols], 128-byte swizzle,
-// out-of-bounds elements read as zero.
-int make_tmap_bf16_2d(CUtensorMap* tm, const void* ptr, uint64_t rows, uint64_t cols, uint32_t box_rows) {
+// 2-D row-major tensor [rows, cols], box [box_rows, box_cols], out-of-bounds elements read as
+// zero (loads) / are clipped (stores).
+int make_tmap_2d(CUtensorMap* tm, const void* ptr, CUtensorMapDataType dt, int esize, uint64_t rows, uint64_t cols,
+                 uint64_t pitch_elems, uint32_t box_rows, uint32_t box_cols, CUtensorMapSwizzle swz) {
   EncodeTiledFn fn = encode_fn();
   if (!fn) return LDIT_E_NO_DRIVER;
   cuuint64_t dims[2] = {cols, rows};
-  cuuint64_t strides[1] = {cols * 2};
-  cuuint32_t box[2] = {64, box_rows};
+  cuuint64_t strides[1] = {pitch_elems * esize};
+  cuuint32_t box[2] = {box_cols, box_rows};
   cuuint32_t estr[2] = {1, 1};
-  CUresult r = fn(tm, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(ptr), dims, strides, box, estr,
-                  CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
-                  CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  CUresult r = fn(tm, dt, 2, const_cast<void*>(ptr), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, swz,
+                  CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   return r == CUDA_SUCCESS ? 0 : 10000 + static_cast<int>(r);
+}
+
+// bf16 GEMM operand: box [box_rows, 64 cols] = 128-byte rows, 128-byte swizzle
+int make_tmap_bf16_2d(CUtensorMap* tm, const void* ptr, uint64_t rows, uint64_t cols, uint32_t box_rows) {
+  return make_tmap_2d(tm, ptr, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, rows, cols, cols, box_rows, 64, CU_TENSOR_MAP_SWIZZLE_128B);
 }
 
 int num_sms() {
@@ -68,7 +73,21 @@ inline int check_launch() {
 // wider tile (fewer re-reads of A).  LDIT_GEMM_BN overrides for experiments.
 std::atomic<int> g_forced_bn{-1};
 
-int pick_bn(int M, int N) {
+std::atomic<int> g_cta_pair{-1};  // -1: read LDIT_GEMM_CTAS once; 1 or 2 afterwards
+
+int gemm_ctas() {
+  int v = g_cta_pair.load(std::memory_order_relaxed);
+  if (v < 0) {
+    const char* e = getenv("LDIT_GEMM_CTAS");
+    v = (e && atoi(e) == 1) ? 1 : 2;
+    g_cta_pair.store(v);
+  }
+  return v;
+}
+
+// Tile width: minimise (rounds of the persistent schedule) x (tile width); ties go to the
+// wider tile (fewer operand bytes per FLOP).  Widths that divide N are preferred.
+int pick_bn(int M, int N, int ctas) {
   int forced = g_forced_bn.load(std::memory_order_relaxed);
   if (forced < 0) {
     const char* e = getenv("LDIT_GEMM_BN");
@@ -76,40 +95,68 @@ int pick_bn(int M, int N) {
     g_forced_bn.store(forced);
   }
   if (forced == 128 || forced == 192 || forced == 256) return forced;
-  const int sms = num_sms();
-  const int mb = (M + kBM - 1) / kBM;
+  const int units = num_sms() / ctas;  // CTAs or CTA pairs working in parallel
+  const int mb = (M + kBM * ctas - 1) / (kBM * ctas);
   int best = 256;
   long best_cost = -1;
   const int cands[3] = {256, 192, 128};
+  bool any_divides = false;
+  for (int bn : cands) any_divides |= (N % bn == 0);
   for (int bn : cands) {
+    if (any_divides && (N % bn)) continue;  // no ragged last column of tiles if it can be avoided
     const long tiles = static_cast<long>(mb) * ((N + bn - 1) / bn);
-    const long rounds = (tiles + sms - 1) / sms;
+    const long rounds = (tiles + units - 1) / units;
     const long cost = rounds * (bn + 16);  // +16: per-tile fixed overhead in "column" units
     if (best_cost < 0 || cost < best_cost) { best_cost = cost; best = bn; }
   }
   return best;
 }
 
-template <int BN, int EPI>
+template <int BN, int EPI, int CTAS>
 int launch_gemm_t(const void* A, const void* W, GemmArgs g, cudaStream_t st) {
-  using Cfg = GemmCfg<BN>;
+  using Cfg = GemmCfg<BN, EPI, CTAS>;
   static bool attr_set = false;
   if (!attr_set) {
-    cudaError_t e = cudaFuncSetAttribute(gemm_tcgen05_kernel<BN, EPI>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES);
+    cudaError_t e = cudaFuncSetAttribute(gemm_tcgen05_kernel<BN, EPI, CTAS>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                         Cfg::SMEM_BYTES);
     if (e != cudaSuccess) return static_cast<int>(e);
     attr_set = true;
   }
-  CUtensorMap tmA, tmB;
+  CUtensorMap tmA, tmB, tmC;
   int rc = make_tmap_bf16_2d(&tmA, A, g.M, g.K, kBM);
   if (rc) return rc;
-  rc = make_tmap_bf16_2d(&tmB, W, g.N, g.K, BN);
+  rc = make_tmap_bf16_2d(&tmB, W, g.N, g.K, Cfg::B_ROWS);
   if (rc) return rc;
-  g.num_m_blocks = (g.M + kBM - 1) / kBM;
+  if (Cfg::STAGED) {  // epilogue staging: 32 x 32 element boxes, rows of 64 B (bf16) / 128 B (fp32)
+    rc = Cfg::OUT_F32 ? make_tmap_2d(&tmC, g.out, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, g.M, g.N, g.ldo, 32, 32, CU_TENSOR_MAP_SWIZZLE_128B)
+                      : make_tmap_2d(&tmC, g.out, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, g.M, g.N, g.ldo, 32, 32, CU_TENSOR_MAP_SWIZZLE_64B);
+    if (rc) return rc;
+  } else {
+    tmC = tmA;
+  }
+  static const int dbg = [] { const char* e = getenv("LDIT_GEMM_DBG"); return e ? atoi(e) : 0; }();
+  g.dbg = dbg;
+  g.num_m_blocks = (g.M + Cfg::TILE_M - 1) / Cfg::TILE_M;
   g.num_n_blocks = (g.N + BN - 1) / BN;
   const int tiles = g.num_m_blocks * g.num_n_blocks;
-  const int grid = tiles < num_sms() ? tiles : num_sms();
-  gemm_tcgen05_kernel<BN, EPI><<<grid, kGemmThreads, Cfg::SMEM_BYTES, st>>>(tmA, tmB, g);
-  return check_launch();
+  const int units = num_sms() / CTAS;
+  const int grid = (tiles < units ? tiles : units) * CTAS;
+  cudaLaunchConfig_t cfg{};
+  cfg.gridDim = dim3(grid);
+  cfg.blockDim = dim3(kGemmThreads);
+  cfg.dynamicSmemBytes = Cfg::SMEM_BYTES;
+  cfg.stream = st;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = CTAS;
+  attr[0].val.clusterDim.y = 1;
+  attr[0].val.clusterDim.z = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+  cudaError_t e = cudaLaunchKernelEx(&cfg, gemm_tcgen05_kernel<BN, EPI, CTAS>, tmA, tmB, tmC, g);
+  g_launches.fetch_add(1, std::memory_order_relaxed);
+  if (e != cudaSuccess) { (void)cudaGetLastError(); return static_cast<int>(e); }
+  return static_cast<int>(cudaGetLastError());
 }
 
 template <int EPI>
@@ -119,10 +166,19 @@ int launch_gemm(const void* A, const void* W, GemmArgs g, cudaStream_t st) {
   if (!aligned16(A) || !aligned16(W) || !aligned16(g.out) || !aligned16(g.bias) || !aligned16(g.scale) ||
       !aligned16(g.resid) || !aligned16(g.posb))
     return LDIT_E_ALIGN;
-  switch (pick_bn(g.M, g.N)) {
-    case 128: return launch_gemm_t<128, EPI>(A, W, g, st);
-    case 192: return launch_gemm_t<192, EPI>(A, W, g, st);
-    default: return launch_gemm_t<256, EPI>(A, W, g, st);
+  const int ctas = gemm_ctas();
+  const int bn = pick_bn(g.M, g.N, ctas);
+  if (ctas == 2) {
+    switch (bn) {
+      case 128: return launch_gemm_t<128, EPI, 2>(A, W, g, st);
+      case 192: return launch_gemm_t<192, EPI, 2>(A, W, g, st);
+      default: return launch_gemm_t<256, EPI, 2>(A, W, g, st);
+    }
+  }
+  switch (bn) {
+    case 128: return launch_gemm_t<128, EPI, 1>(A, W, g, st);
+    case 192: return launch_gemm_t<192, EPI, 1>(A, W, g, st);
+    default: return launch_gemm_t<256, EPI, 1>(A, W, g, st);
   }
 }
 
@@ -152,6 +208,7 @@ const char* ldit_error_string(int code) {
 }
 
 void ldit_set_gemm_tile_n(int bn) { g_forced_bn.store((bn == 128 || bn == 192 || bn == 256) ? bn : 0); }
+void ldit_set_gemm_cta_pair(int ctas) { g_cta_pair.store(ctas == 1 ? 1 : 2); }
 
 unsigned long long ldit_launch_count(void) { return g_launches.load(); }
 void ldit_reset_launch_count(void) { g_launches.store(0); }

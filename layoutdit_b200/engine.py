@@ -288,8 +288,10 @@ class Engine:
         x = self.prepare_input(x)
         geo = self._geometry(x.shape[0], x.shape[2], x.shape[3])
         if geo.graph is None or geo.graph_in.dtype != x.dtype:
-            geo.graph_in = torch.empty_like(x)
-            geo.graph_in.copy_(x)
+            if geo.graph_in is None or geo.graph_in.dtype != x.dtype:
+                geo.graph_in = torch.empty_like(x)
+            if x.data_ptr() != geo.graph_in.data_ptr():
+                geo.graph_in.copy_(x)
             outs = self._alloc_outputs(geo)
             side = torch.cuda.Stream(self.device)
             side.wait_stream(torch.cuda.current_stream(self.device))

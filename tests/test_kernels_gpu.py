@@ -24,6 +24,7 @@ def lib(cuda_device):
     lib = _lib.load()
     yield lib
     lib.ldit_set_gemm_tile_n(0)
+    lib.ldit_set_gemm_cta_pair(2)
 
 
 # ----------------------------------------------------------------------------- LayerNorm
@@ -55,9 +56,11 @@ def _gemm_inputs(M, N, K, seed):
     return A, W, bias
 
 
+@pytest.mark.parametrize("ctas", [2, 1])
 @pytest.mark.parametrize("bn", [0, 128, 192, 256])
 @pytest.mark.parametrize("M,N,K", GEMM_SHAPES)
-def test_gemm_bias(lib, M, N, K, bn):
+def test_gemm_bias(lib, M, N, K, bn, ctas):
+    lib.ldit_set_gemm_cta_pair(ctas)
     lib.ldit_set_gemm_tile_n(bn)
     A, W, bias = _gemm_inputs(M, N, K, M + N + K)
     out = torch.full((M, N), float("nan"), device="cuda", dtype=torch.bfloat16)
@@ -68,8 +71,10 @@ def test_gemm_bias(lib, M, N, K, bn):
     torch.testing.assert_close(out.float(), ref, rtol=2 ** -7, atol=2e-2)
 
 
+@pytest.mark.parametrize("ctas", [2, 1])
 @pytest.mark.parametrize("M,N,K", [(333, 3072, 768), (12608, 3072, 768)])
-def test_gemm_bias_gelu(lib, M, N, K):
+def test_gemm_bias_gelu(lib, M, N, K, ctas):
+    lib.ldit_set_gemm_cta_pair(ctas)
     lib.ldit_set_gemm_tile_n(0)
     A, W, bias = _gemm_inputs(M, N, K, 7)
     out = torch.empty(M, N, device="cuda", dtype=torch.bfloat16)
@@ -79,9 +84,11 @@ def test_gemm_bias_gelu(lib, M, N, K):
     torch.testing.assert_close(out.float(), ref, rtol=2 ** -7, atol=2e-2)
 
 
+@pytest.mark.parametrize("ctas", [2, 1])
 @pytest.mark.parametrize("with_scale", [True, False])
 @pytest.mark.parametrize("M,N,K", [(333, 768, 768), (12608, 768, 3072), (197, 1024, 4096)])
-def test_gemm_bias_scale_residual(lib, M, N, K, with_scale):
+def test_gemm_bias_scale_residual(lib, M, N, K, with_scale, ctas):
+    lib.ldit_set_gemm_cta_pair(ctas)
     lib.ldit_set_gemm_tile_n(0)
     A, W, bias = _gemm_inputs(M, N, K, 11)
     g = torch.Generator(device="cuda").manual_seed(5)
@@ -106,6 +113,8 @@ def test_gemm_rejects_bad_arguments(lib):
 @pytest.mark.parametrize("dtype", [torch.float32, torch.float16, torch.bfloat16])
 @pytest.mark.parametrize("B,H,W,D", [(2, 64, 96, 128), (3, 224, 224, 768)])
 def test_patch_embed(lib, B, H, W, D, dtype):
+    lib.ldit_set_gemm_cta_pair(2)
+    lib.ldit_set_gemm_tile_n(0)
     g = torch.Generator(device="cuda").manual_seed(B * H + W)
     px = (torch.rand(B, 3, H, W, device="cuda", generator=g) * 2 - 1).to(dtype)
     w = (torch.randn(D, 3, 16, 16, device="cuda", generator=g) * 0.04).to(torch.bfloat16)

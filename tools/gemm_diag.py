@@ -44,6 +44,7 @@ def run(M, N, K, bn, mode="rand"):
 
 
 if __name__ == "__main__":
+    lib.ldit_set_gemm_cta_pair(int(os.environ.get("CTAS", "2")))
     for args in [(128, 128, 64, 128, "struct"), (128, 128, 64, 128, "rand"), (128, 256, 64, 256, "rand"),
                  (128, 192, 64, 192, "rand"), (128, 128, 256, 128, "rand"), (256, 256, 768, 128, "rand"),
                  (1000, 768, 768, 192, "rand"), (12608, 2304, 768, 0, "rand")]:
