@@ -95,6 +95,10 @@ void ldit_set_gemm_tile_n(int bn);
  * 1 = independent CTAs (128 x BN tile).  Also settable with LDIT_GEMM_CTAS. */
 void ldit_set_gemm_cta_pair(int ctas);
 
+/* Tuning knob: 0 (default) = tcgen05/TMEM attention kernel; 1 = the warp-level mma.sync
+ * variant kept for comparison.  Also settable with LDIT_ATTN_IMPL. */
+void ldit_set_attention_impl(int impl);
+
 /* Number of kernels the library has enqueued since load / last reset (for gpu_launches). */
 unsigned long long ldit_launch_count(void);
 void ldit_reset_launch_count(void);

@@ -25,6 +25,7 @@ SIGNATURES = {
     "ldit_patch_embed_scratch_bytes": (_c.c_size_t, [_i, _i, _i]),
     "ldit_set_gemm_tile_n": (None, [_i]),
     "ldit_set_gemm_cta_pair": (None, [_i]),
+    "ldit_set_attention_impl": (None, [_i]),
     "ldit_launch_count": (_c.c_ulonglong, []),
     "ldit_reset_launch_count": (None, []),
 }

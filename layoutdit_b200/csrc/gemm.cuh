@@ -11,13 +11,13 @@
 // 128 x BN variant of the same code.
 //
 // CTA = 128 + 256 threads, one CTA per SM, static round-robin tile scheduler over clusters:
-//   warp 0    TMA producer   (one lane, both CTAs): A/B tiles -> 128B-swizzled smem ring; all
+//   warp 10   TMA producer   (one lane, both CTAs): A/B tiles -> 128B-swizzled smem ring; all
 //             completion bytes are credited to the LEADER CTA's "full" barrier
-//   warp 1    MMA issuer     (one lane, leader CTA only): tcgen05.mma, accumulators
+//   warp 11   MMA issuer     (one lane, leader CTA only): tcgen05.mma, accumulators
 //             double-buffered in TMEM; tcgen05.commit multicasts "slot free" / "accumulator ready"
 //             to both CTAs
-//   warp 2    TMEM allocator
-//   warps 4-11 epilogue (both CTAs, own 128 rows): tcgen05.ld -> registers -> bias / erf-GELU /
+//   warp 9    TMEM allocator
+//   warps 0-7 epilogue (both CTAs, own 128 rows): tcgen05.ld -> registers -> bias / erf-GELU /
 //             layer-scale + residual -> swizzled smem staging -> TMA store (the residual tile
 //             arrives by TMA load into the same staging buffer, prefetched one chunk ahead)
 //
@@ -49,6 +49,12 @@ constexpr int kBK = 64;   // 64 bf16 = one 128-byte swizzle row
 constexpr int kUmmaK = 16;
 constexpr int kGemmEpiWarps = 8;
 constexpr int kGemmThreads = 128 + kGemmEpiWarps * 32;
+// Warp roles.  The SM's warp arbiter favours the highest warp id on each scheduler, so the two
+// latency-critical single-lane roles (TMA producer, MMA issuer) get the highest ids and the
+// compute-heavy epilogue warps the lowest: a busy epilogue must never delay an MMA issue.
+constexpr int kWarpAlloc = kGemmEpiWarps + 1;     // 9
+constexpr int kWarpProducer = kGemmEpiWarps + 2;  // 10
+constexpr int kWarpMma = kGemmEpiWarps + 3;       // 11
 constexpr int kAccStride = 256;  // TMEM columns between the two accumulator stages
 constexpr int kTmemCols = 512;
 constexpr int kMaxSmem = 232448;  // 227 KB opt-in limit per CTA
@@ -112,18 +118,18 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
   uint64_t* resid_bar = tempty_bar + 2;  // [kGemmEpiWarps][2]
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(resid_bar + 2 * kGemmEpiWarps);
 
-  const int warp = threadIdx.x >> 5;
+  const int warp = __shfl_sync(0xffffffffu, static_cast<int>(threadIdx.x >> 5), 0);  // provably warp-uniform
   const int lane = threadIdx.x & 31;
   const uint32_t rank = CTAS == 2 ? cluster_ctarank() : 0u;  // 0 = leader of the pair
   const int cluster_id = blockIdx.x / CTAS;
   const int num_clusters = gridDim.x / CTAS;
 
-  if (warp == 0 && lane == 0) {
+  if (warp == kWarpProducer && lane == 0) {
     tma_prefetch_desc(&tmA);
     tma_prefetch_desc(&tmB);
     if constexpr (Cfg::STAGED) tma_prefetch_desc(&tmC);
   }
-  if (warp == 1 && lane == 0) {
+  if (warp == kWarpMma && lane == 0) {
     for (int i = 0; i < S; ++i) {
       mbar_init(&full_bar[i], 1);
       mbar_init(&empty_bar[i], 1);
@@ -136,7 +142,7 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
     fence_barrier_init();
     fence_proxy_async_smem();
   }
-  if (warp == 2) {
+  if (warp == kWarpAlloc) {
     if constexpr (CTAS == 2) {
       tmem_alloc_cg2(tmem_slot, kTmemCols);
       tmem_relinquish_cg2();
@@ -153,15 +159,20 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
   const int num_tiles = g.num_m_blocks * g.num_n_blocks;
   const int nkb = (g.K + kBK - 1) / kBK;
 
-  if (warp == 0) {
-    if (lane == 0) {
-      int stage = 0;
-      uint32_t phase = 0;
-      for (int tile = cluster_id; tile < num_tiles; tile += num_clusters) {
-        const int m0 = (tile / g.num_n_blocks) * Cfg::TILE_M + static_cast<int>(rank) * kBM;
-        const int n0 = (tile % g.num_n_blocks) * BN + static_cast<int>(rank) * Cfg::B_ROWS;
-        for (int kb = 0; kb < nkb; ++kb) {
-          mbar_wait(&empty_bar[stage], phase ^ 1);
+  // Producer and MMA loops are executed by ALL lanes of their warp (warp-uniform control flow,
+  // so ptxas keeps stage / phase / descriptors in uniform registers); only the TMA / tcgen05
+  // instructions themselves are issued by one elected lane.  A single-lane loop costs ~80
+  // dependent SASS instructions per k-block (ELECT + R2UR per operand) and starves the tensor
+  // core whenever an epilogue warp shares the scheduler.
+  if (warp == kWarpProducer) {
+    int stage = 0;
+    uint32_t phase = 0;
+    for (int tile = cluster_id; tile < num_tiles; tile += num_clusters) {
+      const int m0 = (tile / g.num_n_blocks) * Cfg::TILE_M + static_cast<int>(rank) * kBM;
+      const int n0 = (tile % g.num_n_blocks) * BN + static_cast<int>(rank) * Cfg::B_ROWS;
+      for (int kb = 0; kb < nkb; ++kb) {
+        mbar_wait(&empty_bar[stage], phase ^ 1);
+        if (elect_one_sync()) {
           if constexpr (CTAS == 2) {
             if (rank == 0) mbar_arrive_expect_tx(&full_bar[stage], Cfg::STAGE_BYTES * 2);
             const uint32_t leader_full = mapa_shared(smem_u32(&full_bar[stage]), 0);
@@ -172,13 +183,16 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
             tma_load_2d(sA + stage * Cfg::A_BYTES, &tmA, &full_bar[stage], kb * kBK, m0);
             tma_load_2d(sB + stage * Cfg::B_BYTES, &tmB, &full_bar[stage], kb * kBK, n0);
           }
-          if (++stage == S) { stage = 0; phase ^= 1; }
         }
+        __syncwarp();
+        if (++stage == S) { stage = 0; phase ^= 1; }
       }
     }
-  } else if (warp == 1) {
-    if (lane == 0 && rank == 0) {
+  } else if (warp == kWarpMma) {
+    if (rank == 0) {
       constexpr uint32_t idesc = umma_idesc_bf16(Cfg::TILE_M, BN, 0, 0);
+      const uint64_t adesc0 = umma_desc_kmajor_sw128(smem_u32(sA));
+      const uint64_t bdesc0 = umma_desc_kmajor_sw128(smem_u32(sB));
       int stage = 0;
       uint32_t phase = 0;
       int acc = 0;
@@ -190,25 +204,30 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
         for (int kb = 0; kb < nkb; ++kb) {
           mbar_wait(&full_bar[stage], phase);
           tcgen05_fence_after();
-          const uint64_t adesc = umma_desc_kmajor_sw128(smem_u32(sA + stage * Cfg::A_BYTES));
-          const uint64_t bdesc = umma_desc_kmajor_sw128(smem_u32(sB + stage * Cfg::B_BYTES));
+          if (elect_one_sync()) {
+            const uint64_t adesc = adesc0 + static_cast<uint32_t>(stage * (Cfg::A_BYTES >> 4));
+            const uint64_t bdesc = bdesc0 + static_cast<uint32_t>(stage * (Cfg::B_BYTES >> 4));
 #pragma unroll
-          for (int k = 0; k < kBK / kUmmaK; ++k) {
-            if constexpr (CTAS == 2) umma_bf16_ss_cg2(d_tmem, adesc + 2 * k, bdesc + 2 * k, idesc, (kb | k) != 0);
-            else umma_bf16_ss(d_tmem, adesc + 2 * k, bdesc + 2 * k, idesc, (kb | k) != 0);
+            for (int k = 0; k < kBK / kUmmaK; ++k) {
+              if constexpr (CTAS == 2) umma_bf16_ss_cg2(d_tmem, adesc + 2 * k, bdesc + 2 * k, idesc, (kb | k) != 0);
+              else umma_bf16_ss(d_tmem, adesc + 2 * k, bdesc + 2 * k, idesc, (kb | k) != 0);
+            }
+            // smem slot reusable (in both CTAs) once these MMAs have read it
+            if constexpr (CTAS == 2) tcgen05_commit_cg2(&empty_bar[stage], 3); else tcgen05_commit(&empty_bar[stage]);
+            // last k-block: the accumulator is complete (both CTAs' epilogues)
+            if (kb == nkb - 1) {
+              if constexpr (CTAS == 2) tcgen05_commit_cg2(&tfull_bar[acc], 3); else tcgen05_commit(&tfull_bar[acc]);
+            }
           }
-          // smem slot reusable (in both CTAs) once these MMAs have read it
-          if constexpr (CTAS == 2) tcgen05_commit_cg2(&empty_bar[stage], 3); else tcgen05_commit(&empty_bar[stage]);
+          __syncwarp();
           if (++stage == S) { stage = 0; phase ^= 1; }
         }
-        // accumulator complete (both CTAs' epilogues)
-        if constexpr (CTAS == 2) tcgen05_commit_cg2(&tfull_bar[acc], 3); else tcgen05_commit(&tfull_bar[acc]);
         acc ^= 1;
         if (acc == 0) acc_phase ^= 1;
       }
     }
-  } else if (warp >= 4) {
-    const int ew = warp - 4;
+  } else if (warp < kGemmEpiWarps) {
+    const int ew = warp;
     const int quarter = warp & 3;   // TMEM lane quarter this warp may access
     const int half = ew >> 2;       // which half of the BN columns
     constexpr int kChunks = BN / 2 / 32;
@@ -318,9 +337,9 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
               *reinterpret_cast<uint4*>(buf + lane * 64 + ((j ^ ((lane >> 1) & 3)) << 4)) = o;
             }
           }
-          fence_proxy_async_smem();  // generic-proxy smem writes -> visible to the TMA engine
+          if (!(g.dbg & 4)) fence_proxy_async_smem();  // generic-proxy smem writes -> visible to the TMA engine
           __syncwarp();
-          if (lane == 0 && col_ok) {
+          if (lane == 0 && col_ok && !(g.dbg & 2)) {
             tma_store_2d(&tmC, buf, col, row0);
             tma_store_commit();
           }
@@ -369,10 +388,10 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
   tcgen05_fence_before();
   if constexpr (CTAS == 2) {
     cluster_sync_all();  // the peer may still be signalling this CTA's barriers / reading its smem
-    if (warp == 2) tmem_dealloc_cg2(tmem_base, kTmemCols);
+    if (warp == kWarpAlloc) tmem_dealloc_cg2(tmem_base, kTmemCols);
   } else {
     __syncthreads();
-    if (warp == 2) tmem_dealloc(tmem_base, kTmemCols);
+    if (warp == kWarpAlloc) tmem_dealloc(tmem_base, kTmemCols);
   }
 }
 

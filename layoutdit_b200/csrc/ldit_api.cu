@@ -7,6 +7,7 @@
 
 #include "../../include/ldit.h"
 #include "attention_mma.cuh"
+#include "attention_tc.cuh"
 #include "gemm.cuh"
 #include "rowwise.cuh"
 
@@ -52,6 +53,23 @@ int make_tmap_2d(CUtensorMap* tm, const void* ptr, CUtensorMapDataType dt, int e
 int make_tmap_bf16_2d(CUtensorMap* tm, const void* ptr, uint64_t rows, uint64_t cols, uint32_t box_rows) {
   return make_tmap_2d(tm, ptr, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, rows, cols, cols, box_rows, 64, CU_TENSOR_MAP_SWIZZLE_128B);
 }
+
+// qkv viewed as [B, N, 3D] bf16: box [1, box_rows, 64 cols], 128-byte swizzle.  The image is its
+// own dimension so that rows past the end of an image read as zero instead of the next image.
+int make_tmap_qkv_3d(CUtensorMap* tm, const void* ptr, uint64_t B, uint64_t N, uint64_t cols, uint32_t box_rows) {
+  EncodeTiledFn fn = encode_fn();
+  if (!fn) return LDIT_E_NO_DRIVER;
+  cuuint64_t dims[3] = {cols, N, B};
+  cuuint64_t strides[2] = {cols * 2, N * cols * 2};
+  cuuint32_t box[3] = {64, box_rows, 1};
+  cuuint32_t estr[3] = {1, 1, 1};
+  CUresult r = fn(tm, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 3, const_cast<void*>(ptr), dims, strides, box, estr,
+                  CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                  CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  return r == CUDA_SUCCESS ? 0 : 10000 + static_cast<int>(r);
+}
+
+std::atomic<int> g_attn_impl{-1};  // 0 = tcgen05 (default), 1 = mma.sync variant
 
 int num_sms() {
   static int sms = [] {
@@ -208,6 +226,7 @@ const char* ldit_error_string(int code) {
 }
 
 void ldit_set_gemm_tile_n(int bn) { g_forced_bn.store((bn == 128 || bn == 192 || bn == 256) ? bn : 0); }
+void ldit_set_attention_impl(int impl) { g_attn_impl.store(impl == 1 ? 1 : 0); }
 void ldit_set_gemm_cta_pair(int ctas) { g_cta_pair.store(ctas == 1 ? 1 : 2); }
 
 unsigned long long ldit_launch_count(void) { return g_launches.load(); }
@@ -303,13 +322,51 @@ int ldit_attention(const void* qkv, void* ctx, const void* bias_table, int B, in
   if (B <= 0 || heads <= 0 || Gh <= 0 || Gw <= 0 || N != Gh * Gw + 1) return LDIT_E_SHAPE;
   if (!aligned16(qkv) || !aligned16(ctx) || !aligned16(bias_table)) return LDIT_E_ALIGN;
   cudaStream_t st = static_cast<cudaStream_t>(stream);
+  const int D = heads * kAttDh;
+  const int T = (2 * Gh - 1) * (2 * Gw - 1) + 3;
+  const float scale_log2e = 0.125f * 1.4426950408889634f;
+  int impl = g_attn_impl.load(std::memory_order_relaxed);
+  if (impl < 0) {
+    const char* e = getenv("LDIT_ATTN_IMPL");
+    impl = (e && atoi(e) == 1) ? 1 : 0;
+    g_attn_impl.store(impl);
+  }
+  if (impl == 0) {
+    AttnTcArgs a{};
+    a.ctx = static_cast<__nv_bfloat16*>(ctx);
+    a.bias_table = static_cast<const float*>(bias_table);
+    a.B = B; a.N = N; a.heads = heads; a.D = D; a.Gh = Gh; a.Gw = Gw; a.T = T;
+    a.n_kv_tiles = (N + kAtcMaxKv - 1) / kAtcMaxKv;
+    a.kv_tile = (((N + a.n_kv_tiles - 1) / a.n_kv_tiles) + 15) / 16 * 16;
+    a.scale_log2e = scale_log2e;
+    CUtensorMap tmQ, tmKV;
+    int rc = make_tmap_qkv_3d(&tmQ, qkv, B, N, 3 * D, kAtcQ);
+    if (rc) return rc;
+    rc = make_tmap_qkv_3d(&tmKV, qkv, B, N, 3 * D, a.kv_tile);
+    if (rc) return rc;
+    size_t smem = 1024 + 16384 + 2 * kAtcMaxKv * 128 + 64;
+    if (bias_table) smem += (static_cast<size_t>(T) + N) * 4;
+    if (smem > 110 * 1024) return LDIT_E_SHAPE;
+    dim3 grid((N + kAtcQ - 1) / kAtcQ, heads, B);
+    static size_t max_set[2] = {0, 0};
+    const int bi = bias_table ? 1 : 0;
+    if (smem > max_set[bi]) {
+      cudaError_t e = bias_table ? cudaFuncSetAttribute(attention_tc_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem))
+                                 : cudaFuncSetAttribute(attention_tc_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem));
+      if (e != cudaSuccess) return static_cast<int>(e);
+      max_set[bi] = smem;
+    }
+    if (bias_table) attention_tc_kernel<true><<<grid, kAtcThreads, smem, st>>>(tmQ, tmKV, a);
+    else attention_tc_kernel<false><<<grid, kAtcThreads, smem, st>>>(tmQ, tmKV, a);
+    return check_launch();
+  }
   AttnArgs a{};
   a.qkv = static_cast<const __nv_bfloat16*>(qkv);
   a.ctx = static_cast<__nv_bfloat16*>(ctx);
   a.bias_table = static_cast<const float*>(bias_table);
-  a.B = B; a.N = N; a.heads = heads; a.D = heads * kAttDh;
-  a.Gh = Gh; a.Gw = Gw; a.T = (2 * Gh - 1) * (2 * Gw - 1) + 3;
-  a.scale_log2e = 0.125f * 1.4426950408889634f;
+  a.B = B; a.N = N; a.heads = heads; a.D = D;
+  a.Gh = Gh; a.Gw = Gw; a.T = T;
+  a.scale_log2e = scale_log2e;
   dim3 grid((N + kAttBQ - 1) / kAttBQ, heads, B);
   size_t smem = 8192 + 32768;
   if (bias_table) {

@@ -25,6 +25,7 @@ def lib(cuda_device):
     yield lib
     lib.ldit_set_gemm_tile_n(0)
     lib.ldit_set_gemm_cta_pair(2)
+    lib.ldit_set_attention_impl(0)
 
 
 # ----------------------------------------------------------------------------- LayerNorm
@@ -158,9 +159,12 @@ def _dense_bias(table_t, Gh, Gw):
     return table_t[:, idx.to(table_t.device)].unsqueeze(0)
 
 
+@pytest.mark.parametrize("impl", [0, 1])
 @pytest.mark.parametrize("with_bias", [False, True])
-@pytest.mark.parametrize("B,heads,Gh,Gw", [(2, 2, 4, 4), (3, 12, 14, 14), (2, 4, 14, 20), (1, 3, 32, 32), (2, 2, 5, 7)])
-def test_attention(lib, B, heads, Gh, Gw, with_bias):
+@pytest.mark.parametrize("B,heads,Gh,Gw", [(2, 2, 4, 4), (3, 12, 14, 14), (2, 4, 14, 20), (1, 3, 32, 32), (2, 2, 5, 7),
+                                           (1, 2, 13, 16), (2, 1, 1, 1)])
+def test_attention(lib, B, heads, Gh, Gw, with_bias, impl):
+    lib.ldit_set_attention_impl(impl)
     N, D = Gh * Gw + 1, heads * 64
     g = torch.Generator(device="cuda").manual_seed(N + heads)
     qkv = (torch.randn(B * N, 3 * D, device="cuda", generator=g) * 1.5).to(torch.bfloat16)
