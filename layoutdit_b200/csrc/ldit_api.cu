@@ -391,10 +391,20 @@ int ldit_resample_taps(const void* x, void* out, int B, int Gh, int Gw, int D, f
   if (!aligned16(x) || !aligned16(out)) return LDIT_E_ALIGN;
   const int oh = static_cast<int>(floorf(Gh * scale)), ow = static_cast<int>(floorf(Gw * scale));
   if (oh <= 0 || ow <= 0) return LDIT_E_SHAPE;
-  const size_t total = static_cast<size_t>(B) * oh * ow * (D / 8);
-  const unsigned blocks = static_cast<unsigned>((total + 255) / 256);
-  resample_taps_kernel<<<blocks, 256, 0, static_cast<cudaStream_t>(stream)>>>(
-      static_cast<const float*>(x), static_cast<__nv_bfloat16*>(out), B, Gh * Gw + 1, D, Gh, Gw, oh, ow, 1.0f / scale);
+  if (D / 8 * kTapPix > 1024 || B > 65535) return LDIT_E_SHAPE;
+  if ((scale == 4.0f || scale == 2.0f) && D / 8 * kUpCells <= 512) {  // cell-based integer up-sampling
+    dim3 ublock(D / 8, kUpCells);
+    dim3 ugrid((Gh * Gw + kUpCells - 1) / kUpCells, B);
+    const float* xf = static_cast<const float*>(x);
+    __nv_bfloat16* ob = static_cast<__nv_bfloat16*>(out);
+    if (scale == 4.0f) upsample_taps_kernel<4><<<ugrid, ublock, 0, static_cast<cudaStream_t>(stream)>>>(xf, ob, Gh * Gw + 1, D, Gh, Gw);
+    else upsample_taps_kernel<2><<<ugrid, ublock, 0, static_cast<cudaStream_t>(stream)>>>(xf, ob, Gh * Gw + 1, D, Gh, Gw);
+    return check_launch();
+  }
+  dim3 block(D / 8, kTapPix);
+  dim3 grid((oh * ow + kTapPix - 1) / kTapPix, B);
+  resample_taps_kernel<<<grid, block, 0, static_cast<cudaStream_t>(stream)>>>(
+      static_cast<const float*>(x), static_cast<__nv_bfloat16*>(out), Gh * Gw + 1, D, Gh, Gw, oh, ow, 1.0f / scale);
   return check_launch();
 }
 

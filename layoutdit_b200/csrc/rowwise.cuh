@@ -123,36 +123,34 @@ cls_rows_kernel(const float* __restrict__ cls_pos, float* __restrict__ xres, int
 // NHWC-strided view it is given, and the layout in which both the token reads and the
 // (dominant) tap writes are fully coalesced.  ATen's source-index rule for a given
 // scale_factor: src = max((dst + .5) / s - .5, 0); i0 = min(floor(src), in-1); i1 = min(i0+1, in-1).
-__global__ void __launch_bounds__(256)
-resample_taps_kernel(const float* __restrict__ xres, __nv_bfloat16* __restrict__ out, int B, int N, int D, int Gh, int Gw,
+// blockDim = (D/8, kTapPix): threadIdx.x = 8-channel chunk, threadIdx.y = output pixel of the block;
+// gridDim = (ceil(oh*ow / kTapPix), B).  One 32-bit division per thread; every global access is 16 B
+// per lane with consecutive lanes on consecutive addresses (a pixel's D channels are contiguous in
+// both the token rows and the channels-last output).
+constexpr int kTapPix = 4;
+
+__global__ void __launch_bounds__(1024)
+resample_taps_kernel(const float* __restrict__ xres, __nv_bfloat16* __restrict__ out, int N, int D, int Gh, int Gw,
                      int oh, int ow, float inv_scale) {
-  const int d8 = D / 8;
-  const size_t total = static_cast<size_t>(B) * oh * ow * d8;
-  const size_t idx = static_cast<size_t>(blockIdx.x) * blockDim.x + threadIdx.x;
-  if (idx >= total) return;
-  const int j = static_cast<int>(idx % d8);
-  size_t t = idx / d8;
-  const int ox = static_cast<int>(t % ow); t /= ow;
-  const int oy = static_cast<int>(t % oh);
-  const int b = static_cast<int>(t / oh);
+  const int pix = blockIdx.x * kTapPix + threadIdx.y;
+  if (pix >= oh * ow) return;
+  const int b = blockIdx.y;
+  const int oy = pix / ow, ox = pix - oy * ow;
   const float sy = fmaxf((oy + 0.5f) * inv_scale - 0.5f, 0.f);
   const float sx = fmaxf((ox + 0.5f) * inv_scale - 0.5f, 0.f);
   const int y0 = min(static_cast<int>(sy), Gh - 1), x0 = min(static_cast<int>(sx), Gw - 1);
   const int y1 = min(y0 + 1, Gh - 1), x1 = min(x0 + 1, Gw - 1);
   const float ly = sy - y0, lx = sx - x0;
   const float w00 = (1.f - ly) * (1.f - lx), w01 = (1.f - ly) * lx, w10 = ly * (1.f - lx), w11 = ly * lx;
-  const float* base = xres + (static_cast<size_t>(b) * N + 1) * D + j * 8;
-  const float* p00 = base + static_cast<size_t>(y0 * Gw + x0) * D;
-  const float* p01 = base + static_cast<size_t>(y0 * Gw + x1) * D;
-  const float* p10 = base + static_cast<size_t>(y1 * Gw + x0) * D;
-  const float* p11 = base + static_cast<size_t>(y1 * Gw + x1) * D;
+  const float* base = xres + (static_cast<size_t>(b) * N + 1) * D + threadIdx.x * 8;
+  const float4* p00 = reinterpret_cast<const float4*>(base + static_cast<size_t>(y0 * Gw + x0) * D);
+  const float4* p01 = reinterpret_cast<const float4*>(base + static_cast<size_t>(y0 * Gw + x1) * D);
+  const float4* p10 = reinterpret_cast<const float4*>(base + static_cast<size_t>(y1 * Gw + x0) * D);
+  const float4* p11 = reinterpret_cast<const float4*>(base + static_cast<size_t>(y1 * Gw + x1) * D);
   float acc[8];
 #pragma unroll
   for (int h = 0; h < 2; ++h) {
-    const float4 a = __ldg(reinterpret_cast<const float4*>(p00) + h);
-    const float4 bq = __ldg(reinterpret_cast<const float4*>(p01) + h);
-    const float4 c = __ldg(reinterpret_cast<const float4*>(p10) + h);
-    const float4 d = __ldg(reinterpret_cast<const float4*>(p11) + h);
+    const float4 a = __ldg(p00 + h), bq = __ldg(p01 + h), c = __ldg(p10 + h), d = __ldg(p11 + h);
     // same association order as ATen: w00*a + w01*b + w10*c + w11*d
     acc[4 * h + 0] = w00 * a.x + w01 * bq.x + w10 * c.x + w11 * d.x;
     acc[4 * h + 1] = w00 * a.y + w01 * bq.y + w10 * c.y + w11 * d.y;
@@ -162,7 +160,65 @@ resample_taps_kernel(const float* __restrict__ xres, __nv_bfloat16* __restrict__
   uint4 o;
   o.x = pack_bf16x2(acc[0], acc[1]); o.y = pack_bf16x2(acc[2], acc[3]);
   o.z = pack_bf16x2(acc[4], acc[5]); o.w = pack_bf16x2(acc[6], acc[7]);
-  reinterpret_cast<uint4*>(out)[idx] = o;
+  __nv_bfloat16* dst = out + ((static_cast<size_t>(b) * oh * ow + pix) * D) + threadIdx.x * 8;
+  asm volatile("st.global.cs.v4.b32 [%0], {%1, %2, %3, %4};" ::"l"(dst), "r"(o.x), "r"(o.y), "r"(o.z), "r"(o.w) : "memory");
+}
+
+// Integer up-sampling (S = 2 or 4).  Every output pixel of source cell (y, x) only needs the 3x3
+// token neighbourhood of that cell, so one thread loads it once for its 8 channels (from L1/L2,
+// each token row is touched ~9x instead of 4*S*S times) and emits all S*S outputs of the cell.
+// Weights follow ATen exactly: dst row S*y+a has src = y + fa, fa = (a + .5)/S - .5; fa < 0 blends
+// rows (y-1, y) with l = 1 + fa, fa > 0 blends (y, y+1) with l = fa; at the top/left border ATen
+// clamps src to 0 (weight 1 on row 0), at the bottom/right it blends row Gh-1 with itself.
+// blockDim = (D/8, kUpCells), gridDim = (ceil(Gh*Gw / kUpCells), B).
+constexpr int kUpCells = 2;
+
+template <int S>
+__global__ void __launch_bounds__(512)
+upsample_taps_kernel(const float* __restrict__ xres, __nv_bfloat16* __restrict__ out, int N, int D, int Gh, int Gw) {
+  const int cell = blockIdx.x * kUpCells + threadIdx.y;
+  if (cell >= Gh * Gw) return;
+  const int b = blockIdx.y;
+  const int y = cell / Gw, x = cell - y * Gw;
+  const int yy[3] = {max(y - 1, 0), y, min(y + 1, Gh - 1)};
+  const int xx[3] = {max(x - 1, 0), x, min(x + 1, Gw - 1)};
+  const float* base = xres + (static_cast<size_t>(b) * N + 1) * D + threadIdx.x * 8;
+  float w[3][3][8];
+#pragma unroll
+  for (int r = 0; r < 3; ++r)
+#pragma unroll
+    for (int c = 0; c < 3; ++c) {
+      const float4* p = reinterpret_cast<const float4*>(base + static_cast<size_t>(yy[r] * Gw + xx[c]) * D);
+      const float4 lo = __ldg(p), hi = __ldg(p + 1);
+      w[r][c][0] = lo.x; w[r][c][1] = lo.y; w[r][c][2] = lo.z; w[r][c][3] = lo.w;
+      w[r][c][4] = hi.x; w[r][c][5] = hi.y; w[r][c][6] = hi.z; w[r][c][7] = hi.w;
+    }
+  const int ow = Gw * S;
+  __nv_bfloat16* obase = out + ((static_cast<size_t>(b) * Gh * S + static_cast<size_t>(y) * S) * ow + static_cast<size_t>(x) * S) * D +
+                         threadIdx.x * 8;
+#pragma unroll
+  for (int a = 0; a < S; ++a) {
+    constexpr float inv = 1.0f / S;
+    const float fa = (a + 0.5f) * inv - 0.5f;
+    const int r0 = fa < 0.f ? 0 : 1;
+    const float ly = fa < 0.f ? (y == 0 ? 1.0f : 1.0f + fa) : fa;
+#pragma unroll
+    for (int bb = 0; bb < S; ++bb) {
+      const float fb = (bb + 0.5f) * inv - 0.5f;
+      const int c0 = fb < 0.f ? 0 : 1;
+      const float lx = fb < 0.f ? (x == 0 ? 1.0f : 1.0f + fb) : fb;
+      const float w00 = (1.f - ly) * (1.f - lx), w01 = (1.f - ly) * lx, w10 = ly * (1.f - lx), w11 = ly * lx;
+      float acc[8];
+#pragma unroll
+      for (int e = 0; e < 8; ++e)
+        acc[e] = w00 * w[r0][c0][e] + w01 * w[r0][c0 + 1][e] + w10 * w[r0 + 1][c0][e] + w11 * w[r0 + 1][c0 + 1][e];
+      uint4 o;
+      o.x = pack_bf16x2(acc[0], acc[1]); o.y = pack_bf16x2(acc[2], acc[3]);
+      o.z = pack_bf16x2(acc[4], acc[5]); o.w = pack_bf16x2(acc[6], acc[7]);
+      __nv_bfloat16* dst = obase + (static_cast<size_t>(a) * ow + bb) * D;
+      asm volatile("st.global.cs.v4.b32 [%0], {%1, %2, %3, %4};" ::"l"(dst), "r"(o.x), "r"(o.y), "r"(o.z), "r"(o.w) : "memory");
+    }
+  }
 }
 
 }  // namespace ldit
