@@ -95,9 +95,14 @@ void ldit_set_gemm_tile_n(int bn);
  * 1 = independent CTAs (128 x BN tile).  Also settable with LDIT_GEMM_CTAS. */
 void ldit_set_gemm_cta_pair(int ctas);
 
-/* Tuning knob: 0 (default) = tcgen05/TMEM attention kernel; 1 = the warp-level mma.sync
- * variant kept for comparison.  Also settable with LDIT_ATTN_IMPL. */
+/* Tuning knob: 0 (default) = persistent ping-pong tcgen05/TMEM attention kernel; 1 = the
+ * warp-level mma.sync variant and 2 = the one-tile-per-CTA tcgen05 variant, both kept for
+ * comparison.  Also settable with LDIT_ATTN_IMPL. */
 void ldit_set_attention_impl(int impl);
+
+/* Experiments only: when non-NULL, the default attention kernel records clock64() stamps of its
+ * softmax phases into this device buffer of gridDim*2*16*8 int64.  NULL switches it off. */
+void ldit_debug_attention_timeline(void* device_buffer);
 
 /* Number of kernels the library has enqueued since load / last reset (for gpu_launches). */
 unsigned long long ldit_launch_count(void);

@@ -1,0 +1,422 @@
+// Persistent, ping-pong tcgen05 attention for sm_100a (head_dim 64):
+//     ctx = softmax(q k^T / 8 + bias) v      per (image, head)          HF:249-306 / HF:310-368
+// reading Q/K/V in place from the fused QKV GEMM output [B, N, 3D] and writing the
+// merged-heads context [B, N, D] (HF:365-367).
+//
+// One CTA per SM loops over work items (image, head, pair of 128-query tiles).  Both tiles of a
+// pair share the K/V tiles that stream through a 2-stage smem ring; each tile belongs to one
+// softmax warpgroup that owns 256 TMEM columns:
+//   warps 0-3   softmax warpgroup 0  (thread <-> query row <-> TMEM lane)
+//   warps 4-7   softmax warpgroup 1
+//   warp  8     TMA producer + TMEM allocator (warp-uniform loop, one elected lane issues)
+//   warp  9     MMA issuer                    (warp-uniform loop, one elected lane issues)
+// K/V tiles hold at most 128 keys (kv_tile = 16 * NCH, NCH <= 8), so that a whole row of
+//   S = Q K^T   (tcgen05.mma SS, fp32 [128 x kv_tile] in TMEM columns [0, kv_tile))
+// fits in the registers of the thread that owns the row: ONE TMEM read per tile, then row max,
+// exp2 and row sum entirely in registers.  P goes back to TMEM as packed bf16 over columns
+// [0, kv_tile/2) and is the A operand of
+//   O += P V    (tcgen05.mma TS, V consumed as an MN-major smem operand exactly as it sits in
+//                the QKV buffer; O = fp32 [128 x 64] accumulates in TMEM columns [128, 192)).
+// When the running row max moves between tiles the warpgroup rescales O in place (TMEM load /
+// multiply / store) before it releases P -- the online-softmax recurrence without keeping O in
+// registers.  The issuer chains  O_g += P_g V(t)  and  S_g = Q_g K(t+1)^T  back to back, so a
+// warpgroup's next scores are being computed while the other warpgroup is in its exponentials.
+// The relative-position bias is gathered in-tile from a per-head table in smem with the index
+// rule of HF:522-544.
+#pragma once
+
+#include "ptx.cuh"
+
+namespace ldit {
+
+struct AttnP2Args {
+  __nv_bfloat16* ctx;       // [B*N, D]
+  const float* bias_table;  // [heads, T] fp32 or nullptr
+  int B, N, heads, D;
+  int Gh, Gw, T;
+  int kv_tile, n_kv_tiles, n_qpairs, num_items;
+  float scale_log2e;
+  long long* dbg;           // optional timeline buffer [gridDim][2][16][8] of clock64 (experiments only)
+};
+
+constexpr int kA2Threads = 320;
+constexpr int kA2MaxKv = 128;
+constexpr int kA2KvBytes = kA2MaxKv * 128;  // 16 KB per K or V stage
+constexpr int kA2OCol = 128;
+constexpr int kA2WarpProducer = 8, kA2WarpMma = 9;
+constexpr int kA2SmemTiles = 4 * 16384 + 4 * kA2KvBytes + 8 * 4096;  // Q[2][2] + K[2] + V[2] + per-warp output staging = 160 KB
+constexpr int kA2NumBars = 20;
+
+// tcgen05.wait::ld that also ties the destination registers, so no use can be scheduled above it
+__device__ __forceinline__ void tmem_wait_ld16(uint32_t (&r)[16]) {
+  asm volatile("tcgen05.wait::ld.sync.aligned;"
+               : "+r"(r[0]), "+r"(r[1]), "+r"(r[2]), "+r"(r[3]), "+r"(r[4]), "+r"(r[5]), "+r"(r[6]), "+r"(r[7]),
+                 "+r"(r[8]), "+r"(r[9]), "+r"(r[10]), "+r"(r[11]), "+r"(r[12]), "+r"(r[13]), "+r"(r[14]), "+r"(r[15])
+               :: "memory");
+}
+__device__ __forceinline__ float a2_fmax3(float a, float b, float c) {
+  float d;
+  asm("max.f32 %0, %1, %2, %3;" : "=f"(d) : "f"(a), "f"(b), "f"(c));
+  return d;
+}
+__device__ __forceinline__ float a2_exp2(float x) {
+  float y;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+__device__ __forceinline__ void named_bar_sync(int id, int nthreads) {
+  asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory");
+}
+
+template <bool HAS_BIAS, int NCH>  // NCH = kv_tile / 16
+__global__ void __launch_bounds__(kA2Threads, 1)
+attention_pp_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmKV,
+                    const __grid_constant__ CUtensorMap tmO, const AttnP2Args a) {
+  constexpr int KVT = NCH * 16;
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint8_t* sQ = smem;                       // [qb][g] 16 KB each
+  uint8_t* sK = smem + 4 * 16384;           // [stage]
+  uint8_t* sV = sK + 2 * kA2KvBytes;        // [stage]
+  uint8_t* sOut = sV + 2 * kA2KvBytes;      // [softmax warp] 32 rows x 128 B, 128B-swizzled, for the TMA store of ctx
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + kA2SmemTiles);
+  uint64_t* q_full = bars + 0;    // [2]
+  uint64_t* q_empty = bars + 2;   // [2]
+  uint64_t* k_full = bars + 4;    // [2]
+  uint64_t* k_empty = bars + 6;   // [2]
+  uint64_t* v_full = bars + 8;    // [2]
+  uint64_t* v_empty = bars + 10;  // [2]
+  uint64_t* s_full = bars + 12;   // [2] per warpgroup: S complete (and every earlier MMA of the CTA)
+  uint64_t* p_full = bars + 14;   // [2] per warpgroup: P written, O rescaled (4 warp arrivals)
+  uint64_t* o_full = bars + 16;   // [2] per warpgroup: O of the item complete
+  uint64_t* o_done = bars + 18;   // [2] per warpgroup: O read back, TMEM columns reusable (4 warp arrivals)
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + kA2NumBars);
+  float* sTab = reinterpret_cast<float*>(bars + kA2NumBars + 2);  // [2][T] (one copy per warpgroup)
+  int* sCol = reinterpret_cast<int*>(sTab + (HAS_BIAS ? 2 * a.T : 0));
+
+  const int warp = __shfl_sync(0xffffffffu, static_cast<int>(threadIdx.x >> 5), 0);
+  const int lane = threadIdx.x & 31;
+  constexpr uint32_t kv_bytes = KVT * 128;
+
+  if (warp == kA2WarpMma && lane == 0) {
+    for (int i = 0; i < kA2NumBars; ++i) mbar_init(&bars[i], (i == 14 || i == 15 || i == 18 || i == 19) ? 4 : 1);
+    fence_barrier_init();
+    fence_proxy_async_smem();
+  }
+  if (warp == kA2WarpProducer) {
+    if (lane == 0) {
+      tma_prefetch_desc(&tmQ);
+      tma_prefetch_desc(&tmKV);
+      tma_prefetch_desc(&tmO);
+    }
+    tmem_alloc(tmem_slot, 512);
+    tmem_relinquish();
+  }
+  if constexpr (HAS_BIAS) {
+    for (int k = threadIdx.x; k < a.N; k += kA2Threads) {
+      const int p = k - 1;
+      sCol[k] = (k == 0) ? 0 : (p / a.Gw) * (2 * a.Gw - 1) + (p % a.Gw);
+    }
+  }
+  tcgen05_fence_before();
+  __syncthreads();
+  tcgen05_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+  const int T = a.n_kv_tiles;
+
+  if (warp == kA2WarpProducer) {
+    // ------------------------------------------------------------------ TMA producer
+    uint32_t it = 0, kcount = 0;
+    for (int item = blockIdx.x; item < a.num_items; item += gridDim.x, ++it) {
+      const int p = item % a.n_qpairs, bh = item / a.n_qpairs;
+      const int h = bh % a.heads, b = bh / a.heads;
+      const int nvalid = (256 * p + 128 < a.N) ? 2 : 1;
+      const uint32_t qb = it & 1, qph = (it >> 1) & 1;
+      mbar_wait(&q_empty[qb], qph ^ 1);
+      if (elect_one_sync()) {
+        mbar_arrive_expect_tx(&q_full[qb], 16384u * nvalid);
+        tma_load_3d(sQ + (qb * 2 + 0) * 16384, &tmQ, &q_full[qb], h * 64, 256 * p, b);
+        if (nvalid == 2) tma_load_3d(sQ + (qb * 2 + 1) * 16384, &tmQ, &q_full[qb], h * 64, 256 * p + 128, b);
+      }
+      __syncwarp();
+      for (int t = 0; t < T; ++t, ++kcount) {
+        const uint32_t ks = kcount & 1, kph = (kcount >> 1) & 1;
+        mbar_wait(&k_empty[ks], kph ^ 1);
+        if (elect_one_sync()) {
+          mbar_arrive_expect_tx(&k_full[ks], kv_bytes);
+          tma_load_3d(sK + ks * kA2KvBytes, &tmKV, &k_full[ks], a.D + h * 64, t * KVT, b);
+        }
+        __syncwarp();
+        mbar_wait(&v_empty[ks], kph ^ 1);
+        if (elect_one_sync()) {
+          mbar_arrive_expect_tx(&v_full[ks], kv_bytes);
+          tma_load_3d(sV + ks * kA2KvBytes, &tmKV, &v_full[ks], 2 * a.D + h * 64, t * KVT, b);
+        }
+        __syncwarp();
+      }
+    }
+  } else if (warp == kA2WarpMma) {
+    // ------------------------------------------------------------------ MMA issuer
+    constexpr uint32_t idesc_s = umma_idesc_bf16(128, KVT, 0, 0);
+    constexpr uint32_t idesc_o = umma_idesc_bf16(128, 64, 0, 1);  // B = V is MN-major
+    const uint64_t qdesc0 = umma_desc_kmajor_sw128(smem_u32(sQ));
+    const uint64_t kdesc0 = umma_desc_kmajor_sw128(smem_u32(sK));
+    const uint64_t vdesc0 = umma_desc_mnmajor_sw128(smem_u32(sV));
+    uint32_t it = 0, kcount = 0;
+    uint32_t pcnt[2] = {0, 0};   // p_full phases consumed per warpgroup
+    uint32_t icnt[2] = {0, 0};   // items processed per warpgroup (o_done phases)
+    auto issue_s = [&](int g, uint32_t qb, uint32_t ks) {
+      if (elect_one_sync()) {
+        const uint64_t qd = qdesc0 + static_cast<uint32_t>((qb * 2 + g) * (16384 >> 4));
+        const uint64_t kd = kdesc0 + static_cast<uint32_t>(ks * (kA2KvBytes >> 4));
+#pragma unroll
+        for (int k = 0; k < 4; ++k) umma_bf16_ss(tmem_base + g * 256, qd + 2 * k, kd + 2 * k, idesc_s, k != 0);
+        tcgen05_commit(&s_full[g]);
+      }
+      __syncwarp();
+    };
+    for (int item = blockIdx.x; item < a.num_items; item += gridDim.x, ++it) {
+      const int p = item % a.n_qpairs;
+      const int nvalid = (256 * p + 128 < a.N) ? 2 : 1;
+      const uint32_t qb = it & 1, qph = (it >> 1) & 1;
+      mbar_wait(&q_full[qb], qph);
+      {  // S(0) of both warpgroups
+        const uint32_t ks = kcount & 1, kph = (kcount >> 1) & 1;
+        mbar_wait(&k_full[ks], kph);
+#pragma unroll
+        for (int g = 0; g < 2; ++g) {
+          if (g < nvalid) {
+            if (icnt[g] > 0) mbar_wait(&o_done[g], (icnt[g] - 1) & 1);  // previous item's O has been read back
+            tcgen05_fence_after();
+            issue_s(g, qb, ks);
+          }
+        }
+        if (elect_one_sync()) tcgen05_commit(&k_empty[ks]);
+        __syncwarp();
+      }
+      for (int t = 0; t < T; ++t, ++kcount) {
+        const uint32_t ks = kcount & 1, kph = (kcount >> 1) & 1;
+        const uint32_t ks1 = (kcount + 1) & 1, kph1 = ((kcount + 1) >> 1) & 1;
+        mbar_wait(&v_full[ks], kph);
+        if (t + 1 < T) mbar_wait(&k_full[ks1], kph1);
+#pragma unroll
+        for (int g = 0; g < 2; ++g) {
+          if (g < nvalid) {
+            mbar_wait(&p_full[g], pcnt[g] & 1);
+            ++pcnt[g];
+            tcgen05_fence_after();
+            if (elect_one_sync()) {
+              const uint64_t vd = vdesc0 + static_cast<uint32_t>(ks * (kA2KvBytes >> 4));
+#pragma unroll
+              for (int k = 0; k < NCH; ++k)
+                umma_bf16_ts(tmem_base + g * 256 + kA2OCol, tmem_base + g * 256 + 8 * k, vd + 128 * k, idesc_o, (t | k) != 0);
+              if (t + 1 == T) tcgen05_commit(&o_full[g]);
+            }
+            __syncwarp();
+            if (t + 1 < T) issue_s(g, qb, ks1);   // in order behind P V: S may overwrite the P columns
+          }
+        }
+        if (elect_one_sync()) {
+          tcgen05_commit(&v_empty[ks]);
+          if (t + 1 < T) tcgen05_commit(&k_empty[ks1]);
+        }
+        __syncwarp();
+      }
+#pragma unroll
+      for (int g = 0; g < 2; ++g) if (g < nvalid) ++icnt[g];
+      if (elect_one_sync()) tcgen05_commit(&q_empty[qb]);    // everything that read this Q pair is done
+      __syncwarp();
+    }
+  } else {
+    // ------------------------------------------------------------------ softmax warpgroups
+    const int g = warp >> 2;
+    const int quarter = warp & 3;
+    const uint32_t lane_addr = tmem_base + g * 256 + (static_cast<uint32_t>(quarter * 32) << 16);
+    float* myTab = sTab + (HAS_BIAS ? g * a.T : 0);
+    const float sc = a.scale_log2e;
+    uint32_t scnt = 0, icnt = 0;
+    int cur_h = -1;
+    for (int item = blockIdx.x; item < a.num_items; item += gridDim.x) {
+      const int p = item % a.n_qpairs, bh = item / a.n_qpairs;
+      const int h = bh % a.heads, b = bh / a.heads;
+      const int nvalid = (256 * p + 128 < a.N) ? 2 : 1;
+      if (g >= nvalid) continue;
+      const int row0 = 256 * p + 128 * g;
+      const int q = row0 + quarter * 32 + lane;          // token index inside the image
+      const bool warp_active = (row0 + quarter * 32) < a.N;
+      const bool rec = a.dbg != nullptr && quarter == 0 && lane == 0 && icnt < 16;
+      long long* tl = rec ? a.dbg + ((static_cast<size_t>(blockIdx.x) * 2 + g) * 16 + icnt) * 8 : nullptr;
+      if (rec) tl[0] = clock64();
+      int rowterm = 0;
+      if constexpr (HAS_BIAS) {
+        if (h != cur_h) {  // (re)load this head's table; 128 threads of the warpgroup
+          named_bar_sync(1 + g, 128);
+          const float* tab = a.bias_table + static_cast<size_t>(h) * a.T;
+          for (int i = quarter * 32 + lane; i < a.T; i += 128) myTab[i] = tab[i] * 1.4426950408889634f;
+          named_bar_sync(1 + g, 128);
+          cur_h = h;
+        }
+        if (q >= 1) { const int pp = q - 1; rowterm = (pp / a.Gw + a.Gh - 1) * (2 * a.Gw - 1) + (pp % a.Gw) + a.Gw - 1; }
+      }
+      float m_run = -INFINITY, l_run = 0.f;
+
+      for (int t = 0; t < T; ++t, ++scnt) {
+        const int k0 = t * KVT;
+        const int valid = min(KVT, a.N - k0);   // keys of this tile that exist
+        mbar_wait(&s_full[g], scnt & 1);
+        tcgen05_fence_after();
+        if (rec && t == 0) tl[1] = clock64();
+        if (warp_active) {
+          // ---- the whole row of S into registers: NCH loads in flight, one wait each
+          uint32_t s[NCH][16];
+#pragma unroll
+          for (int c = 0; c < NCH; ++c) tmem_ld_32x32b_x16(lane_addr + c * 16, s[c]);
+#pragma unroll
+          for (int c = 0; c < NCH; ++c) tmem_wait_ld16(s[c]);
+          // ---- logits in log2 units (+ bias), keys past the end of the image masked out
+          if (HAS_BIAS || valid < KVT) {
+#pragma unroll
+            for (int c = 0; c < NCH; ++c)
+#pragma unroll
+              for (int i = 0; i < 16; ++i) {
+                const int kk = c * 16 + i;
+                float v = __uint_as_float(s[c][i]);
+                if constexpr (HAS_BIAS) {
+                  v *= sc;
+                  if (kk < valid && q < a.N) {
+                    const int kc = k0 + kk;
+                    int idx;
+                    if (q == 0) idx = (kc == 0) ? a.T - 1 : a.T - 3;
+                    else if (kc == 0) idx = a.T - 2;
+                    else idx = rowterm - sCol[kc];
+                    v += myTab[idx];
+                  }
+                }
+                s[c][i] = __float_as_uint(kk < valid ? v : -INFINITY);
+              }
+          }
+          // ---- row max
+          float mx[4] = {-INFINITY, -INFINITY, -INFINITY, -INFINITY};
+#pragma unroll
+          for (int c = 0; c < NCH; ++c) {
+#pragma unroll
+            for (int i = 0; i < 16; i += 8) {
+              mx[0] = a2_fmax3(mx[0], __uint_as_float(s[c][i]), __uint_as_float(s[c][i + 1]));
+              mx[1] = a2_fmax3(mx[1], __uint_as_float(s[c][i + 2]), __uint_as_float(s[c][i + 3]));
+              mx[2] = a2_fmax3(mx[2], __uint_as_float(s[c][i + 4]), __uint_as_float(s[c][i + 5]));
+              mx[3] = a2_fmax3(mx[3], __uint_as_float(s[c][i + 6]), __uint_as_float(s[c][i + 7]));
+            }
+          }
+          float mt = fmaxf(fmaxf(mx[0], mx[1]), fmaxf(mx[2], mx[3]));
+          if constexpr (!HAS_BIAS) mt *= sc;   // scale > 0: max commutes with it
+          const float m_new = fmaxf(m_run, mt);
+          const float alpha = a2_exp2(m_run - m_new);   // first tile: exp2(-inf) = 0
+          m_run = m_new;
+          // ---- rescale the O accumulated so far (every earlier MMA is complete: s_full covers them)
+          if (t > 0 && __any_sync(0xffffffffu, alpha != 1.0f)) {
+            uint32_t ob[16];
+#pragma unroll
+            for (int c = 0; c < 4; ++c) {
+              tmem_ld_32x32b_x16(lane_addr + kA2OCol + c * 16, ob);
+              tmem_wait_ld16(ob);
+#pragma unroll
+              for (int i = 0; i < 16; ++i) ob[i] = __float_as_uint(__uint_as_float(ob[i]) * alpha);
+              tmem_st_32x32b_x16(lane_addr + kA2OCol + c * 16, ob);
+            }
+          }
+          // ---- p = exp2(s - m), row sum, P -> TMEM as packed bf16 over columns [0, kv_tile/2)
+          const float neg_m = -m_new;
+          float ps[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+          for (int c = 0; c < NCH; ++c) {
+            uint32_t pk[8];
+#pragma unroll
+            for (int i = 0; i < 16; i += 4) {
+              float p0, p1, p2, p3;
+              if constexpr (HAS_BIAS) {
+                p0 = a2_exp2(__uint_as_float(s[c][i]) + neg_m);
+                p1 = a2_exp2(__uint_as_float(s[c][i + 1]) + neg_m);
+                p2 = a2_exp2(__uint_as_float(s[c][i + 2]) + neg_m);
+                p3 = a2_exp2(__uint_as_float(s[c][i + 3]) + neg_m);
+              } else {
+                p0 = a2_exp2(fmaf(__uint_as_float(s[c][i]), sc, neg_m));
+                p1 = a2_exp2(fmaf(__uint_as_float(s[c][i + 1]), sc, neg_m));
+                p2 = a2_exp2(fmaf(__uint_as_float(s[c][i + 2]), sc, neg_m));
+                p3 = a2_exp2(fmaf(__uint_as_float(s[c][i + 3]), sc, neg_m));
+              }
+              ps[0] += p0; ps[1] += p1; ps[2] += p2; ps[3] += p3;
+              pk[i >> 1] = pack_bf16x2(p0, p1);
+              pk[(i >> 1) + 1] = pack_bf16x2(p2, p3);
+            }
+            tmem_st_32x32b_x8(lane_addr + c * 8, pk);
+          }
+          l_run = l_run * alpha + ((ps[0] + ps[1]) + (ps[2] + ps[3]));
+          tcgen05_wait_st();
+        }
+        tcgen05_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&p_full[g]);
+      }
+
+      // ---- O of the item: normalise and store (merged heads)
+      if (rec) tl[2] = clock64();
+      mbar_wait(&o_full[g], icnt & 1);
+      tcgen05_fence_after();
+      if (rec) tl[3] = clock64();
+      if (warp_active) {
+        // 32 rows x 64 bf16 of this warp -> swizzled smem -> one TMA store (rows past N are clipped by
+        // the 3-D tensor map).  Row-per-thread global stores would cost 32 LSU tags per instruction.
+        const float inv = 1.0f / l_run;
+        uint8_t* stage = sOut + warp * 4096;
+        if (lane == 0) tma_store_wait_read<0>();   // the previous item's store has finished reading `stage`
+        __syncwarp();
+        uint32_t oa[16], ob[16];
+        tmem_ld_32x32b_x16(lane_addr + kA2OCol, oa);
+#pragma unroll
+        for (int c = 0; c < 4; c += 2) {
+          tmem_wait_ld16(oa);
+          tmem_ld_32x32b_x16(lane_addr + kA2OCol + (c + 1) * 16, ob);
+#pragma unroll
+          for (int j = 0; j < 2; ++j) {
+            uint4 v;
+            v.x = pack_bf16x2(__uint_as_float(oa[8 * j]) * inv, __uint_as_float(oa[8 * j + 1]) * inv);
+            v.y = pack_bf16x2(__uint_as_float(oa[8 * j + 2]) * inv, __uint_as_float(oa[8 * j + 3]) * inv);
+            v.z = pack_bf16x2(__uint_as_float(oa[8 * j + 4]) * inv, __uint_as_float(oa[8 * j + 5]) * inv);
+            v.w = pack_bf16x2(__uint_as_float(oa[8 * j + 6]) * inv, __uint_as_float(oa[8 * j + 7]) * inv);
+            *reinterpret_cast<uint4*>(stage + lane * 128 + (((2 * c + j) ^ (lane & 7)) << 4)) = v;
+          }
+          tmem_wait_ld16(ob);
+          if (c + 2 < 4) tmem_ld_32x32b_x16(lane_addr + kA2OCol + (c + 2) * 16, oa);
+#pragma unroll
+          for (int j = 0; j < 2; ++j) {
+            uint4 v;
+            v.x = pack_bf16x2(__uint_as_float(ob[8 * j]) * inv, __uint_as_float(ob[8 * j + 1]) * inv);
+            v.y = pack_bf16x2(__uint_as_float(ob[8 * j + 2]) * inv, __uint_as_float(ob[8 * j + 3]) * inv);
+            v.z = pack_bf16x2(__uint_as_float(ob[8 * j + 4]) * inv, __uint_as_float(ob[8 * j + 5]) * inv);
+            v.w = pack_bf16x2(__uint_as_float(ob[8 * j + 6]) * inv, __uint_as_float(ob[8 * j + 7]) * inv);
+            *reinterpret_cast<uint4*>(stage + lane * 128 + (((2 * (c + 1) + j) ^ (lane & 7)) << 4)) = v;
+          }
+        }
+        fence_proxy_async_smem();
+        __syncwarp();
+        if (lane == 0) {
+          tma_store_3d(&tmO, stage, h * 64, row0 + quarter * 32, b);
+          tma_store_commit();
+        }
+      }
+      tcgen05_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&o_done[g]);
+      if (rec) tl[4] = clock64();
+      ++icnt;
+    }
+  }
+
+  if (warp < 8 && lane == 0) tma_store_wait<0>();   // smem must outlive the last ctx stores
+  __syncwarp();
+  tcgen05_fence_before();
+  __syncthreads();
+  if (warp == kA2WarpProducer) tmem_dealloc(tmem_base, 512);
+}
+
+}  // namespace ldit

@@ -8,6 +8,7 @@
 #include "../../include/ldit.h"
 #include "attention_mma.cuh"
 #include "attention_tc.cuh"
+#include "attention_tc2.cuh"
 #include "gemm.cuh"
 #include "rowwise.cuh"
 
@@ -56,6 +57,10 @@ int make_tmap_bf16_2d(CUtensorMap* tm, const void* ptr, uint64_t rows, uint64_t 
 
 // qkv viewed as [B, N, 3D] bf16: box [1, box_rows, 64 cols], 128-byte swizzle.  The image is its
 // own dimension so that rows past the end of an image read as zero instead of the next image.
+int make_tmap_qkv_3d(CUtensorMap* tm, const void* ptr, uint64_t B, uint64_t N, uint64_t cols, uint32_t box_rows);
+int make_tmap_rows_3d(CUtensorMap* tm, const void* ptr, uint64_t B, uint64_t N, uint64_t cols, uint32_t box_rows) {
+  return make_tmap_qkv_3d(tm, ptr, B, N, cols, box_rows);
+}
 int make_tmap_qkv_3d(CUtensorMap* tm, const void* ptr, uint64_t B, uint64_t N, uint64_t cols, uint32_t box_rows) {
   EncodeTiledFn fn = encode_fn();
   if (!fn) return LDIT_E_NO_DRIVER;
@@ -69,7 +74,8 @@ int make_tmap_qkv_3d(CUtensorMap* tm, const void* ptr, uint64_t B, uint64_t N, u
   return r == CUDA_SUCCESS ? 0 : 10000 + static_cast<int>(r);
 }
 
-std::atomic<int> g_attn_impl{-1};  // 0 = tcgen05 (default), 1 = mma.sync variant
+long long* g_attn_dbg = nullptr;  // experiments only: device buffer for the attention timeline
+std::atomic<int> g_attn_impl{-1};  // 0 = persistent ping-pong tcgen05 (default), 1 = mma.sync, 2 = one-tile-per-CTA tcgen05
 
 int num_sms() {
   static int sms = [] {
@@ -226,7 +232,8 @@ const char* ldit_error_string(int code) {
 }
 
 void ldit_set_gemm_tile_n(int bn) { g_forced_bn.store((bn == 128 || bn == 192 || bn == 256) ? bn : 0); }
-void ldit_set_attention_impl(int impl) { g_attn_impl.store(impl == 1 ? 1 : 0); }
+void ldit_debug_attention_timeline(void* device_buffer) { g_attn_dbg = static_cast<long long*>(device_buffer); }
+void ldit_set_attention_impl(int impl) { g_attn_impl.store((impl == 1 || impl == 2) ? impl : 0); }
 void ldit_set_gemm_cta_pair(int ctas) { g_cta_pair.store(ctas == 1 ? 1 : 2); }
 
 unsigned long long ldit_launch_count(void) { return g_launches.load(); }
@@ -328,10 +335,56 @@ int ldit_attention(const void* qkv, void* ctx, const void* bias_table, int B, in
   int impl = g_attn_impl.load(std::memory_order_relaxed);
   if (impl < 0) {
     const char* e = getenv("LDIT_ATTN_IMPL");
-    impl = (e && atoi(e) == 1) ? 1 : 0;
+    impl = e ? atoi(e) : 0;
+    if (impl != 1 && impl != 2) impl = 0;
     g_attn_impl.store(impl);
   }
   if (impl == 0) {
+    AttnP2Args a{};
+    a.ctx = static_cast<__nv_bfloat16*>(ctx);
+    a.bias_table = static_cast<const float*>(bias_table);
+    a.B = B; a.N = N; a.heads = heads; a.D = D; a.Gh = Gh; a.Gw = Gw; a.T = T;
+    a.n_kv_tiles = (N + kA2MaxKv - 1) / kA2MaxKv;
+    a.kv_tile = (((N + a.n_kv_tiles - 1) / a.n_kv_tiles) + 15) / 16 * 16;
+    a.n_qpairs = (N + 255) / 256;
+    a.num_items = B * heads * a.n_qpairs;
+    a.scale_log2e = scale_log2e;
+    a.dbg = g_attn_dbg;
+    CUtensorMap tmQ, tmKV, tmO;
+    int rc = make_tmap_qkv_3d(&tmQ, qkv, B, N, 3 * D, 128);
+    if (rc) return rc;
+    rc = make_tmap_qkv_3d(&tmKV, qkv, B, N, 3 * D, a.kv_tile);
+    if (rc) return rc;
+    rc = make_tmap_rows_3d(&tmO, ctx, B, N, D, 32);   // ctx as [B, N, D]: box 32 rows x 64 cols
+    if (rc) return rc;
+    size_t smem = 1024 + kA2SmemTiles + (kA2NumBars + 2) * 8;
+    if (bias_table) smem += (2 * static_cast<size_t>(T) + N) * 4;
+    if (smem > 227 * 1024) return LDIT_E_SHAPE;
+    const int grid = a.num_items < num_sms() ? a.num_items : num_sms();
+    const int nch = a.kv_tile / 16;
+    static size_t max_set[2][9] = {};
+    const int bi = bias_table ? 1 : 0;
+    cudaError_t e = cudaSuccess;
+#define LDIT_ATTN_CASE(NCH)                                                                                             \
+  case NCH:                                                                                                             \
+    if (smem > max_set[bi][NCH]) {                                                                                      \
+      e = bi ? cudaFuncSetAttribute(attention_pp_kernel<true, NCH>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)  \
+             : cudaFuncSetAttribute(attention_pp_kernel<false, NCH>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); \
+      if (e != cudaSuccess) return static_cast<int>(e);                                                                 \
+      max_set[bi][NCH] = smem;                                                                                          \
+    }                                                                                                                   \
+    if (bi) attention_pp_kernel<true, NCH><<<grid, kA2Threads, smem, st>>>(tmQ, tmKV, tmO, a);                               \
+    else attention_pp_kernel<false, NCH><<<grid, kA2Threads, smem, st>>>(tmQ, tmKV, tmO, a);                                 \
+    break;
+    switch (nch) {
+      LDIT_ATTN_CASE(1) LDIT_ATTN_CASE(2) LDIT_ATTN_CASE(3) LDIT_ATTN_CASE(4)
+      LDIT_ATTN_CASE(5) LDIT_ATTN_CASE(6) LDIT_ATTN_CASE(7) LDIT_ATTN_CASE(8)
+      default: return LDIT_E_SHAPE;
+    }
+#undef LDIT_ATTN_CASE
+    return check_launch();
+  }
+  if (impl == 2) {
     AttnTcArgs a{};
     a.ctx = static_cast<__nv_bfloat16*>(ctx);
     a.bias_table = static_cast<const float*>(bias_table);
