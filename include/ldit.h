@@ -103,6 +103,8 @@ void ldit_set_attention_impl(int impl);
 /* Experiments only: when non-NULL, the default attention kernel records clock64() stamps of its
  * softmax phases into this device buffer of gridDim*2*16*8 int64.  NULL switches it off. */
 void ldit_debug_attention_timeline(void* device_buffer);
+/* Same for the GEMM kernels: (num_SMs/2)*16*8 int64 (issuer and epilogue stamps per tile). */
+void ldit_debug_gemm_timeline(void* device_buffer);
 
 /* Number of kernels the library has enqueued since load / last reset (for gpu_launches). */
 unsigned long long ldit_launch_count(void);

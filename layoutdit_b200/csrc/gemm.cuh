@@ -42,6 +42,7 @@ struct GemmArgs {
   const float* posb;   // EPI_PATCH: [P, N] fp32 = position rows 1..P + conv bias
   int num_m_blocks, num_n_blocks;
   int dbg;             // experiments only (LDIT_GEMM_DBG): bit 0 = epilogue drains TMEM but stores nothing
+  long long* tl;       // experiments only: clock64 timeline [cluster][16 tiles][8] (leader CTA), or nullptr
 };
 
 constexpr int kBM = 128;  // rows per CTA
@@ -197,9 +198,13 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
       uint32_t phase = 0;
       int acc = 0;
       uint32_t acc_phase = 0;
-      for (int tile = cluster_id; tile < num_tiles; tile += num_clusters) {
+      int ti = 0;
+      for (int tile = cluster_id; tile < num_tiles; tile += num_clusters, ++ti) {
+        long long* tl = (g.tl != nullptr && lane == 0 && ti < 16) ? g.tl + (static_cast<size_t>(cluster_id) * 16 + ti) * 8 : nullptr;
+        if (tl) tl[0] = clock64();
         mbar_wait(&tempty_bar[acc], acc_phase ^ 1);
         tcgen05_fence_after();
+        if (tl) tl[1] = clock64();
         const uint32_t d_tmem = tmem_base + acc * kAccStride;
         for (int kb = 0; kb < nkb; ++kb) {
           mbar_wait(&full_bar[stage], phase);
@@ -221,7 +226,9 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
           }
           __syncwarp();
           if (++stage == S) { stage = 0; phase ^= 1; }
+          if (tl && kb == 0) tl[2] = clock64();
         }
+        if (tl) tl[3] = clock64();
         acc ^= 1;
         if (acc == 0) acc_phase ^= 1;
       }
@@ -257,11 +264,16 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
                       (tile / g.num_n_blocks) * Cfg::TILE_M + row_in_tile);
         }
       }
-      for (int tile = cluster_id; tile < num_tiles; tile += num_clusters) {
+      int ti = 0;
+      for (int tile = cluster_id; tile < num_tiles; tile += num_clusters, ++ti) {
         const int row0 = (tile / g.num_n_blocks) * Cfg::TILE_M + row_in_tile;
         const int col0 = (tile % g.num_n_blocks) * BN + half * (BN / 2);
+        long long* tl = (g.tl != nullptr && rank == 0 && ew == 0 && lane == 0 && ti < 16)
+                            ? g.tl + (static_cast<size_t>(cluster_id) * 16 + ti) * 8 : nullptr;
+        if (tl) tl[4] = clock64();
         mbar_wait(&tfull_bar[acc], acc_phase);
         tcgen05_fence_after();
+        if (tl) tl[5] = clock64();
         const uint32_t taddr = tmem_base + acc * kAccStride + half * (BN / 2) + (static_cast<uint32_t>(quarter * 32) << 16);
 #pragma unroll 1
         for (int c = 0; c < kChunks; ++c, ++gc) {
@@ -344,6 +356,7 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
             tma_store_commit();
           }
         }
+        if (tl) tl[6] = clock64();
         acc ^= 1;
         if (acc == 0) acc_phase ^= 1;
       }

@@ -74,6 +74,7 @@ int make_tmap_qkv_3d(CUtensorMap* tm, const void* ptr, uint64_t B, uint64_t N, u
   return r == CUDA_SUCCESS ? 0 : 10000 + static_cast<int>(r);
 }
 
+long long* g_gemm_tl = nullptr;   // experiments only: device buffer for the GEMM timeline
 long long* g_attn_dbg = nullptr;  // experiments only: device buffer for the attention timeline
 std::atomic<int> g_attn_impl{-1};  // 0 = persistent ping-pong tcgen05 (default), 1 = mma.sync, 2 = one-tile-per-CTA tcgen05
 
@@ -160,6 +161,7 @@ int launch_gemm_t(const void* A, const void* W, GemmArgs g, cudaStream_t st) {
   }
   static const int dbg = [] { const char* e = getenv("LDIT_GEMM_DBG"); return e ? atoi(e) : 0; }();
   g.dbg = dbg;
+  g.tl = g_gemm_tl;
   g.num_m_blocks = (g.M + Cfg::TILE_M - 1) / Cfg::TILE_M;
   g.num_n_blocks = (g.N + BN - 1) / BN;
   const int tiles = g.num_m_blocks * g.num_n_blocks;
@@ -232,6 +234,7 @@ const char* ldit_error_string(int code) {
 }
 
 void ldit_set_gemm_tile_n(int bn) { g_forced_bn.store((bn == 128 || bn == 192 || bn == 256) ? bn : 0); }
+void ldit_debug_gemm_timeline(void* device_buffer) { g_gemm_tl = static_cast<long long*>(device_buffer); }
 void ldit_debug_attention_timeline(void* device_buffer) { g_attn_dbg = static_cast<long long*>(device_buffer); }
 void ldit_set_attention_impl(int impl) { g_attn_impl.store((impl == 1 || impl == 2) ? impl : 0); }
 void ldit_set_gemm_cta_pair(int ctas) { g_cta_pair.store(ctas == 1 ? 1 : 2); }
