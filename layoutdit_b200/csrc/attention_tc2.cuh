@@ -47,13 +47,6 @@ constexpr int kA2WarpProducer = 8, kA2WarpMma = 9;
 constexpr int kA2SmemTiles = 4 * 16384 + 4 * kA2KvBytes + 8 * 4096;  // Q[2][2] + K[2] + V[2] + per-warp output staging = 160 KB
 constexpr int kA2NumBars = 20;
 
-// tcgen05.wait::ld that also ties the destination registers, so no use can be scheduled above it
-__device__ __forceinline__ void tmem_wait_ld16(uint32_t (&r)[16]) {
-  asm volatile("tcgen05.wait::ld.sync.aligned;"
-               : "+r"(r[0]), "+r"(r[1]), "+r"(r[2]), "+r"(r[3]), "+r"(r[4]), "+r"(r[5]), "+r"(r[6]), "+r"(r[7]),
-                 "+r"(r[8]), "+r"(r[9]), "+r"(r[10]), "+r"(r[11]), "+r"(r[12]), "+r"(r[13]), "+r"(r[14]), "+r"(r[15])
-               :: "memory");
-}
 __device__ __forceinline__ float a2_fmax3(float a, float b, float c) {
   float d;
   asm("max.f32 %0, %1, %2, %3;" : "=f"(d) : "f"(a), "f"(b), "f"(c));

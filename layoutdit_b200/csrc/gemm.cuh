@@ -10,16 +10,16 @@
 // otherwise) and each SM's shared-memory operand traffic halves.  CTAS = 1 is the single-CTA
 // 128 x BN variant of the same code.
 //
-// CTA = 128 + 256 threads, one CTA per SM, static round-robin tile scheduler over clusters:
-//   warp 10   TMA producer   (one lane, both CTAs): A/B tiles -> 128B-swizzled smem ring; all
-//             completion bytes are credited to the LEADER CTA's "full" barrier
-//   warp 11   MMA issuer     (one lane, leader CTA only): tcgen05.mma, accumulators
-//             double-buffered in TMEM; tcgen05.commit multicasts "slot free" / "accumulator ready"
-//             to both CTAs
-//   warp 9    TMEM allocator
-//   warps 0-7 epilogue (both CTAs, own 128 rows): tcgen05.ld -> registers -> bias / erf-GELU /
-//             layer-scale + residual -> swizzled smem staging -> TMA store (the residual tile
-//             arrives by TMA load into the same staging buffer, prefetched one chunk ahead)
+// CTA = 19 warps, one CTA per SM, static round-robin tile scheduler over clusters:
+//   warp 17     TMA producer   (one lane, both CTAs): A/B tiles -> 128B-swizzled smem ring; all
+//               completion bytes are credited to the LEADER CTA's "full" barrier
+//   warp 18     MMA issuer     (one lane, leader CTA only): tcgen05.mma, accumulators
+//               double-buffered in TMEM; tcgen05.commit multicasts "slot free" / "accumulator ready"
+//               to both CTAs
+//   warp 16     TMEM allocator
+//   warps 0-15  epilogue (both CTAs, own 128 rows; warp = TMEM lane quarter x column quarter):
+//               tcgen05.ld -> registers -> bias / erf-GELU / layer-scale -> swizzled smem staging
+//               -> TMA store (bf16 outputs) or TMA reduce-add into the fp32 residual stream
 //
 // Replaces the cuBLAS calls behind nn.Linear at HF:324-338 (QKV), HF:383 (+HF:488-492),
 // HF:429-430 and HF:442 (+HF:500-504), and the conv at HF:218 (as an im2col GEMM).
@@ -35,8 +35,8 @@ struct GemmArgs {
   int M, N, K;
   const float* bias;   // [N] or nullptr
   const float* scale;  // [N] layer-scale (EPI_SCALE_RESID) or nullptr (== 1)
-  const float* resid;  // fp32 [M, ldo] residual stream (EPI_SCALE_RESID); may alias out
-  void* out;           // bf16 [M, ldo] (EPI_BIAS, EPI_BIAS_GELU) or fp32 (EPI_SCALE_RESID, EPI_PATCH)
+  void* out;           // bf16 [M, ldo] (EPI_BIAS, EPI_BIAS_GELU); fp32 [M, ldo] written (EPI_PATCH) or
+                       // accumulated into (EPI_SCALE_RESID: the residual stream itself)
   int ldo;             // output row pitch in elements
   int P;               // EPI_PATCH: patches per image; GEMM row b*P+p -> token row b*(P+1)+1+p
   const float* posb;   // EPI_PATCH: [P, N] fp32 = position rows 1..P + conv bias
@@ -48,14 +48,18 @@ struct GemmArgs {
 constexpr int kBM = 128;  // rows per CTA
 constexpr int kBK = 64;   // 64 bf16 = one 128-byte swizzle row
 constexpr int kUmmaK = 16;
-constexpr int kGemmEpiWarps = 8;
-constexpr int kGemmThreads = 128 + kGemmEpiWarps * 32;
-// Warp roles.  The SM's warp arbiter favours the highest warp id on each scheduler, so the two
-// latency-critical single-lane roles (TMA producer, MMA issuer) get the highest ids and the
-// compute-heavy epilogue warps the lowest: a busy epilogue must never delay an MMA issue.
-constexpr int kWarpAlloc = kGemmEpiWarps + 1;     // 9
-constexpr int kWarpProducer = kGemmEpiWarps + 2;  // 10
-constexpr int kWarpMma = kGemmEpiWarps + 3;       // 11
+// Warp roles.  16 epilogue warps = 4 per SM sub-partition (a TMEM lane quarter is only reachable
+// from warps with warp_id % 4 == quarter): with fewer, the fixed latencies of the epilogue chain
+// (tcgen05.ld -> math -> st.shared -> proxy fence -> TMA store) are exposed and the tile time
+// is set by the epilogue instead of the tensor core.  The SM's warp arbiter favours the highest
+// warp id on each scheduler, so the two latency-critical single-lane roles (TMA producer, MMA
+// issuer) get the highest ids: a busy epilogue must never delay an MMA issue.
+constexpr int kGemmEpiWarps = 16;
+constexpr int kWarpAlloc = kGemmEpiWarps;         // 16
+constexpr int kWarpProducer = kGemmEpiWarps + 1;  // 17
+constexpr int kWarpMma = kGemmEpiWarps + 2;       // 18
+constexpr int kGemmThreads = (kGemmEpiWarps + 3) * 32;  // 608
+constexpr int kEpiCols = 16;     // accumulator columns per epilogue chunk (one tcgen05.ld.x16)
 constexpr int kAccStride = 256;  // TMEM columns between the two accumulator stages
 constexpr int kTmemCols = 512;
 constexpr int kMaxSmem = 232448;  // 227 KB opt-in limit per CTA
@@ -65,16 +69,18 @@ struct GemmCfg {
   static_assert(BN == 128 || BN == 192 || BN == 256, "BN");
   static_assert(CTAS == 1 || CTAS == 2, "CTAS");
   static constexpr bool OUT_F32 = (EPI == EPI_SCALE_RESID || EPI == EPI_PATCH);
-  static constexpr bool STAGED = (EPI != EPI_PATCH);  // patch rows are re-indexed per image: direct stores
   static constexpr int TILE_M = kBM * CTAS;
   static constexpr int A_BYTES = kBM * kBK * 2;
   static constexpr int B_ROWS = BN / CTAS;            // rows of W staged by each CTA
   static constexpr int B_BYTES = B_ROWS * kBK * 2;
   static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
-  // epilogue staging: per warp two buffers of 32 rows x 32 columns
-  static constexpr int CHUNK_BYTES = 32 * 32 * (OUT_F32 ? 4 : 2);
-  static constexpr int STAGING_BYTES = STAGED ? kGemmEpiWarps * 2 * CHUNK_BYTES : 0;
-  static constexpr int BAR_BYTES = 512;
+  // epilogue: warp (quarter, column group) owns 32 rows x BN/4 columns, in chunks of 16 columns;
+  // per warp two staging buffers of 32 rows x 16 columns (rows of 32 B bf16 / 64 B fp32)
+  static constexpr int CG_COLS = BN / 4;
+  static constexpr int CHUNKS = CG_COLS / kEpiCols;
+  static constexpr int CHUNK_BYTES = 32 * kEpiCols * (OUT_F32 ? 4 : 2);
+  static constexpr int STAGING_BYTES = kGemmEpiWarps * 2 * CHUNK_BYTES;
+  static constexpr int BAR_BYTES = 256;
   static constexpr int STAGES_FIT = (kMaxSmem - 1024 - BAR_BYTES - STAGING_BYTES) / STAGE_BYTES;
   static constexpr int STAGES = STAGES_FIT > 8 ? 8 : STAGES_FIT;
   static_assert(STAGES >= 3, "pipeline too shallow");
@@ -82,23 +88,69 @@ struct GemmCfg {
   static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + STAGING_BYTES + BAR_BYTES + 1024;  // + alignment slack
 };
 
-// exact-erf GELU (HF:430, ACT2FN["gelu"]) evaluated as x * Phi(x) with
-// Phi(x) = 0.5 erfc(-x / sqrt 2) from the Abramowitz-Stegun 7.1.26 rational form (|erf error|
-// < 1.5e-7, i.e. far below the bf16 rounding of the result): ~13 FMA-pipe ops + 2 MUFU, so
-// the epilogue stays under the MMA time of its tile -- erff() costs ~2x that.
-__device__ __forceinline__ float gelu_erf_fast(float x) {
-  const float z = fabsf(x) * 0.70710678118654752f;
-  float t;
-  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(t) : "f"(fmaf(0.3275911f, z, 1.0f)));
-  float p = fmaf(t, 0.5f * 1.061405429f, 0.5f * -1.453152027f);
-  p = fmaf(p, t, 0.5f * 1.421413741f);
-  p = fmaf(p, t, 0.5f * -0.284496736f);
-  p = fmaf(p, t, 0.5f * 0.254829592f);
-  p *= t;
-  float e;
-  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e) : "f"(z * z * -1.4426950408889634f));
-  const float h = p * e;  // 0.5 * erfc(|x| / sqrt 2)
-  return x * (x >= 0.f ? 1.0f - h : h);
+// exact-erf GELU (HF:430, ACT2FN["gelu"]):  gelu(x) = x Phi(x) = max(x, 0) - |x| * 0.5 erfc(|x| / sqrt 2).
+// 0.5 erfc(z) is evaluated as exp2(P(z)), P = degree-7 minimax fit of log2(0.5 erfc(z)) on
+// z in [0, 5] (z is clamped there: 0.5 erfc(5) = 7.7e-13, i.e. x Phi(x) for x < -7.07 is returned
+// as ~-5e-12 instead of something even smaller).  Evaluated in fp32 the result is within 1.5e-5
+// relative / 1.5e-6 absolute of the exact function -- under 1 % of a bf16 half-ulp, so the rounded
+// bf16 output is the one an erff()-based epilogue produces -- for 9 FMA-pipe ops and ONE MUFU per
+// element (erff() costs ~2x that, the rational A&S 7.1.26 form needs two MUFU).
+// Coefficients: Chebyshev-node least-squares fit, tools/fit_gelu_poly.py.
+// Two elements per instruction: Blackwell's packed fp32 pipe (FFMA2 / FMUL2 / FADD2) does the
+// Horner chain for a pair at the issue cost of one -- the epilogue warps share their schedulers
+// with the MMA issuer and the TMA producer, and every issue slot they do not take shortens the
+// main loop (measured: scalar GELU math stretched the MMA issue span of a tile by 14 %).
+__device__ __forceinline__ uint64_t f2_pack(float lo, float hi) {
+  uint64_t r;
+  asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(lo), "f"(hi));
+  return r;
+}
+__device__ __forceinline__ void f2_unpack(uint64_t v, float& lo, float& hi) {
+  asm("mov.b64 {%0, %1}, %2;" : "=f"(lo), "=f"(hi) : "l"(v));
+}
+__device__ __forceinline__ uint64_t f2_fma(uint64_t a, uint64_t b, uint64_t c) {
+  uint64_t d;
+  asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(d) : "l"(a), "l"(b), "l"(c));
+  return d;
+}
+__device__ __forceinline__ uint64_t f2_mul(uint64_t a, uint64_t b) {
+  uint64_t d;
+  asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b));
+  return d;
+}
+__device__ __forceinline__ uint64_t f2_add(uint64_t a, uint64_t b) {
+  uint64_t d;
+  asm("add.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b));
+  return d;
+}
+__device__ __forceinline__ uint64_t f2_splat(float c) { return f2_pack(c, c); }
+
+// P has no clamp: it decreases monotonically beyond the fitted range (P(z) < -40 for z > 5), so
+// 0.5 erfc(z) just keeps underflowing towards 0 as it should.
+struct GeluCoef {
+  uint64_t nk, c0, c1, c2, c3, c4, c5, c6, c7;
+  __device__ __forceinline__ GeluCoef()
+      : nk(f2_splat(-0.70710678118654752f)), c0(f2_splat(-1.000004768371582f)), c1(f2_splat(-1.627893328666687f)),
+        c2(f2_splat(-0.9177651405334473f)), c3(f2_splat(-0.15145094692707062f)), c4(f2_splat(0.03325735405087471f)),
+        c5(f2_splat(-0.005002959165722132f)), c6(f2_splat(0.0004494435270316899f)), c7(f2_splat(-1.794292256818153e-05f)) {}
+};
+__device__ __forceinline__ void gelu_erf_pair(float& x0, float& x1, const GeluCoef& k) {
+  const uint64_t nu = f2_pack(__uint_as_float(__float_as_uint(x0) | 0x80000000u),
+                              __uint_as_float(__float_as_uint(x1) | 0x80000000u));  // -|x|
+  const uint64_t z = f2_mul(nu, k.nk);                                              // |x| / sqrt 2
+  uint64_t p = f2_fma(z, k.c7, k.c6);
+  p = f2_fma(p, z, k.c5);
+  p = f2_fma(p, z, k.c4);
+  p = f2_fma(p, z, k.c3);
+  p = f2_fma(p, z, k.c2);
+  p = f2_fma(p, z, k.c1);
+  p = f2_fma(p, z, k.c0);
+  float p0, p1, h0, h1;
+  f2_unpack(p, p0, p1);
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(h0) : "f"(p0));  // 0.5 * erfc(|x| / sqrt 2)
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(h1) : "f"(p1));
+  const uint64_t y = f2_fma(nu, f2_pack(h0, h1), f2_pack(fmaxf(x0, 0.0f), fmaxf(x1, 0.0f)));
+  f2_unpack(y, x0, x1);
 }
 
 template <int BN, int EPI, int CTAS>
@@ -116,8 +168,7 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
   uint64_t* empty_bar = full_bar + S;
   uint64_t* tfull_bar = empty_bar + S;
   uint64_t* tempty_bar = tfull_bar + 2;
-  uint64_t* resid_bar = tempty_bar + 2;  // [kGemmEpiWarps][2]
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(resid_bar + 2 * kGemmEpiWarps);
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty_bar + 2);
 
   const int warp = __shfl_sync(0xffffffffu, static_cast<int>(threadIdx.x >> 5), 0);  // provably warp-uniform
   const int lane = threadIdx.x & 31;
@@ -128,7 +179,7 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
   if (warp == kWarpProducer && lane == 0) {
     tma_prefetch_desc(&tmA);
     tma_prefetch_desc(&tmB);
-    if constexpr (Cfg::STAGED) tma_prefetch_desc(&tmC);
+    if constexpr (EPI != EPI_PATCH) tma_prefetch_desc(&tmC);
   }
   if (warp == kWarpMma && lane == 0) {
     for (int i = 0; i < S; ++i) {
@@ -139,7 +190,6 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
       mbar_init(&tfull_bar[i], 1);
       mbar_init(&tempty_bar[i], kGemmEpiWarps * CTAS);
     }
-    for (int i = 0; i < 2 * kGemmEpiWarps; ++i) mbar_init(&resid_bar[i], 1);
     fence_barrier_init();
     fence_proxy_async_smem();
   }
@@ -234,13 +284,27 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
       }
     }
   } else if (warp < kGemmEpiWarps) {
-    const int ew = warp;
+    // ------------------------------------------------------------------------- epilogue
+    // warp -> (TMEM lane quarter, column group); thread <-> accumulator row; per chunk of 16
+    // columns: tcgen05.ld (the next chunk's load is already in flight) -> fused math in
+    // registers -> swizzled smem staging -> one TMA op per chunk issued by lane 0:
+    //   EPI_BIAS / EPI_BIAS_GELU  bf16 tile store
+    //   EPI_SCALE_RESID           fp32 tile REDUCE-ADD into the residual stream: x += scale * (acc + bias)
+    //                             is performed by the L2 atomic units, the residual is never
+    //                             loaded into the SM (every element has exactly one contributor,
+    //                             so the result is deterministic)
+    //   EPI_PATCH                 no TMA: rows are re-indexed per image, so the staged chunk is read
+    //                             back row-contiguously (4 lanes x 16 B per row) and written with the
+    //                             position / conv-bias rows added
     const int quarter = warp & 3;   // TMEM lane quarter this warp may access
-    const int half = ew >> 2;       // which half of the BN columns
-    constexpr int kChunks = BN / 2 / 32;
+    const int cgrp = warp >> 2;     // which quarter of the BN columns
+    constexpr int kChunks = Cfg::CHUNKS;
     int acc = 0;
     uint32_t acc_phase = 0;
     const int row_in_tile = static_cast<int>(rank) * kBM + quarter * 32;
+    uint8_t* my_stage = sStage + warp * 2 * Cfg::CHUNK_BYTES;
+    uint32_t gc = 0;  // chunks processed by this warp so far: staging buffer = gc & 1
+    const GeluCoef gelu_k;
 
     auto release_accumulator = [&](int a) {
       // all TMEM reads of this accumulator are done: hand it back to the (leader's) MMA warp
@@ -252,152 +316,146 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
       }
     };
 
-    if constexpr (Cfg::STAGED) {
-      uint8_t* my_stage = sStage + ew * 2 * Cfg::CHUNK_BYTES;
-      uint64_t* my_bar = resid_bar + ew * 2;
-      uint32_t gc = 0;  // chunks processed by this warp so far: buffer = gc & 1, residual phase = (gc >> 1) & 1
-      if constexpr (EPI == EPI_SCALE_RESID) {
-        if (lane == 0 && cluster_id < num_tiles) {  // residual of the very first chunk
-          const int tile = cluster_id;
-          mbar_arrive_expect_tx(&my_bar[0], Cfg::CHUNK_BYTES);
-          tma_load_2d(my_stage, &tmC, &my_bar[0], (tile % g.num_n_blocks) * BN + half * (BN / 2),
-                      (tile / g.num_n_blocks) * Cfg::TILE_M + row_in_tile);
+    int ti = 0;
+    for (int tile = cluster_id; tile < num_tiles; tile += num_clusters, ++ti) {
+      const int row0 = (tile / g.num_n_blocks) * Cfg::TILE_M + row_in_tile;
+      const int col0 = (tile % g.num_n_blocks) * BN + cgrp * Cfg::CG_COLS;
+      long long* tl = (g.tl != nullptr && rank == 0 && warp == 0 && lane == 0 && ti < 16)
+                          ? g.tl + (static_cast<size_t>(cluster_id) * 16 + ti) * 8 : nullptr;
+
+      // EPI_PATCH: this lane reads back rows (lane >> 2) + 8 i, 16-byte piece lane & 3
+      size_t p_orow[4];
+      int p_prow[4];
+      if constexpr (EPI == EPI_PATCH) {
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+          const int gm = row0 + (lane >> 2) + 8 * i;
+          const int b = gm / g.P, p = gm - b * g.P;
+          p_prow[i] = gm < g.M ? p : -1;
+          p_orow[i] = static_cast<size_t>(b) * (g.P + 1) + 1 + p;
         }
       }
-      int ti = 0;
-      for (int tile = cluster_id; tile < num_tiles; tile += num_clusters, ++ti) {
-        const int row0 = (tile / g.num_n_blocks) * Cfg::TILE_M + row_in_tile;
-        const int col0 = (tile % g.num_n_blocks) * BN + half * (BN / 2);
-        long long* tl = (g.tl != nullptr && rank == 0 && ew == 0 && lane == 0 && ti < 16)
-                            ? g.tl + (static_cast<size_t>(cluster_id) * 16 + ti) * 8 : nullptr;
-        if (tl) tl[4] = clock64();
-        mbar_wait(&tfull_bar[acc], acc_phase);
-        tcgen05_fence_after();
-        if (tl) tl[5] = clock64();
-        const uint32_t taddr = tmem_base + acc * kAccStride + half * (BN / 2) + (static_cast<uint32_t>(quarter * 32) << 16);
-#pragma unroll 1
-        for (int c = 0; c < kChunks; ++c, ++gc) {
-          uint8_t* buf = my_stage + (gc & 1) * Cfg::CHUNK_BYTES;
-          uint8_t* nbuf = my_stage + ((gc + 1) & 1) * Cfg::CHUNK_BYTES;
-          if (lane == 0) {
+
+      if (tl) tl[4] = clock64();
+      mbar_wait(&tfull_bar[acc], acc_phase);
+      tcgen05_fence_after();
+      if (tl) tl[5] = clock64();
+      const uint32_t taddr = tmem_base + acc * kAccStride + cgrp * Cfg::CG_COLS + (static_cast<uint32_t>(quarter * 32) << 16);
+      uint32_t r[2][16];
+      tmem_ld_32x32b_x16(taddr, r[0]);
+#pragma unroll
+      for (int c = 0; c < kChunks; ++c, ++gc) {
+        const int col = col0 + c * kEpiCols;
+        const bool col_ok = col < g.N;
+        uint32_t (&rc)[16] = r[c & 1];
+        // per-column operands of this chunk, requested before the TMEM wait
+        float4 b4[4], s4[4];
+        if constexpr (EPI != EPI_PATCH) {
+#pragma unroll
+          for (int j = 0; j < 4; ++j) {
+            b4[j] = (g.bias != nullptr && col_ok) ? __ldg(reinterpret_cast<const float4*>(g.bias + col) + j) : make_float4(0.f, 0.f, 0.f, 0.f);
+            if constexpr (EPI == EPI_SCALE_RESID)
+              s4[j] = (g.scale != nullptr && col_ok) ? __ldg(reinterpret_cast<const float4*>(g.scale + col) + j) : make_float4(1.f, 1.f, 1.f, 1.f);
+          }
+        }
+        tmem_wait_ld16(rc);
+        if (c + 1 < kChunks) tmem_ld_32x32b_x16(taddr + (c + 1) * kEpiCols, r[(c + 1) & 1]);
+        else release_accumulator(acc);
+        if (g.dbg & 1) continue;
+        uint8_t* buf = my_stage + (gc & 1) * Cfg::CHUNK_BYTES;
+
+        if constexpr (!Cfg::OUT_F32) {
+          float v[16];
+#pragma unroll
+          for (int j = 0; j < 4; ++j) {
+            f2_unpack(f2_add(f2_pack(__uint_as_float(rc[4 * j + 0]), __uint_as_float(rc[4 * j + 1])), f2_pack(b4[j].x, b4[j].y)),
+                      v[4 * j + 0], v[4 * j + 1]);
+            f2_unpack(f2_add(f2_pack(__uint_as_float(rc[4 * j + 2]), __uint_as_float(rc[4 * j + 3])), f2_pack(b4[j].z, b4[j].w)),
+                      v[4 * j + 2], v[4 * j + 3]);
+          }
+          if constexpr (EPI == EPI_BIAS_GELU) {
+            if (!(g.dbg & 8)) {
+#pragma unroll
+              for (int e = 0; e < 16; e += 2) gelu_erf_pair(v[e], v[e + 1], gelu_k);
+            }
+          }
+          uint4 o[2];
+#pragma unroll
+          for (int j = 0; j < 2; ++j) {
+            o[j].x = pack_bf16x2(v[8 * j + 0], v[8 * j + 1]);
+            o[j].y = pack_bf16x2(v[8 * j + 2], v[8 * j + 3]);
+            o[j].z = pack_bf16x2(v[8 * j + 4], v[8 * j + 5]);
+            o[j].w = pack_bf16x2(v[8 * j + 6], v[8 * j + 7]);
+          }
+          if (lane == 0) tma_store_wait_read<1>();  // the store of chunk gc-2 has finished reading this buffer
+          __syncwarp();
+          // bf16 rows of 32 B, 32B swizzle: 16-byte piece j of row `lane` sits at j ^ ((lane >> 2) & 1)
+          if (!(g.dbg & 16)) {
+#pragma unroll
+            for (int j = 0; j < 2; ++j)
+              *reinterpret_cast<uint4*>(buf + lane * 32 + ((j ^ ((lane >> 2) & 1)) << 4)) = o[j];
+          } else if (o[0].x == 0x12345678u && o[1].y == 0x9abcdef0u) {
+            *reinterpret_cast<uint4*>(buf) = o[0];
+          }
+        } else {
+          float4 o[4];
+#pragma unroll
+          for (int j = 0; j < 4; ++j) {
+            o[j] = make_float4(__uint_as_float(rc[4 * j + 0]), __uint_as_float(rc[4 * j + 1]),
+                               __uint_as_float(rc[4 * j + 2]), __uint_as_float(rc[4 * j + 3]));
             if constexpr (EPI == EPI_SCALE_RESID) {
-              // the other buffer was last read by the store of chunk gc-1: it must have drained
-              // before the next residual chunk is prefetched into it
-              tma_store_wait_read<0>();
-              int ntile = tile, nc = c + 1;
-              if (nc == kChunks) { ntile = tile + num_clusters; nc = 0; }
-              if (ntile < num_tiles) {
-                mbar_arrive_expect_tx(&my_bar[(gc + 1) & 1], Cfg::CHUNK_BYTES);
-                tma_load_2d(nbuf, &tmC, &my_bar[(gc + 1) & 1], (ntile % g.num_n_blocks) * BN + half * (BN / 2) + nc * 32,
-                            (ntile / g.num_n_blocks) * Cfg::TILE_M + row_in_tile);
-              }
-            } else {
-              tma_store_wait_read<1>();  // only the store of chunk gc-2 (this chunk's buffer) must have drained
+              o[j].x = s4[j].x * (o[j].x + b4[j].x);
+              o[j].y = s4[j].y * (o[j].y + b4[j].y);
+              o[j].z = s4[j].z * (o[j].z + b4[j].z);
+              o[j].w = s4[j].w * (o[j].w + b4[j].w);
             }
           }
-          uint32_t r[32];
-          tmem_ld_32x32b_x32(taddr + c * 32, r);
-          tcgen05_wait_ld();
-          if (c == kChunks - 1) release_accumulator(acc);
-          if (g.dbg & 1) continue;
-          __syncwarp();  // lane 0's wait_group.read above covers the whole warp's writes into buf
-          const int col = col0 + c * 32;
-          const bool col_ok = col < g.N;
           if constexpr (EPI == EPI_SCALE_RESID) {
-            mbar_wait(&my_bar[gc & 1], (gc >> 1) & 1);
-            // fp32 rows of 128 B, 128B swizzle: 16-byte chunk j of row `lane` sits at j ^ (lane & 7)
+            if (lane == 0) tma_store_wait_read<1>();
+          }
+          __syncwarp();  // EPI_PATCH: every lane has finished reading this buffer (chunk gc-2) long ago; keeps the warp converged
+          // fp32 rows of 64 B, 64B swizzle: 16-byte piece j of row `lane` sits at j ^ ((lane >> 1) & 3)
 #pragma unroll
-            for (int j = 0; j < 8; ++j) {
-              float4* p = reinterpret_cast<float4*>(buf + lane * 128 + ((j ^ (lane & 7)) << 4));
-              float4 x = *p;
-              float v0 = __uint_as_float(r[4 * j]), v1 = __uint_as_float(r[4 * j + 1]);
-              float v2 = __uint_as_float(r[4 * j + 2]), v3 = __uint_as_float(r[4 * j + 3]);
-              if (g.bias != nullptr && col_ok) {
-                const float4 b = __ldg(reinterpret_cast<const float4*>(g.bias + col) + j);
-                v0 += b.x; v1 += b.y; v2 += b.z; v3 += b.w;
-              }
-              if (g.scale != nullptr && col_ok) {
-                const float4 s = __ldg(reinterpret_cast<const float4*>(g.scale + col) + j);
-                x.x = fmaf(s.x, v0, x.x); x.y = fmaf(s.y, v1, x.y); x.z = fmaf(s.z, v2, x.z); x.w = fmaf(s.w, v3, x.w);
-              } else {
-                x.x += v0; x.y += v1; x.z += v2; x.w += v3;
-              }
-              *p = x;
-            }
-          } else {
-            // bf16 rows of 64 B, 64B swizzle: 16-byte chunk j of row `lane` sits at j ^ ((lane >> 1) & 3)
+          for (int j = 0; j < 4; ++j)
+            *reinterpret_cast<float4*>(buf + lane * 64 + ((j ^ ((lane >> 1) & 3)) << 4)) = o[j];
+        }
+
+        if constexpr (EPI == EPI_PATCH) {
+          // GEMM row b*P+p lands on token row b*(P+1)+1+p, plus position/conv-bias row p (HF:176-180)
+          __syncwarp();
+          if (col_ok) {
+            const int piece = lane & 3;
 #pragma unroll
-            for (int j = 0; j < 4; ++j) {
-              float v[8];
-#pragma unroll
-              for (int e = 0; e < 8; ++e) v[e] = __uint_as_float(r[8 * j + e]);
-              if (g.bias != nullptr && col_ok) {
-                const float4 b0 = __ldg(reinterpret_cast<const float4*>(g.bias + col) + 2 * j);
-                const float4 b1 = __ldg(reinterpret_cast<const float4*>(g.bias + col) + 2 * j + 1);
-                v[0] += b0.x; v[1] += b0.y; v[2] += b0.z; v[3] += b0.w;
-                v[4] += b1.x; v[5] += b1.y; v[6] += b1.z; v[7] += b1.w;
+            for (int i = 0; i < 4; ++i) {
+              const int rr = (lane >> 2) + 8 * i;
+              if (p_prow[i] >= 0) {
+                float4 x = *reinterpret_cast<const float4*>(buf + rr * 64 + ((piece ^ ((rr >> 1) & 3)) << 4));
+                const float4 pb = __ldg(reinterpret_cast<const float4*>(g.posb + static_cast<size_t>(p_prow[i]) * g.N + col) + piece);
+                x.x += pb.x; x.y += pb.y; x.z += pb.z; x.w += pb.w;
+                reinterpret_cast<float4*>(reinterpret_cast<float*>(g.out) + p_orow[i] * g.ldo + col)[piece] = x;
               }
-              if constexpr (EPI == EPI_BIAS_GELU) {
-#pragma unroll
-                for (int e = 0; e < 8; ++e) v[e] = gelu_erf_fast(v[e]);
-              }
-              uint4 o;
-              o.x = pack_bf16x2(v[0], v[1]);
-              o.y = pack_bf16x2(v[2], v[3]);
-              o.z = pack_bf16x2(v[4], v[5]);
-              o.w = pack_bf16x2(v[6], v[7]);
-              *reinterpret_cast<uint4*>(buf + lane * 64 + ((j ^ ((lane >> 1) & 3)) << 4)) = o;
             }
           }
-          if (!(g.dbg & 4)) fence_proxy_async_smem();  // generic-proxy smem writes -> visible to the TMA engine
+        } else {
+          fence_proxy_async_smem();  // generic-proxy smem writes -> visible to the TMA engine
           __syncwarp();
           if (lane == 0 && col_ok && !(g.dbg & 2)) {
-            tma_store_2d(&tmC, buf, col, row0);
+            if constexpr (EPI == EPI_SCALE_RESID) tma_reduce_add_2d(&tmC, buf, col, row0);
+            else tma_store_2d(&tmC, buf, col, row0);
             tma_store_commit();
           }
         }
-        if (tl) tl[6] = clock64();
-        acc ^= 1;
-        if (acc == 0) acc_phase ^= 1;
       }
+      if (tl) tl[6] = clock64();
+      acc ^= 1;
+      if (acc == 0) acc_phase ^= 1;
+    }
+    if constexpr (EPI != EPI_PATCH) {
       if (lane == 0) tma_store_wait<0>();  // smem must stay valid until the last stores have read it
-    } else {
-      // EPI_PATCH: GEMM row b*P+p lands on token row b*(P+1)+1+p, plus position/conv-bias row p
-      for (int tile = cluster_id; tile < num_tiles; tile += num_clusters) {
-        const int n0 = (tile % g.num_n_blocks) * BN;
-        const int row = (tile / g.num_n_blocks) * Cfg::TILE_M + row_in_tile + lane;
-        const bool row_ok = row < g.M;
-        mbar_wait(&tfull_bar[acc], acc_phase);
-        tcgen05_fence_after();
-        const uint32_t taddr = tmem_base + acc * kAccStride + half * (BN / 2) + (static_cast<uint32_t>(quarter * 32) << 16);
-        const int b = row / g.P, p = row - b * g.P;
-        const size_t orow = static_cast<size_t>(b) * (g.P + 1) + 1 + p;
-        const float* posb_row = g.posb + static_cast<size_t>(p) * g.N;
-#pragma unroll 1
-        for (int c = 0; c < kChunks; ++c) {
-          uint32_t r[32];
-          tmem_ld_32x32b_x32(taddr + c * 32, r);
-          tcgen05_wait_ld();
-          if (c == kChunks - 1) release_accumulator(acc);
-          const int col = n0 + half * (BN / 2) + c * 32;
-          if (row_ok && col < g.N) {
-            float* op = reinterpret_cast<float*>(g.out) + orow * g.ldo + col;
-#pragma unroll
-            for (int j = 0; j < 8; ++j) {
-              const float4 pb = __ldg(reinterpret_cast<const float4*>(posb_row + col) + j);
-              float4 x = make_float4(__uint_as_float(r[4 * j]) + pb.x, __uint_as_float(r[4 * j + 1]) + pb.y,
-                                     __uint_as_float(r[4 * j + 2]) + pb.z, __uint_as_float(r[4 * j + 3]) + pb.w);
-              reinterpret_cast<float4*>(op)[j] = x;
-            }
-          }
-        }
-        acc ^= 1;
-        if (acc == 0) acc_phase ^= 1;
-      }
     }
   }
 
-  __syncwarp();  // warps 0/1 ran single-lane loops: reconverge before the .aligned barriers
+  __syncwarp();  // single-lane branches above: reconverge before the .aligned barriers
   tcgen05_fence_before();
   if constexpr (CTAS == 2) {
     cluster_sync_all();  // the peer may still be signalling this CTA's barriers / reading its smem

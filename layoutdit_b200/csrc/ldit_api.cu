@@ -152,9 +152,9 @@ int launch_gemm_t(const void* A, const void* W, GemmArgs g, cudaStream_t st) {
   if (rc) return rc;
   rc = make_tmap_bf16_2d(&tmB, W, g.N, g.K, Cfg::B_ROWS);
   if (rc) return rc;
-  if (Cfg::STAGED) {  // epilogue staging: 32 x 32 element boxes, rows of 64 B (bf16) / 128 B (fp32)
-    rc = Cfg::OUT_F32 ? make_tmap_2d(&tmC, g.out, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, g.M, g.N, g.ldo, 32, 32, CU_TENSOR_MAP_SWIZZLE_128B)
-                      : make_tmap_2d(&tmC, g.out, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, g.M, g.N, g.ldo, 32, 32, CU_TENSOR_MAP_SWIZZLE_64B);
+  if (EPI != EPI_PATCH) {  // epilogue staging: 32-row x 16-column boxes, rows of 32 B (bf16) / 64 B (fp32)
+    rc = Cfg::OUT_F32 ? make_tmap_2d(&tmC, g.out, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, g.M, g.N, g.ldo, 32, kEpiCols, CU_TENSOR_MAP_SWIZZLE_64B)
+                      : make_tmap_2d(&tmC, g.out, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, g.M, g.N, g.ldo, 32, kEpiCols, CU_TENSOR_MAP_SWIZZLE_32B);
     if (rc) return rc;
   } else {
     tmC = tmA;
@@ -190,7 +190,7 @@ int launch_gemm(const void* A, const void* W, GemmArgs g, cudaStream_t st) {
   if (!A || !W || !g.out) return LDIT_E_NULL;
   if (g.M <= 0 || g.N <= 0 || g.K <= 0 || (g.N % 32) || (g.K % 8)) return LDIT_E_SHAPE;
   if (!aligned16(A) || !aligned16(W) || !aligned16(g.out) || !aligned16(g.bias) || !aligned16(g.scale) ||
-      !aligned16(g.resid) || !aligned16(g.posb))
+      !aligned16(g.posb))
     return LDIT_E_ALIGN;
   const int ctas = gemm_ctas();
   const int bn = pick_bn(g.M, g.N, ctas);
@@ -286,7 +286,6 @@ int ldit_gemm_bias_scale_residual(const void* A, const void* W, const void* bias
   g.M = M; g.N = N; g.K = K;
   g.bias = static_cast<const float*>(bias);
   g.scale = static_cast<const float*>(scale);
-  g.resid = static_cast<const float*>(x);
   g.out = x; g.ldo = N;
   return launch_gemm<EPI_SCALE_RESID>(A, W, g, static_cast<cudaStream_t>(stream));
 }
