@@ -6,7 +6,7 @@ import ctypes
 import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libldit_b200.so")
+LIB_PATH = os.environ.get("LDIT_LIB_PATH") or os.path.join(_HERE, "libldit_b200.so")  # override: A/B builds in experiments
 
 _c = ctypes
 _vp, _i, _f = _c.c_void_p, _c.c_int, _c.c_float

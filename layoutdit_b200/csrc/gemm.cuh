@@ -45,6 +45,18 @@ struct GemmArgs {
   long long* tl;       // experiments only: clock64 timeline [cluster][16 tiles][8] (leader CTA), or nullptr
 };
 
+#ifndef LDIT_EPI_BUFS
+#define LDIT_EPI_BUFS 1        // staging buffers per epilogue warp (1: the smem goes to the operand ring instead)
+#endif
+#ifndef LDIT_KSTEP
+#define LDIT_KSTEP 1           // 2: producer / MMA loops take two ring slots per iteration (measured slower: coarser turnaround)
+#endif
+#ifndef LDIT_EPI_ROLLED
+#define LDIT_EPI_ROLLED 0      // 1: chunk loop not unrolled (no cross-chunk overlap inside a warp)
+#endif
+#ifndef LDIT_EPI_SYNC_PAIRS
+#define LDIT_EPI_SYNC_PAIRS 0  // n > 0: __syncwarp() after every n GELU pairs (caps the ILP of the math burst)
+#endif
 constexpr int kBM = 128;  // rows per CTA
 constexpr int kBK = 64;   // 64 bf16 = one 128-byte swizzle row
 constexpr int kUmmaK = 16;
@@ -79,11 +91,11 @@ struct GemmCfg {
   static constexpr int CG_COLS = BN / 4;
   static constexpr int CHUNKS = CG_COLS / kEpiCols;
   static constexpr int CHUNK_BYTES = 32 * kEpiCols * (OUT_F32 ? 4 : 2);
-  static constexpr int STAGING_BYTES = kGemmEpiWarps * 2 * CHUNK_BYTES;
+  static constexpr int STAGING_BYTES = kGemmEpiWarps * LDIT_EPI_BUFS * CHUNK_BYTES;
   static constexpr int BAR_BYTES = 256;
   static constexpr int STAGES_FIT = (kMaxSmem - 1024 - BAR_BYTES - STAGING_BYTES) / STAGE_BYTES;
-  static constexpr int STAGES = STAGES_FIT > 8 ? 8 : STAGES_FIT;
-  static_assert(STAGES >= 3, "pipeline too shallow");
+  static constexpr int STAGES = (STAGES_FIT > 8 ? 8 : STAGES_FIT) & ~(LDIT_KSTEP - 1);  // even when the loops take slots in pairs
+  static_assert(STAGES >= 4, "pipeline too shallow");
   static_assert(A_BYTES % 1024 == 0 && B_BYTES % 1024 == 0, "swizzle-128B tiles must stay 1 KB aligned");
   static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + STAGING_BYTES + BAR_BYTES + 1024;  // + alignment slack
 };
@@ -139,16 +151,22 @@ __device__ __forceinline__ void gelu_erf_pair(float& x0, float& x1, const GeluCo
                               __uint_as_float(__float_as_uint(x1) | 0x80000000u));  // -|x|
   const uint64_t z = f2_mul(nu, k.nk);                                              // |x| / sqrt 2
   uint64_t p = f2_fma(z, k.c7, k.c6);
+#if !defined(LDIT_EXP_NO_HORNER)  // experiment only
   p = f2_fma(p, z, k.c5);
   p = f2_fma(p, z, k.c4);
   p = f2_fma(p, z, k.c3);
   p = f2_fma(p, z, k.c2);
   p = f2_fma(p, z, k.c1);
   p = f2_fma(p, z, k.c0);
+#endif
   float p0, p1, h0, h1;
   f2_unpack(p, p0, p1);
+#if defined(LDIT_EXP_NO_MUFU)   // experiment only (wrong numbers): same instruction count without the MUFU
+  h0 = p0 * 1.0001f; h1 = p1 * 1.0001f;
+#else
   asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(h0) : "f"(p0));  // 0.5 * erfc(|x| / sqrt 2)
   asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(h1) : "f"(p1));
+#endif
   const uint64_t y = f2_fma(nu, f2_pack(h0, h1), f2_pack(fmaxf(x0, 0.0f), fmaxf(x1, 0.0f)));
   f2_unpack(y, x0, x1);
 }
@@ -215,28 +233,42 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
   // instructions themselves are issued by one elected lane.  A single-lane loop costs ~80
   // dependent SASS instructions per k-block (ELECT + R2UR per operand) and starves the tensor
   // core whenever an epilogue warp shares the scheduler.
+  // Experiment knob LDIT_KSTEP=2: both loops take two ring slots per iteration.  Measured slower --
+  // the ring is then released and refilled 128 of K at a time and its turnaround latency, which is
+  // what limits the main loop under epilogue load, gets longer.
+  const int kstep = (LDIT_KSTEP == 2 && !(nkb & 1)) ? 2 : 1;
   if (warp == kWarpProducer) {
     int stage = 0;
     uint32_t phase = 0;
-    for (int tile = cluster_id; tile < num_tiles; tile += num_clusters) {
+    int pti = 0;
+    for (int tile = cluster_id; tile < num_tiles; tile += num_clusters, ++pti) {
       const int m0 = (tile / g.num_n_blocks) * Cfg::TILE_M + static_cast<int>(rank) * kBM;
       const int n0 = (tile % g.num_n_blocks) * BN + static_cast<int>(rank) * Cfg::B_ROWS;
-      for (int kb = 0; kb < nkb; ++kb) {
+      long long* ptl = (g.tl != nullptr && rank == 0 && lane == 0 && pti < 16) ? g.tl + (static_cast<size_t>(cluster_id) * 16 + pti) * 16 : nullptr;
+      long long wempty = 0;
+      for (int kb = 0; kb < nkb; kb += kstep) {
+        const long long w0 = ptl ? clock64() : 0;
         mbar_wait(&empty_bar[stage], phase ^ 1);
+        if (kstep == 2) mbar_wait(&empty_bar[stage + 1], phase ^ 1);
+        if (ptl) { wempty += clock64() - w0; if (kb + kstep >= nkb) ptl[9] = wempty; }
         if (elect_one_sync()) {
-          if constexpr (CTAS == 2) {
-            if (rank == 0) mbar_arrive_expect_tx(&full_bar[stage], Cfg::STAGE_BYTES * 2);
-            const uint32_t leader_full = mapa_shared(smem_u32(&full_bar[stage]), 0);
-            tma_load_2d_cg2(sA + stage * Cfg::A_BYTES, &tmA, leader_full, kb * kBK, m0);
-            tma_load_2d_cg2(sB + stage * Cfg::B_BYTES, &tmB, leader_full, kb * kBK, n0);
-          } else {
-            mbar_arrive_expect_tx(&full_bar[stage], Cfg::STAGE_BYTES);
-            tma_load_2d(sA + stage * Cfg::A_BYTES, &tmA, &full_bar[stage], kb * kBK, m0);
-            tma_load_2d(sB + stage * Cfg::B_BYTES, &tmB, &full_bar[stage], kb * kBK, n0);
+          for (int j = 0; j < kstep; ++j) {
+            const int st = stage + j;
+            if constexpr (CTAS == 2) {
+              if (rank == 0) mbar_arrive_expect_tx(&full_bar[st], Cfg::STAGE_BYTES * 2);
+              const uint32_t leader_full = mapa_shared(smem_u32(&full_bar[st]), 0);
+              tma_load_2d_cg2(sA + st * Cfg::A_BYTES, &tmA, leader_full, (kb + j) * kBK, m0);
+              tma_load_2d_cg2(sB + st * Cfg::B_BYTES, &tmB, leader_full, (kb + j) * kBK, n0);
+            } else {
+              mbar_arrive_expect_tx(&full_bar[st], Cfg::STAGE_BYTES);
+              tma_load_2d(sA + st * Cfg::A_BYTES, &tmA, &full_bar[st], (kb + j) * kBK, m0);
+              tma_load_2d(sB + st * Cfg::B_BYTES, &tmB, &full_bar[st], (kb + j) * kBK, n0);
+            }
           }
         }
         __syncwarp();
-        if (++stage == S) { stage = 0; phase ^= 1; }
+        stage += kstep;
+        if (stage >= S) { stage = 0; phase ^= 1; }
       }
     }
   } else if (warp == kWarpMma) {
@@ -250,35 +282,43 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
       uint32_t acc_phase = 0;
       int ti = 0;
       for (int tile = cluster_id; tile < num_tiles; tile += num_clusters, ++ti) {
-        long long* tl = (g.tl != nullptr && lane == 0 && ti < 16) ? g.tl + (static_cast<size_t>(cluster_id) * 16 + ti) * 8 : nullptr;
+        long long* tl = (g.tl != nullptr && lane == 0 && ti < 16) ? g.tl + (static_cast<size_t>(cluster_id) * 16 + ti) * 16 : nullptr;
         if (tl) tl[0] = clock64();
         mbar_wait(&tempty_bar[acc], acc_phase ^ 1);
         tcgen05_fence_after();
         if (tl) tl[1] = clock64();
         const uint32_t d_tmem = tmem_base + acc * kAccStride;
-        for (int kb = 0; kb < nkb; ++kb) {
+        long long wfull = 0;
+        for (int kb = 0; kb < nkb; kb += kstep) {
+          const long long w0 = tl ? clock64() : 0;
           mbar_wait(&full_bar[stage], phase);
+          if (kstep == 2) mbar_wait(&full_bar[stage + 1], phase);
+          if (tl) wfull += clock64() - w0;
           tcgen05_fence_after();
           if (elect_one_sync()) {
-            const uint64_t adesc = adesc0 + static_cast<uint32_t>(stage * (Cfg::A_BYTES >> 4));
-            const uint64_t bdesc = bdesc0 + static_cast<uint32_t>(stage * (Cfg::B_BYTES >> 4));
+            for (int j = 0; j < kstep; ++j) {
+              const int st = stage + j;
+              const uint64_t adesc = adesc0 + static_cast<uint32_t>(st * (Cfg::A_BYTES >> 4));
+              const uint64_t bdesc = bdesc0 + static_cast<uint32_t>(st * (Cfg::B_BYTES >> 4));
 #pragma unroll
-            for (int k = 0; k < kBK / kUmmaK; ++k) {
-              if constexpr (CTAS == 2) umma_bf16_ss_cg2(d_tmem, adesc + 2 * k, bdesc + 2 * k, idesc, (kb | k) != 0);
-              else umma_bf16_ss(d_tmem, adesc + 2 * k, bdesc + 2 * k, idesc, (kb | k) != 0);
+              for (int k = 0; k < kBK / kUmmaK; ++k) {
+                if constexpr (CTAS == 2) umma_bf16_ss_cg2(d_tmem, adesc + 2 * k, bdesc + 2 * k, idesc, (kb | j | k) != 0);
+                else umma_bf16_ss(d_tmem, adesc + 2 * k, bdesc + 2 * k, idesc, (kb | j | k) != 0);
+              }
+              // smem slot reusable (in both CTAs) once these MMAs have read it
+              if constexpr (CTAS == 2) tcgen05_commit_cg2(&empty_bar[st], 3); else tcgen05_commit(&empty_bar[st]);
             }
-            // smem slot reusable (in both CTAs) once these MMAs have read it
-            if constexpr (CTAS == 2) tcgen05_commit_cg2(&empty_bar[stage], 3); else tcgen05_commit(&empty_bar[stage]);
             // last k-block: the accumulator is complete (both CTAs' epilogues)
-            if (kb == nkb - 1) {
+            if (kb + kstep >= nkb) {
               if constexpr (CTAS == 2) tcgen05_commit_cg2(&tfull_bar[acc], 3); else tcgen05_commit(&tfull_bar[acc]);
             }
           }
           __syncwarp();
-          if (++stage == S) { stage = 0; phase ^= 1; }
+          stage += kstep;
+          if (stage >= S) { stage = 0; phase ^= 1; }
           if (tl && kb == 0) tl[2] = clock64();
         }
-        if (tl) tl[3] = clock64();
+        if (tl) { tl[3] = clock64(); tl[7] = wfull; }
         acc ^= 1;
         if (acc == 0) acc_phase ^= 1;
       }
@@ -302,7 +342,7 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
     int acc = 0;
     uint32_t acc_phase = 0;
     const int row_in_tile = static_cast<int>(rank) * kBM + quarter * 32;
-    uint8_t* my_stage = sStage + warp * 2 * Cfg::CHUNK_BYTES;
+    uint8_t* my_stage = sStage + warp * LDIT_EPI_BUFS * Cfg::CHUNK_BYTES;
     uint32_t gc = 0;  // chunks processed by this warp so far: staging buffer = gc & 1
     const GeluCoef gelu_k;
 
@@ -321,7 +361,7 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
       const int row0 = (tile / g.num_n_blocks) * Cfg::TILE_M + row_in_tile;
       const int col0 = (tile % g.num_n_blocks) * BN + cgrp * Cfg::CG_COLS;
       long long* tl = (g.tl != nullptr && rank == 0 && warp == 0 && lane == 0 && ti < 16)
-                          ? g.tl + (static_cast<size_t>(cluster_id) * 16 + ti) * 8 : nullptr;
+                          ? g.tl + (static_cast<size_t>(cluster_id) * 16 + ti) * 16 : nullptr;
 
       // EPI_PATCH: this lane reads back rows (lane >> 2) + 8 i, 16-byte piece lane & 3
       size_t p_orow[4];
@@ -342,12 +382,21 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
       if (tl) tl[5] = clock64();
       const uint32_t taddr = tmem_base + acc * kAccStride + cgrp * Cfg::CG_COLS + (static_cast<uint32_t>(quarter * 32) << 16);
       uint32_t r[2][16];
+#if LDIT_EPI_ROLLED
+#pragma unroll 1
+#else
       tmem_ld_32x32b_x16(taddr, r[0]);
 #pragma unroll
+#endif
       for (int c = 0; c < kChunks; ++c, ++gc) {
         const int col = col0 + c * kEpiCols;
         const bool col_ok = col < g.N;
+#if LDIT_EPI_ROLLED
+        uint32_t (&rc)[16] = r[0];
+        tmem_ld_32x32b_x16(taddr + c * kEpiCols, rc);
+#else
         uint32_t (&rc)[16] = r[c & 1];
+#endif
         // per-column operands of this chunk, requested before the TMEM wait
         float4 b4[4], s4[4];
         if constexpr (EPI != EPI_PATCH) {
@@ -359,10 +408,14 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
           }
         }
         tmem_wait_ld16(rc);
+#if LDIT_EPI_ROLLED
+        if (c + 1 == kChunks) release_accumulator(acc);
+#else
         if (c + 1 < kChunks) tmem_ld_32x32b_x16(taddr + (c + 1) * kEpiCols, r[(c + 1) & 1]);
         else release_accumulator(acc);
+#endif
         if (g.dbg & 1) continue;
-        uint8_t* buf = my_stage + (gc & 1) * Cfg::CHUNK_BYTES;
+        uint8_t* buf = my_stage + (gc & (LDIT_EPI_BUFS - 1)) * Cfg::CHUNK_BYTES;
 
         if constexpr (!Cfg::OUT_F32) {
           float v[16];
@@ -376,7 +429,12 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
           if constexpr (EPI == EPI_BIAS_GELU) {
             if (!(g.dbg & 8)) {
 #pragma unroll
-              for (int e = 0; e < 16; e += 2) gelu_erf_pair(v[e], v[e + 1], gelu_k);
+              for (int e = 0; e < 16; e += 2) {
+                gelu_erf_pair(v[e], v[e + 1], gelu_k);
+#if LDIT_EPI_SYNC_PAIRS > 0
+                if (((e / 2 + 1) % LDIT_EPI_SYNC_PAIRS) == 0) __syncwarp();
+#endif
+              }
             }
           }
           uint4 o[2];
@@ -387,7 +445,7 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
             o[j].z = pack_bf16x2(v[8 * j + 4], v[8 * j + 5]);
             o[j].w = pack_bf16x2(v[8 * j + 6], v[8 * j + 7]);
           }
-          if (lane == 0) tma_store_wait_read<1>();  // the store of chunk gc-2 has finished reading this buffer
+          if (lane == 0) tma_store_wait_read<LDIT_EPI_BUFS - 1>();  // the last store out of this buffer has finished reading it
           __syncwarp();
           // bf16 rows of 32 B, 32B swizzle: 16-byte piece j of row `lane` sits at j ^ ((lane >> 2) & 1)
           if (!(g.dbg & 16)) {
@@ -411,7 +469,7 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
             }
           }
           if constexpr (EPI == EPI_SCALE_RESID) {
-            if (lane == 0) tma_store_wait_read<1>();
+            if (lane == 0) tma_store_wait_read<LDIT_EPI_BUFS - 1>();
           }
           __syncwarp();  // EPI_PATCH: every lane has finished reading this buffer (chunk gc-2) long ago; keeps the warp converged
           // fp32 rows of 64 B, 64B swizzle: 16-byte piece j of row `lane` sits at j ^ ((lane >> 1) & 3)
