@@ -6,8 +6,9 @@
 
 * A "step" is one backbone forward over one batch of synthetic PubLayNet-shaped pages.
   N=1 workload (``base224``) = BASELINE.json configs[1]: DiT-base, batch 64, 224x224.
-* ``value``  : whole-job images/s with the page batch already resident in HBM (CUDA-graph
-  replay of the launch plan, per-step CUDA events, L2 flushed between steps).
+* ``value``  : whole-job images/s with the page batch already resident in HBM (the launch plan
+  enqueued with programmatic dependent launch, or ``--graph``: CUDA-graph replay; per-step CUDA
+  events, L2 flushed between steps).
 * ``e2e``    : the same metric through the public module call ``DiTBackbone(...)(x)`` with
   HOST inputs: every step copies its fp16 pages from pinned host memory and reads the p5 tap
   back to the host, inside the timed region.
@@ -155,6 +156,9 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--workload", default="base224", choices=sorted(WORKLOADS))
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-graph", dest="graph", action="store_false",
+                    help="enqueue the launch plan on the stream every step instead of replaying its captured CUDA graph "
+                         "(same device time within noise once the launches carry the PDL attribute, but exposed to host jitter)")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
 
@@ -182,11 +186,14 @@ def main():
 
     # random-init weights of the named architecture (HF init, seed 0), synthetic pages
     model = DiTBackbone(pretrained=False, config=cfg, state_dict=make_state_dict(cfg, 0, False),
-                        use_cuda_graph=True).to(dev).eval()
+                        use_cuda_graph=args.graph).to(dev).eval()
     eng = model._get_engine()
     pages = synthetic_pages(B, H, W, 1234 + rank)
-    x_dev = eng.graph_input_buffer(B, H, W, torch.float32)  # the captured graph's own input tensor
-    x_dev.copy_(pages)                                     # fp32, resident in HBM before the timed region
+    if args.graph:
+        x_dev = eng.graph_input_buffer(B, H, W, torch.float32)  # the captured graph's own input tensor
+        x_dev.copy_(pages)
+    else:
+        x_dev = pages.to(dev)                              # fp32, resident in HBM before the timed region
     flush = torch.empty(256 * 1024 * 1024, dtype=torch.uint8, device=dev)   # > 126 MB L2
 
     gathered = None
@@ -236,9 +243,10 @@ def main():
     host_in = [pages.to(torch.float16).pin_memory() for _ in range(2)]
     feats0 = model(x_dev)
     host_out = [torch.empty(p5_flat(feats0).shape, dtype=torch.bfloat16).pin_memory() for _ in range(2)]
-    e2e_model = DiTBackbone(pretrained=False, config=cfg, state_dict=None, use_cuda_graph=True).to(dev).eval()
+    e2e_model = DiTBackbone(pretrained=False, config=cfg, state_dict=None, use_cuda_graph=args.graph).to(dev).eval()
     e2e_model.dit.load_state_dict(model.dit.state_dict())
-    dev_in = e2e_model._get_engine().graph_input_buffer(B, H, W, torch.float16)
+    dev_in = (e2e_model._get_engine().graph_input_buffer(B, H, W, torch.float16) if args.graph
+              else torch.empty(B, 3, H, W, dtype=torch.float16, device=dev))
 
     def step_e2e(i):
         dev_in.copy_(host_in[i & 1], non_blocking=True)           # H2D of this step's pages
@@ -304,7 +312,8 @@ def main():
                                    f"random-init (HF init, seed 0) weights, 4 taps written",
                        "global_batch": world * B, "l2": "256 MiB buffer written between timed steps (outside the events)",
                        "parallelism": f"dp{world}", "gather": "p5 taps all-gathered over NCCL each step" if world > 1 else "none",
-                       "timing": "CUDA-graph replay; per-step CUDA events summed; max over ranks"},
+                       "timing": ("CUDA-graph replay" if args.graph else "stream launches with programmatic dependent launch (PDL)")
+                                 + "; per-step CUDA events summed; max over ranks"},
             "model_tflops": round(model_tflops, 1),
             "model_frac_of_peak": round(model_tflops / peaks["bf16_tflops"], 4),
             "flops_per_image": fl_img,

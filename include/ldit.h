@@ -95,6 +95,10 @@ void ldit_set_gemm_tile_n(int bn);
  * 1 = independent CTAs (128 x BN tile).  Also settable with LDIT_GEMM_CTAS. */
 void ldit_set_gemm_cta_pair(int ctas);
 
+/* 1 (default): kernels are launched with programmatic stream serialization (PDL) -- each kernel's
+ * prologue overlaps the tail of its predecessor in the stream; 0: plain stream order.  Also LDIT_PDL. */
+void ldit_set_pdl(int on);
+
 /* Tuning knob: 0 (default) = persistent ping-pong tcgen05/TMEM attention kernel; 1 = the
  * warp-level mma.sync variant and 2 = the one-tile-per-CTA tcgen05 variant, both kept for
  * comparison.  Also settable with LDIT_ATTN_IMPL. */

@@ -26,6 +26,7 @@ SIGNATURES = {
     "ldit_set_gemm_tile_n": (None, [_i]),
     "ldit_set_gemm_cta_pair": (None, [_i]),
     "ldit_set_attention_impl": (None, [_i]),
+    "ldit_set_pdl": (None, [_i]),
     "ldit_debug_attention_timeline": (None, [_vp]),
     "ldit_debug_gemm_timeline": (None, [_vp]),
     "ldit_launch_count": (_c.c_ulonglong, []),

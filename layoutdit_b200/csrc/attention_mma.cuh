@@ -42,6 +42,8 @@ __device__ __forceinline__ void att_load_tile(uint8_t* dst, const __nv_bfloat16*
 template <bool HAS_BIAS>
 __global__ void __launch_bounds__(128)
 attention_mma_kernel(const AttnArgs a) {
+  pdl_launch_dependents();
+  pdl_wait();
   extern __shared__ __align__(128) uint8_t smem[];
   uint8_t* sQ = smem;
   uint8_t* sK = smem + 8192;

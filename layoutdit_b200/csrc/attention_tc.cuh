@@ -50,6 +50,8 @@ __device__ __forceinline__ float fast_exp2(float x) {
 template <bool HAS_BIAS>
 __global__ void __launch_bounds__(kAtcThreads, 2)
 attention_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmKV, const AttnTcArgs a) {
+  pdl_launch_dependents();
+  pdl_wait();
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   uint8_t* sQ = smem;                                  // 128 x 128 B

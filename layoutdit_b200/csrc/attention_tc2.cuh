@@ -66,6 +66,7 @@ __global__ void __launch_bounds__(kA2Threads, 1)
 attention_pp_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmKV,
                     const __grid_constant__ CUtensorMap tmO, const AttnP2Args a) {
   constexpr int KVT = NCH * 16;
+  pdl_launch_dependents();
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   uint8_t* sQ = smem;                       // [qb][g] 16 KB each
@@ -114,6 +115,7 @@ attention_pp_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
   tcgen05_fence_before();
   __syncthreads();
   tcgen05_fence_after();
+  pdl_wait();   // prologue above touched no global memory; everything below may
   const uint32_t tmem_base = *tmem_slot;
   const int T = a.n_kv_tiles;
 

@@ -177,6 +177,7 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
                     const __grid_constant__ CUtensorMap tmC, const GemmArgs g) {
   using Cfg = GemmCfg<BN, EPI, CTAS>;
   constexpr int S = Cfg::STAGES;
+  pdl_launch_dependents();
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   uint8_t* sA = smem;
@@ -223,6 +224,7 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
   tcgen05_fence_before();
   if constexpr (CTAS == 2) cluster_sync_all(); else __syncthreads();
   tcgen05_fence_after();
+  pdl_wait();   // the prologue above touched no global memory; everything below may
   const uint32_t tmem_base = *tmem_slot;
 
   const int num_tiles = g.num_m_blocks * g.num_n_blocks;
@@ -498,7 +500,7 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
           fence_proxy_async_smem();  // generic-proxy smem writes -> visible to the TMA engine
           __syncwarp();
           if (lane == 0 && col_ok && !(g.dbg & 2)) {
-            if constexpr (EPI == EPI_SCALE_RESID) tma_reduce_add_2d(&tmC, buf, col, row0);
+            if constexpr (EPI == EPI_SCALE_RESID) { if (g.dbg & 32) tma_store_2d(&tmC, buf, col, row0); else tma_reduce_add_2d(&tmC, buf, col, row0); }
             else tma_store_2d(&tmC, buf, col, row0);
             tma_store_commit();
           }

@@ -4,6 +4,7 @@
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
+#include <utility>
 
 #include "../../include/ldit.h"
 #include "attention_mma.cuh"
@@ -87,6 +88,45 @@ int num_sms() {
   return sms;
 }
 
+std::atomic<int> g_pdl{-1};  // programmatic dependent launch: -1 = read LDIT_PDL once; 0 off; 1 on (default)
+bool pdl_enabled() {
+  int v = g_pdl.load(std::memory_order_relaxed);
+  if (v < 0) {
+    const char* e = getenv("LDIT_PDL");
+    v = (e && atoi(e) == 0) ? 0 : 1;
+    g_pdl.store(v);
+  }
+  return v != 0;
+}
+
+// Every kernel goes through here: cluster dimension + programmatic stream serialization (the
+// kernel may start its prologue while its predecessor in the stream drains; see ptx.cuh).
+template <typename... KArgs, typename... Args>
+cudaError_t launch_kernel(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st, int cluster, Args&&... args) {
+  cudaLaunchConfig_t cfg{};
+  cfg.gridDim = grid;
+  cfg.blockDim = block;
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = st;
+  cudaLaunchAttribute attr[2];
+  int n = 0;
+  if (cluster > 1) {
+    attr[n].id = cudaLaunchAttributeClusterDimension;
+    attr[n].val.clusterDim.x = cluster;
+    attr[n].val.clusterDim.y = 1;
+    attr[n].val.clusterDim.z = 1;
+    ++n;
+  }
+  if (pdl_enabled()) {
+    attr[n].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[n].val.programmaticStreamSerializationAllowed = 1;
+    ++n;
+  }
+  cfg.attrs = attr;
+  cfg.numAttrs = n;
+  return cudaLaunchKernelEx(&cfg, kernel, static_cast<KArgs>(std::forward<Args>(args))...);
+}
+
 inline bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15) == 0; }
 
 inline int check_launch() {
@@ -167,19 +207,7 @@ int launch_gemm_t(const void* A, const void* W, GemmArgs g, cudaStream_t st) {
   const int tiles = g.num_m_blocks * g.num_n_blocks;
   const int units = num_sms() / CTAS;
   const int grid = (tiles < units ? tiles : units) * CTAS;
-  cudaLaunchConfig_t cfg{};
-  cfg.gridDim = dim3(grid);
-  cfg.blockDim = dim3(kGemmThreads);
-  cfg.dynamicSmemBytes = Cfg::SMEM_BYTES;
-  cfg.stream = st;
-  cudaLaunchAttribute attr[1];
-  attr[0].id = cudaLaunchAttributeClusterDimension;
-  attr[0].val.clusterDim.x = CTAS;
-  attr[0].val.clusterDim.y = 1;
-  attr[0].val.clusterDim.z = 1;
-  cfg.attrs = attr;
-  cfg.numAttrs = 1;
-  cudaError_t e = cudaLaunchKernelEx(&cfg, gemm_tcgen05_kernel<BN, EPI, CTAS>, tmA, tmB, tmC, g);
+  cudaError_t e = launch_kernel(gemm_tcgen05_kernel<BN, EPI, CTAS>, dim3(grid), dim3(kGemmThreads), Cfg::SMEM_BYTES, st, CTAS, tmA, tmB, tmC, g);
   g_launches.fetch_add(1, std::memory_order_relaxed);
   if (e != cudaSuccess) { (void)cudaGetLastError(); return static_cast<int>(e); }
   return static_cast<int>(cudaGetLastError());
@@ -237,6 +265,7 @@ void ldit_set_gemm_tile_n(int bn) { g_forced_bn.store((bn == 128 || bn == 192 ||
 void ldit_debug_gemm_timeline(void* device_buffer) { g_gemm_tl = static_cast<long long*>(device_buffer); }
 void ldit_debug_attention_timeline(void* device_buffer) { g_attn_dbg = static_cast<long long*>(device_buffer); }
 void ldit_set_attention_impl(int impl) { g_attn_impl.store((impl == 1 || impl == 2) ? impl : 0); }
+void ldit_set_pdl(int on) { g_pdl.store(on ? 1 : 0); }
 void ldit_set_gemm_cta_pair(int ctas) { g_cta_pair.store(ctas == 1 ? 1 : 2); }
 
 unsigned long long ldit_launch_count(void) { return g_launches.load(); }
@@ -253,7 +282,7 @@ int ldit_layernorm(const void* x, const void* gamma, const void* beta, void* y, 
   const float* bf = static_cast<const float*>(beta);
   __nv_bfloat16* yb = static_cast<__nv_bfloat16*>(y);
 #define LDIT_LN_CASE(V) \
-  case V: layernorm_kernel<V><<<blocks, 256, 0, st>>>(xf, gf, bf, yb, rows, eps); break;
+  case V: launch_kernel(layernorm_kernel<V>, dim3(blocks), dim3(256), 0, st, 1, xf, gf, bf, yb, rows, eps); break;
   switch (D / 128) {
     LDIT_LN_CASE(1) LDIT_LN_CASE(2) LDIT_LN_CASE(3) LDIT_LN_CASE(4) LDIT_LN_CASE(5) LDIT_LN_CASE(6) LDIT_LN_CASE(7)
     LDIT_LN_CASE(8) LDIT_LN_CASE(9) LDIT_LN_CASE(10) LDIT_LN_CASE(11) LDIT_LN_CASE(12) LDIT_LN_CASE(13)
@@ -306,16 +335,16 @@ int ldit_patch_embed(const void* pixels, int pixel_dtype, const void* w, const v
   const unsigned blocks = static_cast<unsigned>((threads + 255) / 256);
   __nv_bfloat16* a = static_cast<__nv_bfloat16*>(scratch);
   switch (pixel_dtype) {
-    case LDIT_DTYPE_F32: im2col_kernel<float><<<blocks, 256, 0, st>>>(static_cast<const float*>(pixels), a, B, H, W, Gh, Gw); break;
-    case LDIT_DTYPE_F16: im2col_kernel<__half><<<blocks, 256, 0, st>>>(static_cast<const __half*>(pixels), a, B, H, W, Gh, Gw); break;
+    case LDIT_DTYPE_F32: launch_kernel(im2col_kernel<float>, dim3(blocks), dim3(256), 0, st, 1, static_cast<const float*>(pixels), a, B, H, W, Gh, Gw); break;
+    case LDIT_DTYPE_F16: launch_kernel(im2col_kernel<__half>, dim3(blocks), dim3(256), 0, st, 1, static_cast<const __half*>(pixels), a, B, H, W, Gh, Gw); break;
     case LDIT_DTYPE_BF16:
-      im2col_kernel<__nv_bfloat16><<<blocks, 256, 0, st>>>(static_cast<const __nv_bfloat16*>(pixels), a, B, H, W, Gh, Gw);
+      launch_kernel(im2col_kernel<__nv_bfloat16>, dim3(blocks), dim3(256), 0, st, 1, static_cast<const __nv_bfloat16*>(pixels), a, B, H, W, Gh, Gw);
       break;
     default: return LDIT_E_DTYPE;
   }
   int rc = check_launch();
   if (rc) return rc;
-  cls_rows_kernel<<<(B * (D / 4) + 255) / 256, 256, 0, st>>>(static_cast<const float*>(cls_pos), static_cast<float*>(x), B, P + 1, D);
+  launch_kernel(cls_rows_kernel, dim3((B * (D / 4) + 255) / 256), dim3(256), 0, st, 1, static_cast<const float*>(cls_pos), static_cast<float*>(x), B, P + 1, D);
   rc = check_launch();
   if (rc) return rc;
   GemmArgs g{};
@@ -375,8 +404,8 @@ int ldit_attention(const void* qkv, void* ctx, const void* bias_table, int B, in
       if (e != cudaSuccess) return static_cast<int>(e);                                                                 \
       max_set[bi][NCH] = smem;                                                                                          \
     }                                                                                                                   \
-    if (bi) attention_pp_kernel<true, NCH><<<grid, kA2Threads, smem, st>>>(tmQ, tmKV, tmO, a);                               \
-    else attention_pp_kernel<false, NCH><<<grid, kA2Threads, smem, st>>>(tmQ, tmKV, tmO, a);                                 \
+    if (bi) launch_kernel(attention_pp_kernel<true, NCH>, dim3(grid), dim3(kA2Threads), smem, st, 1, tmQ, tmKV, tmO, a);                               \
+    else launch_kernel(attention_pp_kernel<false, NCH>, dim3(grid), dim3(kA2Threads), smem, st, 1, tmQ, tmKV, tmO, a);                                 \
     break;
     switch (nch) {
       LDIT_ATTN_CASE(1) LDIT_ATTN_CASE(2) LDIT_ATTN_CASE(3) LDIT_ATTN_CASE(4)
@@ -411,8 +440,8 @@ int ldit_attention(const void* qkv, void* ctx, const void* bias_table, int B, in
       if (e != cudaSuccess) return static_cast<int>(e);
       max_set[bi] = smem;
     }
-    if (bias_table) attention_tc_kernel<true><<<grid, kAtcThreads, smem, st>>>(tmQ, tmKV, a);
-    else attention_tc_kernel<false><<<grid, kAtcThreads, smem, st>>>(tmQ, tmKV, a);
+    if (bias_table) launch_kernel(attention_tc_kernel<true>, dim3(grid), dim3(kAtcThreads), smem, st, 1, tmQ, tmKV, a);
+    else launch_kernel(attention_tc_kernel<false>, dim3(grid), dim3(kAtcThreads), smem, st, 1, tmQ, tmKV, a);
     return check_launch();
   }
   AttnArgs a{};
@@ -433,9 +462,9 @@ int ldit_attention(const void* qkv, void* ctx, const void* bias_table, int B, in
       if (e != cudaSuccess) return static_cast<int>(e);
       max_set = smem;
     }
-    attention_mma_kernel<true><<<grid, 128, smem, st>>>(a);
+    launch_kernel(attention_mma_kernel<true>, dim3(grid), dim3(128), smem, st, 1, a);
   } else {
-    attention_mma_kernel<false><<<grid, 128, smem, st>>>(a);
+    launch_kernel(attention_mma_kernel<false>, dim3(grid), dim3(128), smem, st, 1, a);
   }
   return check_launch();
 }
@@ -452,14 +481,13 @@ int ldit_resample_taps(const void* x, void* out, int B, int Gh, int Gw, int D, f
     dim3 ugrid((Gh * Gw + kUpCells - 1) / kUpCells, B);
     const float* xf = static_cast<const float*>(x);
     __nv_bfloat16* ob = static_cast<__nv_bfloat16*>(out);
-    if (scale == 4.0f) upsample_taps_kernel<4><<<ugrid, ublock, 0, static_cast<cudaStream_t>(stream)>>>(xf, ob, Gh * Gw + 1, D, Gh, Gw);
-    else upsample_taps_kernel<2><<<ugrid, ublock, 0, static_cast<cudaStream_t>(stream)>>>(xf, ob, Gh * Gw + 1, D, Gh, Gw);
+    if (scale == 4.0f) launch_kernel(upsample_taps_kernel<4>, ugrid, ublock, 0, static_cast<cudaStream_t>(stream), 1, xf, ob, Gh * Gw + 1, D, Gh, Gw);
+    else launch_kernel(upsample_taps_kernel<2>, ugrid, ublock, 0, static_cast<cudaStream_t>(stream), 1, xf, ob, Gh * Gw + 1, D, Gh, Gw);
     return check_launch();
   }
   dim3 block(D / 8, kTapPix);
   dim3 grid((oh * ow + kTapPix - 1) / kTapPix, B);
-  resample_taps_kernel<<<grid, block, 0, static_cast<cudaStream_t>(stream)>>>(
-      static_cast<const float*>(x), static_cast<__nv_bfloat16*>(out), Gh * Gw + 1, D, Gh, Gw, oh, ow, 1.0f / scale);
+  launch_kernel(resample_taps_kernel, grid, block, 0, static_cast<cudaStream_t>(stream), 1, static_cast<const float*>(x), static_cast<__nv_bfloat16*>(out), Gh * Gw + 1, D, Gh, Gw, oh, ow, 1.0f / scale);
   return check_launch();
 }
 

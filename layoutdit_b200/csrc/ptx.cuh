@@ -32,6 +32,15 @@ __device__ __forceinline__ bool elect_one_sync() {
   return pred != 0;
 }
 
+// ------------------------------------------------- programmatic dependent launch (PDL)
+// Every kernel of the library is launched with programmatic stream serialization: it may become
+// resident while its predecessor in the stream is still draining, runs its prologue (barrier
+// init, TMEM allocation, descriptor prefetch), and only then waits for the predecessor's
+// memory to be complete and visible.  EVERY kernel must call pdl_wait() before its first global
+// memory access (reads AND writes), or completion would no longer be transitive along the stream.
+__device__ __forceinline__ void pdl_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+
 // ------------------------------------------------------------------------------ mbarrier
 __device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
   asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");

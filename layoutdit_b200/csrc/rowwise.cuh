@@ -16,6 +16,8 @@ template <int VPL>  // float4 per lane: D = 128 * VPL
 __global__ void __launch_bounds__(256)
 layernorm_kernel(const float* __restrict__ x, const float* __restrict__ gamma, const float* __restrict__ beta,
                  __nv_bfloat16* __restrict__ y, int rows, float eps) {
+  pdl_launch_dependents();
+  pdl_wait();
   constexpr int D = 128 * VPL;
   const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   const int lane = threadIdx.x & 31;
@@ -85,6 +87,8 @@ __device__ __forceinline__ void load8<__half>(const __half* p, float (&v)[8]) {
 template <typename T>
 __global__ void __launch_bounds__(256)
 im2col_kernel(const T* __restrict__ x, __nv_bfloat16* __restrict__ a, int B, int H, int W, int Gh, int Gw) {
+  pdl_launch_dependents();
+  pdl_wait();
   // one thread = 8 consecutive pixels of one image row (half a patch row)
   const int wchunks = (Gw * 16) / 8;
   const size_t total = static_cast<size_t>(B) * 3 * (Gh * 16) * wchunks;
@@ -108,6 +112,8 @@ im2col_kernel(const T* __restrict__ x, __nv_bfloat16* __restrict__ a, int B, int
 // Token row 0 of every image: cls_token + position row 0 (HF:176-180); cls_pos = their sum.
 __global__ void __launch_bounds__(256)
 cls_rows_kernel(const float* __restrict__ cls_pos, float* __restrict__ xres, int B, int N, int D) {
+  pdl_launch_dependents();
+  pdl_wait();
   const int idx = blockIdx.x * blockDim.x + threadIdx.x;  // float4 index
   const int d4 = D / 4;
   if (idx >= B * d4) return;
@@ -132,6 +138,8 @@ constexpr int kTapPix = 4;
 __global__ void __launch_bounds__(1024)
 resample_taps_kernel(const float* __restrict__ xres, __nv_bfloat16* __restrict__ out, int N, int D, int Gh, int Gw,
                      int oh, int ow, float inv_scale) {
+  pdl_launch_dependents();
+  pdl_wait();
   const int pix = blockIdx.x * kTapPix + threadIdx.y;
   if (pix >= oh * ow) return;
   const int b = blockIdx.y;
@@ -176,6 +184,8 @@ constexpr int kUpCells = 2;
 template <int S>
 __global__ void __launch_bounds__(512)
 upsample_taps_kernel(const float* __restrict__ xres, __nv_bfloat16* __restrict__ out, int N, int D, int Gh, int Gw) {
+  pdl_launch_dependents();
+  pdl_wait();
   const int cell = blockIdx.x * kUpCells + threadIdx.y;
   if (cell >= Gh * Gw) return;
   const int b = blockIdx.y;
