@@ -60,6 +60,9 @@ __device__ __forceinline__ float a2_exp2(float x) {
 __device__ __forceinline__ void named_bar_sync(int id, int nthreads) {
   asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory");
 }
+__device__ __forceinline__ void named_bar_arrive(int id, int nthreads) {
+  asm volatile("bar.arrive %0, %1;" ::"r"(id), "r"(nthreads) : "memory");
+}
 
 template <bool HAS_BIAS, int NCH>  // NCH = kv_tile / 16
 __global__ void __launch_bounds__(kA2Threads, 1)
@@ -194,6 +197,7 @@ attention_pp_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
         const uint32_t ks1 = (kcount + 1) & 1, kph1 = ((kcount + 1) >> 1) & 1;
         mbar_wait(&v_full[ks], kph);
         if (t + 1 < T) mbar_wait(&k_full[ks1], kph1);
+        const int nchv = (min(KVT, a.N - t * KVT) + 15) >> 4;
 #pragma unroll
         for (int g = 0; g < 2; ++g) {
           if (g < nvalid) {
@@ -204,7 +208,8 @@ attention_pp_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
               const uint64_t vd = vdesc0 + static_cast<uint32_t>(ks * (kA2KvBytes >> 4));
 #pragma unroll
               for (int k = 0; k < NCH; ++k)
-                umma_bf16_ts(tmem_base + g * 256 + kA2OCol, tmem_base + g * 256 + 8 * k, vd + 128 * k, idesc_o, (t | k) != 0);
+                if (k < nchv)   // chunks past the last key were never written by the softmax warps
+                  umma_bf16_ts(tmem_base + g * 256 + kA2OCol, tmem_base + g * 256 + 8 * k, vd + 128 * k, idesc_o, (t | k) != 0);
               if (t + 1 == T) tcgen05_commit(&o_full[g]);
             }
             __syncwarp();
@@ -231,6 +236,9 @@ attention_pp_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
     const float sc = a.scale_log2e;
     uint32_t scnt = 0, icnt = 0;
     int cur_h = -1;
+    // (Tried and rejected: forcing the two warpgroups to take strict turns at the softmax math with
+    // named barriers.  A warpgroup's softmax is bound by its own serial latency, not by sharing the
+    // SFU / issue slots with the other one, so alternation only adds waiting: 35.8 -> 39.9 us.)
     for (int item = blockIdx.x; item < a.num_items; item += gridDim.x) {
       const int p = item % a.n_qpairs, bh = item / a.n_qpairs;
       const int h = bh % a.heads, b = bh / a.heads;
@@ -258,6 +266,7 @@ attention_pp_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
       for (int t = 0; t < T; ++t, ++scnt) {
         const int k0 = t * KVT;
         const int valid = min(KVT, a.N - k0);   // keys of this tile that exist
+        const int nch_valid = (valid + 15) >> 4; // 16-key chunks that hold at least one of them
         mbar_wait(&s_full[g], scnt & 1);
         tcgen05_fence_after();
         if (rec && t == 0) tl[1] = clock64();
@@ -319,31 +328,54 @@ attention_pp_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
               tmem_st_32x32b_x16(lane_addr + kA2OCol + c * 16, ob);
             }
           }
-          // ---- p = exp2(s - m), row sum, P -> TMEM as packed bf16 over columns [0, kv_tile/2)
+          // ---- p = exp2(s - m), row sum, P -> TMEM as packed bf16 over columns [0, kv_tile/2).
+          // The SFU (16 ex2/clk/SM) is the binding unit of this kernel at short sequences, so 6 of every
+          // 16 exponentials are evaluated on the FMA pipe instead: round-to-nearest split x = n + f with
+          // the 1.5*2^23 trick, 2^f by a cubic (7.7e-5 relative error, far below the bf16 rounding of
+          // P), 2^n by an integer add into the exponent field; all in packed fp32 (two keys per
+          // instruction).  Chunks that lie entirely beyond the last key of the image are skipped (the
+          // issuer shortens the P V contraction accordingly).
           const float neg_m = -m_new;
+          const uint64_t sc2 = f2_splat(HAS_BIAS ? 1.0f : sc), negm2 = f2_splat(neg_m);
+          const uint64_t magic2 = f2_splat(12582912.0f), nmagic2 = f2_splat(-12582912.0f), mone2 = f2_splat(-1.0f);
+          const uint64_t e3 = f2_splat(0.05508868396282196f), e2 = f2_splat(0.24260404706001282f),
+                         e1 = f2_splat(0.6932762265205383f), e0 = f2_splat(0.9999289512634277f);
           float ps[4] = {0.f, 0.f, 0.f, 0.f};
 #pragma unroll
           for (int c = 0; c < NCH; ++c) {
-            uint32_t pk[8];
+            if (c < nch_valid) {
+              float p[16];
 #pragma unroll
-            for (int i = 0; i < 16; i += 4) {
-              float p0, p1, p2, p3;
-              if constexpr (HAS_BIAS) {
-                p0 = a2_exp2(__uint_as_float(s[c][i]) + neg_m);
-                p1 = a2_exp2(__uint_as_float(s[c][i + 1]) + neg_m);
-                p2 = a2_exp2(__uint_as_float(s[c][i + 2]) + neg_m);
-                p3 = a2_exp2(__uint_as_float(s[c][i + 3]) + neg_m);
-              } else {
-                p0 = a2_exp2(fmaf(__uint_as_float(s[c][i]), sc, neg_m));
-                p1 = a2_exp2(fmaf(__uint_as_float(s[c][i + 1]), sc, neg_m));
-                p2 = a2_exp2(fmaf(__uint_as_float(s[c][i + 2]), sc, neg_m));
-                p3 = a2_exp2(fmaf(__uint_as_float(s[c][i + 3]), sc, neg_m));
+              for (int i = 0; i < 10; ++i) {
+                if constexpr (HAS_BIAS) p[i] = a2_exp2(__uint_as_float(s[c][i]) + neg_m);
+                else p[i] = a2_exp2(fmaf(__uint_as_float(s[c][i]), sc, neg_m));
               }
-              ps[0] += p0; ps[1] += p1; ps[2] += p2; ps[3] += p3;
-              pk[i >> 1] = pack_bf16x2(p0, p1);
-              pk[(i >> 1) + 1] = pack_bf16x2(p2, p3);
+#pragma unroll
+              for (int i = 10; i < 16; i += 2) {
+                uint64_t x = f2_fma(f2_pack(__uint_as_float(s[c][i]), __uint_as_float(s[c][i + 1])), sc2, negm2);
+                float x0, x1;
+                f2_unpack(x, x0, x1);
+                x = f2_pack(fmaxf(x0, -126.0f), fmaxf(x1, -126.0f));   // masked keys are -inf
+                const uint64_t t = f2_add(x, magic2);                  // low mantissa bits = n = round(x)
+                const uint64_t f = f2_fma(f2_add(t, nmagic2), mone2, x);   // x - n in [-0.5, 0.5]
+                uint64_t q = f2_fma(f, e3, e2);
+                q = f2_fma(q, f, e1);
+                q = f2_fma(q, f, e0);
+                float q0, q1, t0, t1;
+                f2_unpack(q, q0, q1);
+                f2_unpack(t, t0, t1);
+                p[i] = __int_as_float(__float_as_int(t0) * 0x800000 + __float_as_int(q0));        // 2^f * 2^n
+                p[i + 1] = __int_as_float(__float_as_int(t1) * 0x800000 + __float_as_int(q1));
+              }
+              uint32_t pk[8];
+#pragma unroll
+              for (int i = 0; i < 16; i += 4) {
+                ps[0] += p[i]; ps[1] += p[i + 1]; ps[2] += p[i + 2]; ps[3] += p[i + 3];
+                pk[i >> 1] = pack_bf16x2(p[i], p[i + 1]);
+                pk[(i >> 1) + 1] = pack_bf16x2(p[i + 2], p[i + 3]);
+              }
+              tmem_st_32x32b_x8(lane_addr + c * 8, pk);
             }
-            tmem_st_32x32b_x8(lane_addr + c * 8, pk);
           }
           l_run = l_run * alpha + ((ps[0] + ps[1]) + (ps[2] + ps[3]));
           tcgen05_wait_st();

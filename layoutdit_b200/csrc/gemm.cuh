@@ -112,31 +112,6 @@ struct GemmCfg {
 // Horner chain for a pair at the issue cost of one -- the epilogue warps share their schedulers
 // with the MMA issuer and the TMA producer, and every issue slot they do not take shortens the
 // main loop (measured: scalar GELU math stretched the MMA issue span of a tile by 14 %).
-__device__ __forceinline__ uint64_t f2_pack(float lo, float hi) {
-  uint64_t r;
-  asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(lo), "f"(hi));
-  return r;
-}
-__device__ __forceinline__ void f2_unpack(uint64_t v, float& lo, float& hi) {
-  asm("mov.b64 {%0, %1}, %2;" : "=f"(lo), "=f"(hi) : "l"(v));
-}
-__device__ __forceinline__ uint64_t f2_fma(uint64_t a, uint64_t b, uint64_t c) {
-  uint64_t d;
-  asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(d) : "l"(a), "l"(b), "l"(c));
-  return d;
-}
-__device__ __forceinline__ uint64_t f2_mul(uint64_t a, uint64_t b) {
-  uint64_t d;
-  asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b));
-  return d;
-}
-__device__ __forceinline__ uint64_t f2_add(uint64_t a, uint64_t b) {
-  uint64_t d;
-  asm("add.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b));
-  return d;
-}
-__device__ __forceinline__ uint64_t f2_splat(float c) { return f2_pack(c, c); }
-
 // P has no clamp: it decreases monotonically beyond the fitted range (P(z) < -40 for z > 5), so
 // 0.5 erfc(z) just keeps underflowing towards 0 as it should.
 struct GeluCoef {
