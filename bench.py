@@ -117,6 +117,12 @@ def cpu_reference_run(workload: str, steps: int, warmup: int, budget_s: float = 
     cfg = getattr(cfgmod, fac)()
     model = hf_reference.build(cfg.to_dict(), make_state_dict(cfg, 0, False))
     x = synthetic_pages(CPU_SAMPLE_IMAGES, H, W, 1234)
+    # all the host threads this process may use (torchrun pins OMP_NUM_THREADS=1 for its children)
+    try:
+        avail = len(os.sched_getaffinity(0))
+    except AttributeError:
+        avail = os.cpu_count() or 1
+    torch.set_num_threads(max(torch.get_num_threads(), avail))
     cores = torch.get_num_threads()
     times = []
     with torch.no_grad():
@@ -315,7 +321,7 @@ def main():
                        "timing": ("CUDA-graph replay" if args.graph else "stream launches with programmatic dependent launch (PDL)")
                                  + "; per-step CUDA events summed; max over ranks"},
             "model_tflops": round(model_tflops, 1),
-            "model_frac_of_peak": round(model_tflops / peaks["bf16_tflops"], 4),
+            "model_frac_of_peak": round(model_tflops / (world * peaks["bf16_tflops"]), 4),
             "flops_per_image": fl_img,
             "roofline": {"bound": "tensor", "kernel": f"gemm_tcgen05_kernel<EPI_BIAS_GELU> M={geo.M} N={I} K={D}",
                          "achieved": round(achieved, 1), "peak": peak, "unit": "TFLOP/s", "frac": round(achieved / peak, 4),
