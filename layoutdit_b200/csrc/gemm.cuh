@@ -92,12 +92,14 @@ struct GemmCfg {
   static constexpr int CHUNKS = CG_COLS / kEpiCols;
   static constexpr int CHUNK_BYTES = 32 * kEpiCols * (OUT_F32 ? 4 : 2);
   static constexpr int STAGING_BYTES = kGemmEpiWarps * LDIT_EPI_BUFS * CHUNK_BYTES;
+  // per epilogue warp: bias and layer-scale of the warp's CG_COLS columns, staged once per tile
+  static constexpr int COLOP_BYTES = (EPI == EPI_PATCH) ? 0 : kGemmEpiWarps * 2 * 64 * 4;
   static constexpr int BAR_BYTES = 256;
-  static constexpr int STAGES_FIT = (kMaxSmem - 1024 - BAR_BYTES - STAGING_BYTES) / STAGE_BYTES;
+  static constexpr int STAGES_FIT = (kMaxSmem - 1024 - BAR_BYTES - STAGING_BYTES - COLOP_BYTES) / STAGE_BYTES;
   static constexpr int STAGES = (STAGES_FIT > 8 ? 8 : STAGES_FIT) & ~(LDIT_KSTEP - 1);  // even when the loops take slots in pairs
-  static_assert(STAGES >= 4, "pipeline too shallow");
+  static_assert(STAGES >= 3, "pipeline too shallow");
   static_assert(A_BYTES % 1024 == 0 && B_BYTES % 1024 == 0, "swizzle-128B tiles must stay 1 KB aligned");
-  static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + STAGING_BYTES + BAR_BYTES + 1024;  // + alignment slack
+  static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + STAGING_BYTES + COLOP_BYTES + BAR_BYTES + 1024;  // + alignment slack
 };
 
 // exact-erf GELU (HF:430, ACT2FN["gelu"]):  gelu(x) = x Phi(x) = max(x, 0) - |x| * 0.5 erfc(|x| / sqrt 2).
@@ -158,7 +160,8 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
   uint8_t* sA = smem;
   uint8_t* sB = smem + S * Cfg::A_BYTES;
   uint8_t* sStage = smem + S * Cfg::STAGE_BYTES;  // 1 KB aligned: every tile size is a multiple of 1 KB
-  uint64_t* full_bar = reinterpret_cast<uint64_t*>(sStage + Cfg::STAGING_BYTES);
+  float* sColOp = reinterpret_cast<float*>(sStage + Cfg::STAGING_BYTES);   // [warp][bias 64 | scale 64]
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(sStage + Cfg::STAGING_BYTES + Cfg::COLOP_BYTES);
   uint64_t* empty_bar = full_bar + S;
   uint64_t* tfull_bar = empty_bar + S;
   uint64_t* tempty_bar = tfull_bar + 2;
@@ -353,6 +356,21 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
         }
       }
 
+      // bias / layer-scale of this warp's columns -> smem, requested before the accumulator wait so the
+      // global-load latency never sits in the per-chunk chain (CG_COLS <= 64 = 2 floats per lane)
+      float* my_colop = sColOp + warp * 128;
+      if constexpr (EPI != EPI_PATCH) {
+        const int cc = col0 + 2 * lane;
+        const bool ok = 2 * lane < Cfg::CG_COLS && cc < g.N;
+        float2 bb = make_float2(0.f, 0.f), ss = make_float2(1.f, 1.f);
+        if (ok && g.bias != nullptr) bb = __ldg(reinterpret_cast<const float2*>(g.bias + cc));
+        if constexpr (EPI == EPI_SCALE_RESID) {
+          if (ok && g.scale != nullptr) ss = __ldg(reinterpret_cast<const float2*>(g.scale + cc));
+        }
+        *reinterpret_cast<float2*>(my_colop + 2 * lane) = bb;
+        if constexpr (EPI == EPI_SCALE_RESID) *reinterpret_cast<float2*>(my_colop + 64 + 2 * lane) = ss;
+        __syncwarp();
+      }
       if (tl) tl[4] = clock64();
       mbar_wait(&tfull_bar[acc], acc_phase);
       tcgen05_fence_after();
@@ -374,14 +392,13 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
 #else
         uint32_t (&rc)[16] = r[c & 1];
 #endif
-        // per-column operands of this chunk, requested before the TMEM wait
+        // per-column operands of this chunk (smem broadcast reads)
         float4 b4[4], s4[4];
         if constexpr (EPI != EPI_PATCH) {
 #pragma unroll
           for (int j = 0; j < 4; ++j) {
-            b4[j] = (g.bias != nullptr && col_ok) ? __ldg(reinterpret_cast<const float4*>(g.bias + col) + j) : make_float4(0.f, 0.f, 0.f, 0.f);
-            if constexpr (EPI == EPI_SCALE_RESID)
-              s4[j] = (g.scale != nullptr && col_ok) ? __ldg(reinterpret_cast<const float4*>(g.scale + col) + j) : make_float4(1.f, 1.f, 1.f, 1.f);
+            b4[j] = *reinterpret_cast<const float4*>(my_colop + c * kEpiCols + 4 * j);
+            if constexpr (EPI == EPI_SCALE_RESID) s4[j] = *reinterpret_cast<const float4*>(my_colop + 64 + c * kEpiCols + 4 * j);
           }
         }
         tmem_wait_ld16(rc);
