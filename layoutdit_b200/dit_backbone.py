@@ -64,6 +64,12 @@ class DiTBackbone(nn.Module):
             self._engine._pack_key = None
         return out
 
+    def forward_host(self, pages: torch.Tensor, result_host: torch.Tensor | None = None, result_key: str = "p5"):
+        """Pipelined forward of a HOST batch (see ``Engine.forward_host``): PCIe copies overlap the
+        kernels of the neighbouring calls.  Returns ``(feats, done_event)``."""
+        with torch.no_grad():
+            return self._get_engine().forward_host(pages, result_host, result_key)
+
     def forward(self, x: torch.Tensor) -> "OrderedDict[str, torch.Tensor]":
         if self.training and torch.is_grad_enabled() and any(p.requires_grad for p in self.dit.parameters()):
             raise NotImplementedError(

@@ -152,8 +152,10 @@ class Engine:
         new = new.permute(0, 2, 3, 1).reshape(nh * nw, -1)
         return torch.cat([new, table[old * old:]], dim=0).t().contiguous()
 
-    def _geometry(self, B, H, W) -> _Geometry:
-        key = (B, H, W)
+    def _geometry(self, B, H, W, slot: int = 0) -> _Geometry:
+        """Workspaces / tables / graph for one (B, H, W).  ``slot`` > 0 gives an independent copy
+        (own workspaces, own captured graph, own static outputs) for pipelined callers."""
+        key = (B, H, W) if slot == 0 else (B, H, W, slot)
         geo = self._geoms.get(key)
         if geo is not None:
             return geo
@@ -279,14 +281,14 @@ class Engine:
         return geo
 
     # ----------------------------------------------------------------------- CUDA graphs
-    def forward_graphed(self, x: torch.Tensor):
+    def forward_graphed(self, x: torch.Tensor, slot: int = 0):
         """Replay a captured CUDA graph of the whole forward for this (B, H, W, dtype).
-        Outputs are STATIC buffers overwritten by the next call with the same geometry."""
+        Outputs are STATIC buffers overwritten by the next call with the same geometry (and slot)."""
         self.refresh_weights()
         if x.shape[2] % 16 or x.shape[3] % 16:
             return self.forward(x)
         x = self.prepare_input(x)
-        geo = self._geometry(x.shape[0], x.shape[2], x.shape[3])
+        geo = self._geometry(x.shape[0], x.shape[2], x.shape[3], slot)
         if geo.graph is None or geo.graph_in.dtype != x.dtype:
             if geo.graph_in is None or geo.graph_in.dtype != x.dtype:
                 geo.graph_in = torch.empty_like(x)
@@ -308,16 +310,61 @@ class Engine:
         geo.graph.replay()
         return geo.graph_out
 
-    def graph_input_buffer(self, B, H, W, dtype=torch.float32):
+    def graph_input_buffer(self, B, H, W, dtype=torch.float32, slot: int = 0):
         """The static input tensor of the captured graph for this geometry: writing pixels
         straight into it (e.g. the H2D copy) skips the staging copy in ``forward_graphed``."""
         self.refresh_weights()
-        geo = self._geometry(B, H, W)
+        geo = self._geometry(B, H, W, slot)
         if geo.graph_in is None or geo.graph_in.dtype != dtype:
             geo.graph = None
             geo.graph_in = torch.zeros(B, 3, H, W, device=self.device, dtype=dtype)
-            self.forward_graphed(geo.graph_in)
+            self.forward_graphed(geo.graph_in, slot)
         return geo.graph_in
+
+    # ------------------------------------------------------------- host-fed, pipelined forward
+    def forward_host(self, pages: torch.Tensor, result_host: torch.Tensor | None = None, result_key: str = "p5",
+                     depth: int = 2):
+        """Forward of a HOST page batch (pinned memory recommended) with the PCIe copies taken off the
+        compute stream: the H2D copy of call i+1 and the D2H copy of call i's ``result_key`` tap run on
+        their own streams under the kernels of call i (``depth`` independent slots, each with its own
+        input buffer, workspaces, captured graph and static outputs).  Returns (feats, done_event):
+        ``feats`` are the slot's static device taps (overwritten ``depth`` calls later), ``done_event``
+        fires when ``result_host`` (if given) holds the tap in channels-last order."""
+        if pages.is_cuda:
+            raise ValueError("forward_host takes a host tensor; call forward() for device tensors")
+        if pages.dim() != 4 or pages.shape[2] % 16 or pages.shape[3] % 16:
+            raise ValueError("forward_host needs [B, 3, H, W] pages with H, W multiples of 16")
+        if pages.dtype not in _DTYPE_CODE:
+            pages = pages.float()
+        self.refresh_weights()
+        B, H, W = pages.shape[0], pages.shape[2], pages.shape[3]
+        st = self.__dict__.setdefault("_host_pipe", {"n": 0, "h2d": None, "d2h": None, "ev": {}})
+        if st["h2d"] is None:
+            st["h2d"], st["d2h"] = torch.cuda.Stream(self.device), torch.cuda.Stream(self.device)
+        slot = 1 + st["n"] % depth          # slot 0 stays the plain forward_graphed() state
+        st["n"] += 1
+        cur = torch.cuda.current_stream(self.device)
+        buf = self.graph_input_buffer(B, H, W, pages.dtype, slot)
+        ev = st["ev"].setdefault((B, H, W, slot), {})
+        with torch.cuda.stream(st["h2d"]):
+            if "compute" in ev:
+                st["h2d"].wait_event(ev["compute"])        # the slot's previous forward has consumed its input
+            buf.copy_(pages, non_blocking=True)
+            ev["h2d"] = torch.cuda.Event(); ev["h2d"].record(st["h2d"])
+        cur.wait_event(ev["h2d"])
+        if "d2h" in ev:
+            cur.wait_event(ev["d2h"])                      # the slot's previous result has left its static tap
+        feats = self.forward_graphed(buf, slot)
+        ev["compute"] = torch.cuda.Event(); ev["compute"].record(cur)
+        done = ev["compute"]
+        if result_host is not None:
+            tap = feats[result_key].permute(0, 2, 3, 1)    # channels-last memory of the static output buffer
+            with torch.cuda.stream(st["d2h"]):
+                st["d2h"].wait_event(ev["compute"])
+                result_host.view(tap.shape).copy_(tap, non_blocking=True)
+                ev["d2h"] = torch.cuda.Event(); ev["d2h"].record(st["d2h"])
+            done = ev["d2h"]
+        return feats, done
 
     def last_launches(self, B, H, W) -> int:
         geo = self._geoms.get((B, H, W))

@@ -139,3 +139,26 @@ def test_full_size_c3_512(cuda_device):
         e = _rel_fro(got[k].float(), ref[k])
         print("c3", k, f"{e:.2e}")
         assert e < REL_FRO
+
+
+def test_forward_host_pipeline_matches_forward(cuda_device):
+    """Host-fed pipelined forward: same numbers as forward() on the device copy, slot reuse is safe."""
+    cfg, sd, x, _, _ = build_case("tiny_abs_native")
+    m = _backbone(cfg, sd)
+    ref = {k: v.clone() for k, v in m(x.cuda().half()).items()}
+    pages = [x.half().pin_memory(), (x.flip(0)).half().pin_memory(), x.half().pin_memory()]
+    p5 = ref["p5"]
+    hosts = [torch.empty(p5.shape[0], p5.shape[2], p5.shape[3], p5.shape[1], dtype=torch.bfloat16).pin_memory() for _ in pages]
+    dones = []
+    for pg, ho in zip(pages, hosts):                      # three calls back to back: slots 1, 2, 1
+        feats, done = m.forward_host(pg, ho, "p5")
+        dones.append(done)
+    for d in dones:
+        d.synchronize()
+    for k in ref:                                          # last call used the same pages as the reference
+        assert torch.equal(feats[k], ref[k])
+    assert torch.equal(hosts[0], ref["p5"].permute(0, 2, 3, 1).cpu())
+    assert torch.equal(hosts[2], hosts[0])
+    assert torch.equal(hosts[1], ref["p5"].flip(0).permute(0, 2, 3, 1).cpu())
+    with pytest.raises(ValueError):
+        m.forward_host(x.cuda())
