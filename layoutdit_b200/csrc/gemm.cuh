@@ -90,6 +90,11 @@ struct GemmCfg {
   // per warp two staging buffers of 32 rows x 16 columns (rows of 32 B bf16 / 64 B fp32)
   static constexpr int CG_COLS = BN / 4;
   static constexpr int CHUNKS = CG_COLS / kEpiCols;
+  // Tried and rejected for the bf16 outputs (same-box A/B, base224 step): one wide box per warp and
+  // tile (96-byte rows; stores arrive in bursts, main loop bimodal 4400 / 7500 cycles, +3 %), and
+  // 256-bit stores straight from registers (no TMA store at all: the operand loads are then on time,
+  // but the LSU traffic delays the MMA warp's own dispatch, +3 %).  L2 prefetch of the A operand
+  // ahead of the ring: +8 % (the prefetches compete with the loads in the TMA unit).
   static constexpr int CHUNK_BYTES = 32 * kEpiCols * (OUT_F32 ? 4 : 2);
   static constexpr int STAGING_BYTES = kGemmEpiWarps * LDIT_EPI_BUFS * CHUNK_BYTES;
   // per epilogue warp: bias and layer-scale of the warp's CG_COLS columns, staged once per tile

@@ -89,6 +89,12 @@ __device__ __forceinline__ void tma_load_2d(void* smem_dst, const CUtensorMap* t
       ::"r"(smem_u32(smem_dst)), "l"(reinterpret_cast<uint64_t>(tm)), "r"(smem_u32(bar)), "r"(c0), "r"(c1)
       : "memory");
 }
+// L2 prefetch of a tile (no smem destination, no barrier): hides HBM latency for operands that miss L2
+__device__ __forceinline__ void tma_prefetch_l2_2d(const CUtensorMap* tm, int c0, int c1) {
+  asm volatile("cp.async.bulk.prefetch.tensor.2d.L2.global.tile [%0, {%1, %2}];"
+               ::"l"(reinterpret_cast<uint64_t>(tm)), "r"(c0), "r"(c1)
+               : "memory");
+}
 __device__ __forceinline__ void tma_load_3d(void* smem_dst, const CUtensorMap* tm, uint64_t* bar, int c0, int c1, int c2) {
   asm volatile(
       "cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];"
@@ -326,6 +332,13 @@ __device__ __forceinline__ uint64_t f2_add(uint64_t a, uint64_t b) {
   return d;
 }
 __device__ __forceinline__ uint64_t f2_splat(float c) { return f2_pack(c, c); }
+
+// 256-bit global store (sm_100+): one full 32-byte sector per thread and instruction
+__device__ __forceinline__ void st_global_256(void* gptr, const uint32_t (&r)[8]) {
+  asm volatile("st.global.v8.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};"
+               ::"l"(gptr), "r"(r[0]), "r"(r[1]), "r"(r[2]), "r"(r[3]), "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7])
+               : "memory");
+}
 
 // ----------------------------------------------------------------------------------- misc
 __device__ __forceinline__ uint32_t pack_bf16x2(float lo, float hi) {
