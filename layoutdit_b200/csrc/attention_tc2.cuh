@@ -4,25 +4,26 @@
 // merged-heads context [B, N, D] (HF:365-367).
 //
 // One CTA per SM loops over work items (image, head, pair of 128-query tiles).  Both tiles of a
-// pair share the K/V tiles that stream through a 2-stage smem ring; each tile belongs to one
+// pair share the K/V tiles that stream through 3-stage smem rings; each tile belongs to one
 // softmax warpgroup that owns 256 TMEM columns:
 //   warps 0-3   softmax warpgroup 0  (thread <-> query row <-> TMEM lane)
 //   warps 4-7   softmax warpgroup 1
 //   warp  8     TMA producer + TMEM allocator (warp-uniform loop, one elected lane issues)
 //   warp  9     MMA issuer                    (warp-uniform loop, one elected lane issues)
-// K/V tiles hold at most 128 keys (kv_tile = 16 * NCH, NCH <= 8), so that a whole row of
-//   S = Q K^T   (tcgen05.mma SS, fp32 [128 x kv_tile] in TMEM columns [0, kv_tile))
-// fits in the registers of the thread that owns the row: ONE TMEM read per tile, then row max,
-// exp2 and row sum entirely in registers.  P goes back to TMEM as packed bf16 over columns
-// [0, kv_tile/2) and is the A operand of
+// K/V tiles hold at most 96 keys (kv_tile = 16 * NCH, NCH <= 6), so that
+//   S = Q K^T   (tcgen05.mma SS, fp32 [128 x kv_tile]) is DOUBLE-BUFFERED per warpgroup in TMEM
+//               columns [0, 96) / [96, 192): the issuer always has the next tile's scores in
+//               flight while the warpgroup is in the exponentials of the current one, so the MMA
+//               and barrier latency of a step is off the warpgroup's serial chain
+// and a whole row of S fits in the registers of the thread that owns the row: ONE TMEM read per
+// tile, then row max, exp2 and row sum entirely in registers.  P goes back to TMEM as packed bf16
+// over the first kv_tile/2 columns of the same S buffer and is the A operand of
 //   O += P V    (tcgen05.mma TS, V consumed as an MN-major smem operand exactly as it sits in
-//                the QKV buffer; O = fp32 [128 x 64] accumulates in TMEM columns [128, 192)).
+//                the QKV buffer; O = fp32 [128 x 64] accumulates in TMEM columns [192, 256)).
 // When the running row max moves between tiles the warpgroup rescales O in place (TMEM load /
-// multiply / store) before it releases P -- the online-softmax recurrence without keeping O in
-// registers.  The issuer chains  O_g += P_g V(t)  and  S_g = Q_g K(t+1)^T  back to back, so a
-// warpgroup's next scores are being computed while the other warpgroup is in its exponentials.
-// The relative-position bias is gathered in-tile from a per-head table in smem with the index
-// rule of HF:522-544.
+// multiply / store, after the previous P V has signalled completion) before it releases P -- the
+// online-softmax recurrence without keeping O in registers.  The relative-position bias is
+// gathered in-tile from a per-head table in smem with the index rule of HF:522-544.
 #pragma once
 
 #include "ptx.cuh"
@@ -40,12 +41,14 @@ struct AttnP2Args {
 };
 
 constexpr int kA2Threads = 320;
-constexpr int kA2MaxKv = 128;
-constexpr int kA2KvBytes = kA2MaxKv * 128;  // 16 KB per K or V stage
-constexpr int kA2OCol = 128;
+constexpr int kA2MaxKv = 96;
+constexpr int kA2KvBytes = kA2MaxKv * 128;  // 12 KB per K or V stage
+constexpr int kA2KvStages = 3;
+constexpr int kA2SCol = 96;                 // TMEM columns between the two S buffers of a warpgroup
+constexpr int kA2OCol = 192;
 constexpr int kA2WarpProducer = 8, kA2WarpMma = 9;
-constexpr int kA2SmemTiles = 4 * 16384 + 4 * kA2KvBytes + 8 * 4096;  // Q[2][2] + K[2] + V[2] + per-warp output staging = 160 KB
-constexpr int kA2NumBars = 20;
+constexpr int kA2SmemTiles = 4 * 16384 + 2 * kA2KvStages * kA2KvBytes + 8 * 4096;  // Q[2][2] + K[3] + V[3] + per-warp output staging = 168 KB
+constexpr int kA2NumBars = 28;
 
 __device__ __forceinline__ float a2_fmax3(float a, float b, float c) {
   float d;
@@ -74,19 +77,19 @@ attention_pp_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   uint8_t* sQ = smem;                       // [qb][g] 16 KB each
   uint8_t* sK = smem + 4 * 16384;           // [stage]
-  uint8_t* sV = sK + 2 * kA2KvBytes;        // [stage]
-  uint8_t* sOut = sV + 2 * kA2KvBytes;      // [softmax warp] 32 rows x 128 B, 128B-swizzled, for the TMA store of ctx
+  uint8_t* sV = sK + kA2KvStages * kA2KvBytes;   // [stage]
+  uint8_t* sOut = sV + kA2KvStages * kA2KvBytes; // [softmax warp] 32 rows x 128 B, 128B-swizzled, for the TMA store of ctx
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem + kA2SmemTiles);
   uint64_t* q_full = bars + 0;    // [2]
   uint64_t* q_empty = bars + 2;   // [2]
-  uint64_t* k_full = bars + 4;    // [2]
-  uint64_t* k_empty = bars + 6;   // [2]
-  uint64_t* v_full = bars + 8;    // [2]
-  uint64_t* v_empty = bars + 10;  // [2]
-  uint64_t* s_full = bars + 12;   // [2] per warpgroup: S complete (and every earlier MMA of the CTA)
-  uint64_t* p_full = bars + 14;   // [2] per warpgroup: P written, O rescaled (4 warp arrivals)
-  uint64_t* o_full = bars + 16;   // [2] per warpgroup: O of the item complete
-  uint64_t* o_done = bars + 18;   // [2] per warpgroup: O read back, TMEM columns reusable (4 warp arrivals)
+  uint64_t* k_full = bars + 4;    // [3]
+  uint64_t* k_empty = bars + 7;   // [3]
+  uint64_t* v_full = bars + 10;   // [3]
+  uint64_t* v_empty = bars + 13;  // [3]
+  uint64_t* s_full = bars + 16;   // [warpgroup][S buffer]: scores complete
+  uint64_t* p_full = bars + 20;   // [2] per warpgroup: P written, O rescaled (4 warp arrivals)
+  uint64_t* pv_done = bars + 22;  // [2] per warpgroup: a P V (and everything before it) complete
+  uint64_t* o_done = bars + 24;   // [2] per warpgroup: O read back, TMEM columns reusable (4 warp arrivals)
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + kA2NumBars);
   float* sTab = reinterpret_cast<float*>(bars + kA2NumBars + 2);  // [2][T] (one copy per warpgroup)
   int* sCol = reinterpret_cast<int*>(sTab + (HAS_BIAS ? 2 * a.T : 0));
@@ -96,7 +99,7 @@ attention_pp_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
   constexpr uint32_t kv_bytes = KVT * 128;
 
   if (warp == kA2WarpMma && lane == 0) {
-    for (int i = 0; i < kA2NumBars; ++i) mbar_init(&bars[i], (i == 14 || i == 15 || i == 18 || i == 19) ? 4 : 1);
+    for (int i = 0; i < kA2NumBars; ++i) mbar_init(&bars[i], (i == 20 || i == 21 || i == 24 || i == 25) ? 4 : 1);
     fence_barrier_init();
     fence_proxy_async_smem();
   }
@@ -124,7 +127,17 @@ attention_pp_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
 
   if (warp == kA2WarpProducer) {
     // ------------------------------------------------------------------ TMA producer
-    uint32_t it = 0, kcount = 0;
+    // order of use by the issuer: K(0), K(1), then per step t: V(t) and K(t+2)
+    uint32_t it = 0, kcount = 0, vcount = 0;
+    auto load_kv = [&](uint8_t* ring, uint64_t* full, uint64_t* empty, uint32_t cnt, int col, int t, int b) {
+      const uint32_t st = cnt % kA2KvStages, ph = (cnt / kA2KvStages) & 1;
+      mbar_wait(&empty[st], ph ^ 1);
+      if (elect_one_sync()) {
+        mbar_arrive_expect_tx(&full[st], kv_bytes);
+        tma_load_3d(ring + st * kA2KvBytes, &tmKV, &full[st], col, t * KVT, b);
+      }
+      __syncwarp();
+    };
     for (int item = blockIdx.x; item < a.num_items; item += gridDim.x, ++it) {
       const int p = item % a.n_qpairs, bh = item / a.n_qpairs;
       const int h = bh % a.heads, b = bh / a.heads;
@@ -137,20 +150,9 @@ attention_pp_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
         if (nvalid == 2) tma_load_3d(sQ + (qb * 2 + 1) * 16384, &tmQ, &q_full[qb], h * 64, 256 * p + 128, b);
       }
       __syncwarp();
-      for (int t = 0; t < T; ++t, ++kcount) {
-        const uint32_t ks = kcount & 1, kph = (kcount >> 1) & 1;
-        mbar_wait(&k_empty[ks], kph ^ 1);
-        if (elect_one_sync()) {
-          mbar_arrive_expect_tx(&k_full[ks], kv_bytes);
-          tma_load_3d(sK + ks * kA2KvBytes, &tmKV, &k_full[ks], a.D + h * 64, t * KVT, b);
-        }
-        __syncwarp();
-        mbar_wait(&v_empty[ks], kph ^ 1);
-        if (elect_one_sync()) {
-          mbar_arrive_expect_tx(&v_full[ks], kv_bytes);
-          tma_load_3d(sV + ks * kA2KvBytes, &tmKV, &v_full[ks], 2 * a.D + h * 64, t * KVT, b);
-        }
-        __syncwarp();
+      for (int j = 0; j < T + 2; ++j) {
+        if (j < T) { load_kv(sK, k_full, k_empty, kcount, a.D + h * 64, j, b); ++kcount; }
+        if (j >= 2) { load_kv(sV, v_full, v_empty, vcount, 2 * a.D + h * 64, j - 2, b); ++vcount; }
       }
     }
   } else if (warp == kA2WarpMma) {
@@ -160,67 +162,72 @@ attention_pp_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
     const uint64_t qdesc0 = umma_desc_kmajor_sw128(smem_u32(sQ));
     const uint64_t kdesc0 = umma_desc_kmajor_sw128(smem_u32(sK));
     const uint64_t vdesc0 = umma_desc_mnmajor_sw128(smem_u32(sV));
-    uint32_t it = 0, kcount = 0;
-    uint32_t pcnt[2] = {0, 0};   // p_full phases consumed per warpgroup
+    uint32_t it = 0, kcount = 0, vcount = 0;
+    uint32_t scnt[2] = {0, 0};   // S tiles issued per warpgroup (buffer = count & 1)
+    uint32_t pcnt[2] = {0, 0};   // p_full phases consumed per warpgroup (P sits in buffer count & 1)
     uint32_t icnt[2] = {0, 0};   // items processed per warpgroup (o_done phases)
     auto issue_s = [&](int g, uint32_t qb, uint32_t ks) {
       if (elect_one_sync()) {
+        const uint32_t sb = scnt[g] & 1;
         const uint64_t qd = qdesc0 + static_cast<uint32_t>((qb * 2 + g) * (16384 >> 4));
         const uint64_t kd = kdesc0 + static_cast<uint32_t>(ks * (kA2KvBytes >> 4));
 #pragma unroll
-        for (int k = 0; k < 4; ++k) umma_bf16_ss(tmem_base + g * 256, qd + 2 * k, kd + 2 * k, idesc_s, k != 0);
-        tcgen05_commit(&s_full[g]);
+        for (int k = 0; k < 4; ++k) umma_bf16_ss(tmem_base + g * 256 + sb * kA2SCol, qd + 2 * k, kd + 2 * k, idesc_s, k != 0);
+        tcgen05_commit(&s_full[g * 2 + sb]);
       }
       __syncwarp();
+      ++scnt[g];
     };
     for (int item = blockIdx.x; item < a.num_items; item += gridDim.x, ++it) {
       const int p = item % a.n_qpairs;
       const int nvalid = (256 * p + 128 < a.N) ? 2 : 1;
       const uint32_t qb = it & 1, qph = (it >> 1) & 1;
       mbar_wait(&q_full[qb], qph);
-      {  // S(0) of both warpgroups
-        const uint32_t ks = kcount & 1, kph = (kcount >> 1) & 1;
+      // S(0) and S(1) of both warpgroups: their buffers are free once the previous item's last P V has been
+      // issued (the tensor pipe executes in order); the O columns are not touched before P V (0)
+      for (int j = 0; j < 2 && j < T; ++j, ++kcount) {
+        const uint32_t ks = kcount % kA2KvStages, kph = (kcount / kA2KvStages) & 1;
         mbar_wait(&k_full[ks], kph);
+        tcgen05_fence_after();
 #pragma unroll
-        for (int g = 0; g < 2; ++g) {
-          if (g < nvalid) {
-            if (icnt[g] > 0) mbar_wait(&o_done[g], (icnt[g] - 1) & 1);  // previous item's O has been read back
-            tcgen05_fence_after();
-            issue_s(g, qb, ks);
-          }
-        }
+        for (int g = 0; g < 2; ++g)
+          if (g < nvalid) issue_s(g, qb, ks);
         if (elect_one_sync()) tcgen05_commit(&k_empty[ks]);
         __syncwarp();
       }
-      for (int t = 0; t < T; ++t, ++kcount) {
-        const uint32_t ks = kcount & 1, kph = (kcount >> 1) & 1;
-        const uint32_t ks1 = (kcount + 1) & 1, kph1 = ((kcount + 1) >> 1) & 1;
-        mbar_wait(&v_full[ks], kph);
-        if (t + 1 < T) mbar_wait(&k_full[ks1], kph1);
+      for (int t = 0; t < T; ++t, ++vcount) {
+        const uint32_t vs = vcount % kA2KvStages, vph = (vcount / kA2KvStages) & 1;
+        const uint32_t ks2 = kcount % kA2KvStages, kph2 = (kcount / kA2KvStages) & 1;   // K(t+2), if there is one
+        const bool more = t + 2 < T;
+        mbar_wait(&v_full[vs], vph);
+        if (more) mbar_wait(&k_full[ks2], kph2);
         const int nchv = (min(KVT, a.N - t * KVT) + 15) >> 4;
 #pragma unroll
         for (int g = 0; g < 2; ++g) {
           if (g < nvalid) {
             mbar_wait(&p_full[g], pcnt[g] & 1);
-            ++pcnt[g];
+            if (t == 0 && icnt[g] > 0) mbar_wait(&o_done[g], (icnt[g] - 1) & 1);  // previous item's O has been read back
             tcgen05_fence_after();
             if (elect_one_sync()) {
-              const uint64_t vd = vdesc0 + static_cast<uint32_t>(ks * (kA2KvBytes >> 4));
+              const uint32_t pb = pcnt[g] & 1;   // P(t) lives in the buffer S(t) was computed in
+              const uint64_t vd = vdesc0 + static_cast<uint32_t>(vs * (kA2KvBytes >> 4));
 #pragma unroll
               for (int k = 0; k < NCH; ++k)
                 if (k < nchv)   // chunks past the last key were never written by the softmax warps
-                  umma_bf16_ts(tmem_base + g * 256 + kA2OCol, tmem_base + g * 256 + 8 * k, vd + 128 * k, idesc_o, (t | k) != 0);
-              if (t + 1 == T) tcgen05_commit(&o_full[g]);
+                  umma_bf16_ts(tmem_base + g * 256 + kA2OCol, tmem_base + g * 256 + pb * kA2SCol + 8 * k, vd + 128 * k, idesc_o, (t | k) != 0);
+              tcgen05_commit(&pv_done[g]);
             }
             __syncwarp();
-            if (t + 1 < T) issue_s(g, qb, ks1);   // in order behind P V: S may overwrite the P columns
+            ++pcnt[g];
+            if (more) issue_s(g, qb, ks2);   // in order behind P V (t): S(t+2) may overwrite the P(t) columns
           }
         }
         if (elect_one_sync()) {
-          tcgen05_commit(&v_empty[ks]);
-          if (t + 1 < T) tcgen05_commit(&k_empty[ks1]);
+          tcgen05_commit(&v_empty[vs]);
+          if (more) tcgen05_commit(&k_empty[ks2]);
         }
         __syncwarp();
+        if (more) ++kcount;
       }
 #pragma unroll
       for (int g = 0; g < 2; ++g) if (g < nvalid) ++icnt[g];
@@ -234,7 +241,7 @@ attention_pp_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
     const uint32_t lane_addr = tmem_base + g * 256 + (static_cast<uint32_t>(quarter * 32) << 16);
     float* myTab = sTab + (HAS_BIAS ? g * a.T : 0);
     const float sc = a.scale_log2e;
-    uint32_t scnt = 0, icnt = 0;
+    uint32_t scnt = 0, icnt = 0, pvcnt = 0;
     int cur_h = -1;
     // (Tried and rejected: forcing the two warpgroups to take strict turns at the softmax math with
     // named barriers.  A warpgroup's softmax is bound by its own serial latency, not by sharing the
@@ -267,14 +274,16 @@ attention_pp_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
         const int k0 = t * KVT;
         const int valid = min(KVT, a.N - k0);   // keys of this tile that exist
         const int nch_valid = (valid + 15) >> 4; // 16-key chunks that hold at least one of them
-        mbar_wait(&s_full[g], scnt & 1);
+        const uint32_t sb = scnt & 1;                                       // S buffer of this tile
+        const uint32_t s_addr = lane_addr + sb * kA2SCol;
+        mbar_wait(&s_full[g * 2 + sb], (scnt >> 1) & 1);
         tcgen05_fence_after();
         if (rec && t == 0) tl[1] = clock64();
         if (warp_active) {
           // ---- the whole row of S into registers: NCH loads in flight, one wait each
           uint32_t s[NCH][16];
 #pragma unroll
-          for (int c = 0; c < NCH; ++c) tmem_ld_32x32b_x16(lane_addr + c * 16, s[c]);
+          for (int c = 0; c < NCH; ++c) tmem_ld_32x32b_x16(s_addr + c * 16, s[c]);
 #pragma unroll
           for (int c = 0; c < NCH; ++c) tmem_wait_ld16(s[c]);
           // ---- logits in log2 units (+ bias), keys past the end of the image masked out
@@ -316,7 +325,12 @@ attention_pp_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
           const float m_new = fmaxf(m_run, mt);
           const float alpha = a2_exp2(m_run - m_new);   // first tile: exp2(-inf) = 0
           m_run = m_new;
-          // ---- rescale the O accumulated so far (every earlier MMA is complete: s_full covers them)
+          // ---- the previous P V must have landed in O before O is rescaled
+          if (t > 0) {
+            mbar_wait(&pv_done[g], pvcnt & 1);
+            tcgen05_fence_after();
+          }
+          // ---- rescale the O accumulated so far
           if (t > 0 && __any_sync(0xffffffffu, alpha != 1.0f)) {
             uint32_t ob[16];
 #pragma unroll
@@ -374,12 +388,18 @@ attention_pp_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
                 pk[i >> 1] = pack_bf16x2(p[i], p[i + 1]);
                 pk[(i >> 1) + 1] = pack_bf16x2(p[i + 2], p[i + 3]);
               }
-              tmem_st_32x32b_x8(lane_addr + c * 8, pk);
+              tmem_st_32x32b_x8(s_addr + c * 8, pk);
             }
           }
           l_run = l_run * alpha + ((ps[0] + ps[1]) + (ps[2] + ps[3]));
           tcgen05_wait_st();
         }
+        else if (t > 0) {
+          // warps past the last row have no math to do, but must not run ahead: with S double-buffered a
+          // free-running warp could arrive on p_full for step t+1 while step t is still collecting arrivals
+          mbar_wait(&pv_done[g], pvcnt & 1);
+        }
+        if (t > 0) ++pvcnt;   // one pv_done phase per P V
         tcgen05_fence_before();
         __syncwarp();
         if (lane == 0) mbar_arrive(&p_full[g]);
@@ -387,7 +407,8 @@ attention_pp_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
 
       // ---- O of the item: normalise and store (merged heads)
       if (rec) tl[2] = clock64();
-      mbar_wait(&o_full[g], icnt & 1);
+      mbar_wait(&pv_done[g], pvcnt & 1);   // the last P V of the item
+      ++pvcnt;
       tcgen05_fence_after();
       if (rec) tl[3] = clock64();
       if (warp_active) {

@@ -393,7 +393,7 @@ int ldit_attention(const void* qkv, void* ctx, const void* bias_table, int B, in
     if (smem > 227 * 1024) return LDIT_E_SHAPE;
     const int grid = a.num_items < num_sms() ? a.num_items : num_sms();
     const int nch = a.kv_tile / 16;
-    static size_t max_set[2][9] = {};
+    static size_t max_set[2][7] = {};
     const int bi = bias_table ? 1 : 0;
     cudaError_t e = cudaSuccess;
 #define LDIT_ATTN_CASE(NCH)                                                                                             \
@@ -409,7 +409,7 @@ int ldit_attention(const void* qkv, void* ctx, const void* bias_table, int B, in
     break;
     switch (nch) {
       LDIT_ATTN_CASE(1) LDIT_ATTN_CASE(2) LDIT_ATTN_CASE(3) LDIT_ATTN_CASE(4)
-      LDIT_ATTN_CASE(5) LDIT_ATTN_CASE(6) LDIT_ATTN_CASE(7) LDIT_ATTN_CASE(8)
+      LDIT_ATTN_CASE(5) LDIT_ATTN_CASE(6)
       default: return LDIT_E_SHAPE;
     }
 #undef LDIT_ATTN_CASE
