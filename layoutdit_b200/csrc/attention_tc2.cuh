@@ -385,8 +385,8 @@ attention_pp_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
 #pragma unroll
               for (int i = 0; i < 16; i += 4) {
                 ps[0] += p[i]; ps[1] += p[i + 1]; ps[2] += p[i + 2]; ps[3] += p[i + 3];
-                pk[i >> 1] = pack_bf16x2(p[i], p[i + 1]);
-                pk[(i >> 1) + 1] = pack_bf16x2(p[i + 2], p[i + 3]);
+                pk[i >> 1] = pack_bf16x2_alu(p[i], p[i + 1]);
+                pk[(i >> 1) + 1] = pack_bf16x2_alu(p[i + 2], p[i + 3]);
               }
               tmem_st_32x32b_x8(s_addr + c * 8, pk);
             }

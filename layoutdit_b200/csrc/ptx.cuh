@@ -345,6 +345,12 @@ __device__ __forceinline__ uint32_t pack_bf16x2(float lo, float hi) {
   __nv_bfloat162 v = __floats2bfloat162_rn(lo, hi);
   return *reinterpret_cast<uint32_t*>(&v);
 }
+// Same packing on the integer pipe: F2FP is a conversion instruction and shares the quarter-rate XU
+// pipe with MUFU.EX2, which is the binding unit of the softmax.  Round-half-up on the magnitude
+// instead of round-half-even: differs from cvt.rn only on exact ties (1 in 2^16 mantissas).
+__device__ __forceinline__ uint32_t pack_bf16x2_alu(float lo, float hi) {
+  return __byte_perm(__float_as_uint(lo) + 0x8000u, __float_as_uint(hi) + 0x8000u, 0x7632);
+}
 __device__ __forceinline__ float gelu_erf(float x) { return 0.5f * x * (1.0f + erff(x * 0.70710678118654752f)); }
 
 __device__ __forceinline__ void cp_async_16(void* smem_dst, const void* gsrc, bool valid) {
