@@ -85,6 +85,27 @@ int ldit_attention(const void* qkv, void* ctx, const void* bias_table, int B, in
  *  (any positive scale is accepted). */
 int ldit_resample_taps(const void* x, void* out, int B, int Gh, int Gw, int D, float scale, void* stream);
 
+/* ---- FPN on the taps: TV = torchvision/ops/feature_pyramid_network.py (0.26),
+ * as instantiated at R:dit_backbone.py:80-90.  All tensors bf16 channels-last.
+ *
+ * Lateral 1x1 convolutions (TV:111-116, 187) are ldit_gemm_bias calls on the token grid BEFORE resampling
+ * (1x1 conv and bilinear resampling commute); ldit_fpn_merge then does R:57-59's bilinear resample of that
+ * lateral plus the nearest-neighbour top-down add (TV:188-190):
+ *   out [B, oh, ow, C] = bilinear(lat [B, Gh, Gw, C], scale) + nearest(top [B, top_h, top_w, C] -> oh x ow)
+ * with oh = floor(Gh*scale), ow = floor(Gw*scale); top may be NULL (coarsest level). */
+int ldit_fpn_merge(const void* lat, const void* top, void* out, int B, int Gh, int Gw, int C, float scale, int top_h,
+                   int top_w, void* stream);
+
+/* Conv2d(Cin, Cout, 3, padding=1) + bias (the FPN layer_blocks, TV:118-124, 193) as an implicit tcgen05 GEMM.
+ *  in  bf16 [B, H, W, Cin]   w bf16 [Cout, 9*Cin] = conv.weight.permute(0, 2, 3, 1) flattened ((ky, kx, cin))
+ *  bias f32 [Cout] or NULL   out bf16 [B, H, W, Cout].  Cin multiple of 64, Cout multiple of 128. */
+int ldit_conv3x3_bias(const void* in, const void* w, const void* bias, void* out, int B, int H, int W, int Cin, int Cout,
+                      void* stream);
+
+/* LastLevelMaxPool (TV:231-249): max_pool2d(kernel 1, stride 2) = out[b, y, x, :] = in[b, 2y, 2x, :];
+ * out is [B, ceil(H/2), ceil(W/2), C]. */
+int ldit_subsample2(const void* in, void* out, int B, int H, int W, int C, void* stream);
+
 /* Bytes of the im2col scratch ldit_patch_embed needs. */
 size_t ldit_patch_embed_scratch_bytes(int B, int H, int W);
 

@@ -21,6 +21,11 @@
 //               tcgen05.ld -> registers -> bias / erf-GELU / layer-scale -> swizzled smem staging
 //               -> TMA store (bf16 outputs) or TMA reduce-add into the fp32 residual stream
 //
+// EPI_CONV_BIAS runs the FPN's 3x3 convolutions (TV:ops/feature_pyramid_network.py:118-124, 193) through the
+// same pipeline as an implicit GEMM: the A tile of k-block (tap, channel block) is ONE 4-D TMA box of the
+// channels-last input shifted by the tap offset -- out-of-image coordinates are zero-filled by the TMA unit,
+// which is the convolution's padding -- so no im2col matrix ever exists in memory.
+//
 // Replaces the cuBLAS calls behind nn.Linear at HF:324-338 (QKV), HF:383 (+HF:488-492),
 // HF:429-430 and HF:442 (+HF:500-504), and the conv at HF:218 (as an im2col GEMM).
 #pragma once
@@ -29,7 +34,7 @@
 
 namespace ldit {
 
-enum : int { EPI_BIAS = 0, EPI_BIAS_GELU = 1, EPI_SCALE_RESID = 2, EPI_PATCH = 3 };
+enum : int { EPI_BIAS = 0, EPI_BIAS_GELU = 1, EPI_SCALE_RESID = 2, EPI_PATCH = 3, EPI_CONV_BIAS = 4 };
 
 struct GemmArgs {
   int M, N, K;
@@ -41,6 +46,10 @@ struct GemmArgs {
   int P;               // EPI_PATCH: patches per image; GEMM row b*P+p -> token row b*(P+1)+1+p
   const float* posb;   // EPI_PATCH: [P, N] fp32 = position rows 1..P + conv bias
   int num_m_blocks, num_n_blocks;
+  // EPI_CONV_BIAS (3x3 convolution, stride 1, zero padding 1, over a channels-last image [B, H, W, Cin] as an
+  // implicit GEMM): a CTA's 128 rows are a cv_th x cv_tw patch of output pixels, a CTA pair covers two patches
+  // side by side; an image is cv_ty x cv_tx pair tiles; K = 9 taps x Cin in (ky, kx, cin) order, cv_cblocks = Cin/64
+  int cv_tw, cv_th, cv_tx, cv_ty, cv_cblocks;
   int dbg;             // experiments only (LDIT_GEMM_DBG): bit 0 = epilogue drains TMEM but stores nothing
   long long* tl;       // experiments only: clock64 timeline [cluster][16 tiles][8] (leader CTA), or nullptr
 };
@@ -159,6 +168,7 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
                     const __grid_constant__ CUtensorMap tmC, const GemmArgs g) {
   using Cfg = GemmCfg<BN, EPI, CTAS>;
   constexpr int S = Cfg::STAGES;
+  static_assert(EPI != EPI_CONV_BIAS || (CTAS == 2 && LDIT_KSTEP == 1), "the convolution mode is written for CTA pairs, one ring slot per step");
   pdl_launch_dependents();
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
@@ -229,6 +239,14 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
     for (int tile = cluster_id; tile < num_tiles; tile += num_clusters, ++pti) {
       const int m0 = (tile / g.num_n_blocks) * Cfg::TILE_M + static_cast<int>(rank) * kBM;
       const int n0 = (tile % g.num_n_blocks) * BN + static_cast<int>(rank) * Cfg::B_ROWS;
+      int cvx = 0, cvy = 0, cvb = 0, cv_c = 0, cv_kx = 0, cv_ky = 0;   // EPI_CONV_BIAS: patch origin, running (ky, kx, channel block)
+      if constexpr (EPI == EPI_CONV_BIAS) {
+        const int mb = tile / g.num_n_blocks, per_img = g.cv_tx * g.cv_ty;
+        cvb = mb / per_img;
+        const int r = mb - cvb * per_img, ty = r / g.cv_tx;
+        cvx = ((r - ty * g.cv_tx) * 2 + static_cast<int>(rank)) * g.cv_tw;
+        cvy = ty * g.cv_th;
+      }
       long long* ptl = (g.tl != nullptr && rank == 0 && lane == 0 && pti < 16) ? g.tl + (static_cast<size_t>(cluster_id) * 16 + pti) * 16 : nullptr;
       long long wempty = 0;
       for (int kb = 0; kb < nkb; kb += kstep) {
@@ -242,7 +260,10 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
             if constexpr (CTAS == 2) {
               if (rank == 0) mbar_arrive_expect_tx(&full_bar[st], Cfg::STAGE_BYTES * 2);
               const uint32_t leader_full = mapa_shared(smem_u32(&full_bar[st]), 0);
-              tma_load_2d_cg2(sA + st * Cfg::A_BYTES, &tmA, leader_full, (kb + j) * kBK, m0);
+              if constexpr (EPI == EPI_CONV_BIAS)
+                tma_load_4d_cg2(sA + st * Cfg::A_BYTES, &tmA, leader_full, cv_c * kBK, cvx + cv_kx - 1, cvy + cv_ky - 1, cvb);
+              else
+                tma_load_2d_cg2(sA + st * Cfg::A_BYTES, &tmA, leader_full, (kb + j) * kBK, m0);
               tma_load_2d_cg2(sB + st * Cfg::B_BYTES, &tmB, leader_full, (kb + j) * kBK, n0);
             } else {
               mbar_arrive_expect_tx(&full_bar[st], Cfg::STAGE_BYTES);
@@ -252,6 +273,9 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
           }
         }
         __syncwarp();
+        if constexpr (EPI == EPI_CONV_BIAS) {   // next k-block: channel block fastest, then kx, then ky
+          if (++cv_c == g.cv_cblocks) { cv_c = 0; if (++cv_kx == 3) { cv_kx = 0; ++cv_ky; } }
+        }
         stage += kstep;
         if (stage >= S) { stage = 0; phase ^= 1; }
       }
@@ -345,6 +369,14 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
     for (int tile = cluster_id; tile < num_tiles; tile += num_clusters, ++ti) {
       const int row0 = (tile / g.num_n_blocks) * Cfg::TILE_M + row_in_tile;
       const int col0 = (tile % g.num_n_blocks) * BN + cgrp * Cfg::CG_COLS;
+      int cvx = 0, cvy = 0, cvb = 0;   // EPI_CONV_BIAS: first pixel of this warp's 32 rows (32 / cv_tw image rows of cv_tw pixels)
+      if constexpr (EPI == EPI_CONV_BIAS) {
+        const int mb = tile / g.num_n_blocks, per_img = g.cv_tx * g.cv_ty;
+        cvb = mb / per_img;
+        const int r = mb - cvb * per_img, ty = r / g.cv_tx;
+        cvx = ((r - ty * g.cv_tx) * 2 + static_cast<int>(rank)) * g.cv_tw;
+        cvy = ty * g.cv_th + quarter * (32 / g.cv_tw);
+      }
       long long* tl = (g.tl != nullptr && rank == 0 && warp == 0 && lane == 0 && ti < 16)
                           ? g.tl + (static_cast<size_t>(cluster_id) * 16 + ti) * 16 : nullptr;
 
@@ -498,6 +530,7 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
           __syncwarp();
           if (lane == 0 && col_ok && !(g.dbg & 2)) {
             if constexpr (EPI == EPI_SCALE_RESID) { if (g.dbg & 32) tma_store_2d(&tmC, buf, col, row0); else tma_reduce_add_2d(&tmC, buf, col, row0); }
+            else if constexpr (EPI == EPI_CONV_BIAS) tma_store_4d(&tmC, buf, col, cvx, cvy, cvb);   // pixels past the image edge are clipped
             else tma_store_2d(&tmC, buf, col, row0);
             tma_store_commit();
           }

@@ -75,6 +75,20 @@ int make_tmap_qkv_3d(CUtensorMap* tm, const void* ptr, uint64_t B, uint64_t N, u
   return r == CUDA_SUCCESS ? 0 : 10000 + static_cast<int>(r);
 }
 
+// channels-last image [B, H, W, C] bf16 as a 4-D tensor (C fastest): box [1, box_h, box_w, box_c]
+int make_tmap_nhwc_4d(CUtensorMap* tm, const void* ptr, uint64_t B, uint64_t H, uint64_t W, uint64_t C, uint32_t box_c,
+                      uint32_t box_w, uint32_t box_h, CUtensorMapSwizzle swz) {
+  EncodeTiledFn fn = encode_fn();
+  if (!fn) return LDIT_E_NO_DRIVER;
+  cuuint64_t dims[4] = {C, W, H, B};
+  cuuint64_t strides[3] = {C * 2, W * C * 2, H * W * C * 2};
+  cuuint32_t box[4] = {box_c, box_w, box_h, 1};
+  cuuint32_t estr[4] = {1, 1, 1, 1};
+  CUresult r = fn(tm, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, const_cast<void*>(ptr), dims, strides, box, estr,
+                  CU_TENSOR_MAP_INTERLEAVE_NONE, swz, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  return r == CUDA_SUCCESS ? 0 : 10000 + static_cast<int>(r);
+}
+
 long long* g_gemm_tl = nullptr;   // experiments only: device buffer for the GEMM timeline
 long long* g_attn_dbg = nullptr;  // experiments only: device buffer for the attention timeline
 std::atomic<int> g_attn_impl{-1};  // 0 = persistent ping-pong tcgen05 (default), 1 = mma.sync, 2 = one-tile-per-CTA tcgen05
@@ -178,15 +192,11 @@ int pick_bn(int M, int N, int ctas) {
 }
 
 template <int BN, int EPI, int CTAS>
+int launch_gemm_maps(const CUtensorMap& tmA, const CUtensorMap& tmB, const CUtensorMap& tmC, GemmArgs g, cudaStream_t st);
+
+template <int BN, int EPI, int CTAS>
 int launch_gemm_t(const void* A, const void* W, GemmArgs g, cudaStream_t st) {
   using Cfg = GemmCfg<BN, EPI, CTAS>;
-  static bool attr_set = false;
-  if (!attr_set) {
-    cudaError_t e = cudaFuncSetAttribute(gemm_tcgen05_kernel<BN, EPI, CTAS>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                         Cfg::SMEM_BYTES);
-    if (e != cudaSuccess) return static_cast<int>(e);
-    attr_set = true;
-  }
   CUtensorMap tmA, tmB, tmC;
   int rc = make_tmap_bf16_2d(&tmA, A, g.M, g.K, kBM);
   if (rc) return rc;
@@ -199,10 +209,23 @@ int launch_gemm_t(const void* A, const void* W, GemmArgs g, cudaStream_t st) {
   } else {
     tmC = tmA;
   }
+  g.num_m_blocks = (g.M + Cfg::TILE_M - 1) / Cfg::TILE_M;
+  return launch_gemm_maps<BN, EPI, CTAS>(tmA, tmB, tmC, g, st);
+}
+
+template <int BN, int EPI, int CTAS>
+int launch_gemm_maps(const CUtensorMap& tmA, const CUtensorMap& tmB, const CUtensorMap& tmC, GemmArgs g, cudaStream_t st) {
+  using Cfg = GemmCfg<BN, EPI, CTAS>;
+  static bool attr_set = false;
+  if (!attr_set) {
+    cudaError_t e = cudaFuncSetAttribute(gemm_tcgen05_kernel<BN, EPI, CTAS>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                         Cfg::SMEM_BYTES);
+    if (e != cudaSuccess) return static_cast<int>(e);
+    attr_set = true;
+  }
   static const int dbg = [] { const char* e = getenv("LDIT_GEMM_DBG"); return e ? atoi(e) : 0; }();
   g.dbg = dbg;
   g.tl = g_gemm_tl;
-  g.num_m_blocks = (g.M + Cfg::TILE_M - 1) / Cfg::TILE_M;
   g.num_n_blocks = (g.N + BN - 1) / BN;
   const int tiles = g.num_m_blocks * g.num_n_blocks;
   const int units = num_sms() / CTAS;
@@ -234,6 +257,20 @@ int launch_gemm(const void* A, const void* W, GemmArgs g, cudaStream_t st) {
     case 192: return launch_gemm_t<192, EPI, 1>(A, W, g, st);
     default: return launch_gemm_t<256, EPI, 1>(A, W, g, st);
   }
+}
+
+// 3x3 convolution as an implicit GEMM (EPI_CONV_BIAS): tensor maps over the channels-last images, patch shape
+template <int BN>
+int launch_conv_t(const void* in, const void* w, GemmArgs g, int B, int H, int W, int Cin, cudaStream_t st) {
+  using Cfg = GemmCfg<BN, EPI_CONV_BIAS, 2>;
+  CUtensorMap tmA, tmB, tmC;
+  int rc = make_tmap_nhwc_4d(&tmA, in, B, H, W, Cin, 64, g.cv_tw, g.cv_th, CU_TENSOR_MAP_SWIZZLE_128B);
+  if (rc) return rc;
+  rc = make_tmap_bf16_2d(&tmB, w, g.N, g.K, Cfg::B_ROWS);
+  if (rc) return rc;
+  rc = make_tmap_nhwc_4d(&tmC, g.out, B, H, W, g.N, kEpiCols, g.cv_tw, 32 / g.cv_tw, CU_TENSOR_MAP_SWIZZLE_32B);
+  if (rc) return rc;
+  return launch_gemm_maps<BN, EPI_CONV_BIAS, 2>(tmA, tmB, tmC, g, st);
 }
 
 }  // namespace
@@ -488,6 +525,60 @@ int ldit_resample_taps(const void* x, void* out, int B, int Gh, int Gw, int D, f
   dim3 block(D / 8, kTapPix);
   dim3 grid((oh * ow + kTapPix - 1) / kTapPix, B);
   launch_kernel(resample_taps_kernel, grid, block, 0, static_cast<cudaStream_t>(stream), 1, static_cast<const float*>(x), static_cast<__nv_bfloat16*>(out), Gh * Gw + 1, D, Gh, Gw, oh, ow, 1.0f / scale);
+  return check_launch();
+}
+
+int ldit_fpn_merge(const void* lat, const void* top, void* out, int B, int Gh, int Gw, int C, float scale, int top_h,
+                   int top_w, void* stream) {
+  if (!lat || !out) return LDIT_E_NULL;
+  if (B <= 0 || B > 65535 || Gh <= 0 || Gw <= 0 || C <= 0 || (C % 8) || C / 8 > 1024 || !(scale > 0.f)) return LDIT_E_SHAPE;
+  if (top && (top_h <= 0 || top_w <= 0)) return LDIT_E_SHAPE;
+  if (!aligned16(lat) || !aligned16(top) || !aligned16(out)) return LDIT_E_ALIGN;
+  const int oh = static_cast<int>(floorf(Gh * scale)), ow = static_cast<int>(floorf(Gw * scale));
+  if (oh <= 0 || ow <= 0) return LDIT_E_SHAPE;
+  const int pix = (1024 / (C / 8)) < 8 ? (1024 / (C / 8)) : 8;   // output pixels per block
+  dim3 block(C / 8, pix);
+  dim3 grid((oh * ow + pix - 1) / pix, B);
+  launch_kernel(fpn_merge_kernel, grid, block, 0, static_cast<cudaStream_t>(stream), 1, static_cast<const __nv_bfloat16*>(lat),
+                static_cast<const __nv_bfloat16*>(top), static_cast<__nv_bfloat16*>(out), C, Gh, Gw, oh, ow, 1.0f / scale, top_h, top_w);
+  return check_launch();
+}
+
+int ldit_conv3x3_bias(const void* in, const void* w, const void* bias, void* out, int B, int H, int W, int Cin, int Cout,
+                      void* stream) {
+  if (!in || !w || !out) return LDIT_E_NULL;
+  if (B <= 0 || H <= 0 || W <= 0 || Cin <= 0 || (Cin % 64) || Cout <= 0 || (Cout % 128)) return LDIT_E_SHAPE;
+  if (!aligned16(in) || !aligned16(w) || !aligned16(bias) || !aligned16(out)) return LDIT_E_ALIGN;
+  GemmArgs g{};
+  g.N = Cout; g.K = 9 * Cin;
+  g.bias = static_cast<const float*>(bias);
+  g.out = out; g.ldo = Cout;
+  // patch shape: 128 output pixels per CTA as th x tw, a pair covers th x 2tw; fewest pair tiles wins
+  long best = -1;
+  const int tws[3] = {16, 8, 32};
+  for (int tw : tws) {
+    const int th = 128 / tw;
+    const long tiles = static_cast<long>((W + 2 * tw - 1) / (2 * tw)) * ((H + th - 1) / th);
+    if (best < 0 || tiles < best) { best = tiles; g.cv_tw = tw; g.cv_th = th; }
+  }
+  g.cv_tx = (W + 2 * g.cv_tw - 1) / (2 * g.cv_tw);
+  g.cv_ty = (H + g.cv_th - 1) / g.cv_th;
+  g.cv_cblocks = Cin / 64;
+  g.num_m_blocks = B * g.cv_tx * g.cv_ty;
+  g.M = g.num_m_blocks * 256;   // rows of the implicit GEMM including the pixels past the image edge
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  const int bn = (Cout % 256 == 0) ? pick_bn(g.M, Cout, 2) : 128;
+  if (bn == 256) return launch_conv_t<256>(in, w, g, B, H, W, Cin, st);
+  return launch_conv_t<128>(in, w, g, B, H, W, Cin, st);
+}
+
+int ldit_subsample2(const void* in, void* out, int B, int H, int W, int C, void* stream) {
+  if (!in || !out) return LDIT_E_NULL;
+  if (B <= 0 || H <= 0 || W <= 0 || C <= 0 || (C % 8)) return LDIT_E_SHAPE;
+  if (!aligned16(in) || !aligned16(out)) return LDIT_E_ALIGN;
+  const size_t n = static_cast<size_t>(B) * ((H + 1) / 2) * ((W + 1) / 2) * (C / 8);
+  launch_kernel(subsample2_kernel, dim3(static_cast<unsigned>((n + 255) / 256)), dim3(256), 0, static_cast<cudaStream_t>(stream), 1,
+                static_cast<const __nv_bfloat16*>(in), static_cast<__nv_bfloat16*>(out), B, H, W, C);
   return check_launch();
 }
 

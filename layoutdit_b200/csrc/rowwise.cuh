@@ -231,4 +231,69 @@ upsample_taps_kernel(const float* __restrict__ xres, __nv_bfloat16* __restrict__
   }
 }
 
+// ------------------------------------------------------------------ FPN top-down pathway
+// torchvision FeaturePyramidNetwork.forward (TV:ops/feature_pyramid_network.py:172-196) on a DiT pyramid:
+//     inner_i = inner_blocks[i](resample_s(h_i)) + F.interpolate(inner_{i+1}, size=..., mode="nearest")
+// The 1x1 lateral convolution and the bilinear resampling of R:dit_backbone.py:57-59 are both linear and the
+// bilinear weights sum to one, so they commute: the lateral runs FIRST, as a GEMM on the Gh x Gw token grid
+// (256 instead of D channels, 1/16 .. 4x fewer pixels), and this kernel resamples its output `lat`
+// [B, Gh, Gw, C] bf16 to [B, oh, ow, C] (ATen's bilinear rule, align_corners=False, as in
+// resample_taps_kernel) and adds the nearest-neighbour up-sampled coarser level `top` [B, th, tw, C]
+// (ATen nearest: src = min(floor(dst * in / out), in - 1)), fp32 math, bf16 out.  The D-channel taps of the
+// reference are never written.  blockDim = (C/8, kTapPix), gridDim = (ceil(oh*ow / kTapPix), B).
+__global__ void __launch_bounds__(1024)
+fpn_merge_kernel(const __nv_bfloat16* __restrict__ lat, const __nv_bfloat16* __restrict__ top, __nv_bfloat16* __restrict__ out,
+                 int C, int Gh, int Gw, int oh, int ow, float inv_scale, int th, int tw) {
+  pdl_launch_dependents();
+  pdl_wait();
+  const int pix = blockIdx.x * blockDim.y + threadIdx.y;
+  if (pix >= oh * ow) return;
+  const int b = blockIdx.y;
+  const int oy = pix / ow, ox = pix - oy * ow;
+  const float sy = fmaxf((oy + 0.5f) * inv_scale - 0.5f, 0.f);
+  const float sx = fmaxf((ox + 0.5f) * inv_scale - 0.5f, 0.f);
+  const int y0 = min(static_cast<int>(sy), Gh - 1), x0 = min(static_cast<int>(sx), Gw - 1);
+  const int y1 = min(y0 + 1, Gh - 1), x1 = min(x0 + 1, Gw - 1);
+  const float ly = sy - y0, lx = sx - x0;
+  const float w00 = (1.f - ly) * (1.f - lx), w01 = (1.f - ly) * lx, w10 = ly * (1.f - lx), w11 = ly * lx;
+  const __nv_bfloat16* base = lat + static_cast<size_t>(b) * Gh * Gw * C + threadIdx.x * 8;
+  float v00[8], v01[8], v10[8], v11[8], acc[8];
+  load8<__nv_bfloat16>(base + static_cast<size_t>(y0 * Gw + x0) * C, v00);
+  load8<__nv_bfloat16>(base + static_cast<size_t>(y0 * Gw + x1) * C, v01);
+  load8<__nv_bfloat16>(base + static_cast<size_t>(y1 * Gw + x0) * C, v10);
+  load8<__nv_bfloat16>(base + static_cast<size_t>(y1 * Gw + x1) * C, v11);
+#pragma unroll
+  for (int e = 0; e < 8; ++e) acc[e] = w00 * v00[e] + w01 * v01[e] + w10 * v10[e] + w11 * v11[e];
+  if (top != nullptr) {
+    const int ty = min(static_cast<int>(floorf(oy * (static_cast<float>(th) / oh))), th - 1);
+    const int tx = min(static_cast<int>(floorf(ox * (static_cast<float>(tw) / ow))), tw - 1);
+    float t[8];
+    load8<__nv_bfloat16>(top + ((static_cast<size_t>(b) * th + ty) * tw + tx) * C + threadIdx.x * 8, t);
+#pragma unroll
+    for (int e = 0; e < 8; ++e) acc[e] += t[e];
+  }
+  uint4 o;
+  o.x = pack_bf16x2(acc[0], acc[1]); o.y = pack_bf16x2(acc[2], acc[3]);
+  o.z = pack_bf16x2(acc[4], acc[5]); o.w = pack_bf16x2(acc[6], acc[7]);
+  *reinterpret_cast<uint4*>(out + (static_cast<size_t>(b) * oh * ow + pix) * C + threadIdx.x * 8) = o;
+}
+
+// LastLevelMaxPool (TV:ops/feature_pyramid_network.py:231-249): max_pool2d(kernel 1, stride 2) == every second
+// pixel of every second row.  in [B, H, W, C] -> out [B, ceil(H/2), ceil(W/2), C], bf16, 16 bytes per thread.
+__global__ void __launch_bounds__(256)
+subsample2_kernel(const __nv_bfloat16* __restrict__ in, __nv_bfloat16* __restrict__ out, int B, int H, int W, int C) {
+  pdl_launch_dependents();
+  pdl_wait();
+  const int oh = (H + 1) / 2, ow = (W + 1) / 2, c8 = C / 8;
+  const size_t idx = static_cast<size_t>(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (idx >= static_cast<size_t>(B) * oh * ow * c8) return;
+  const int c = static_cast<int>(idx % c8);
+  size_t t = idx / c8;
+  const int x = static_cast<int>(t % ow); t /= ow;
+  const int y = static_cast<int>(t % oh);
+  const int b = static_cast<int>(t / oh);
+  reinterpret_cast<uint4*>(out)[idx] =
+      __ldg(reinterpret_cast<const uint4*>(in + ((static_cast<size_t>(b) * H + 2 * y) * W + 2 * x) * C) + c);
+}
+
 }  // namespace ldit

@@ -72,12 +72,25 @@ class _Geometry:
     graph_in: torch.Tensor | None = None
     graph_out: OrderedDict | None = None
     launches: int = 0
+    head: str = "taps"       # "taps": the four D-channel taps of DiTBackbone; "fpn": DiTWithFPN's p2..p5 + pool
     extra: dict = field(default_factory=dict)
+
+
+@dataclass
+class _FpnPack:
+    """torchvision FeaturePyramidNetwork weights (TV:ops/feature_pyramid_network.py:104-124) in kernel layout."""
+    w_lat: list      # 4 x bf16 [C, D]       inner_blocks[i][0].weight[:, :, 0, 0]
+    b_lat: list      # 4 x f32 [C]
+    w_out: list      # 4 x bf16 [C, 9*C]     layer_blocks[i][0].weight.permute(0, 2, 3, 1): (ky, kx, cin) columns
+    b_out: list      # 4 x f32 [C]
+    C: int
 
 
 class Engine:
     def __init__(self, params: DiTParameters, cfg: DiTConfig):
         self.params = params
+        self.fpn_params = None   # set by DiTWithFPN: holder of the torchvision-named FPN parameters
+        self._fpn: _FpnPack | None = None
         self.cfg = cfg
         self.lib = _lib.load()
         self._pack_key = None
@@ -87,7 +100,10 @@ class Engine:
 
     # ------------------------------------------------------------------ weight packing
     def _weights_key(self):
-        return tuple((p.data_ptr(), p._version) for p in self.params.parameters())
+        ps = list(self.params.parameters())
+        if self.fpn_params is not None:
+            ps += list(self.fpn_params.parameters())
+        return tuple((p.data_ptr(), p._version) for p in ps)
 
     def refresh_weights(self, force: bool = False):
         key = self._weights_key()
@@ -126,6 +142,14 @@ class Engine:
                     rel_table=(f32(at.relative_position_bias.relative_position_bias_table)
                                if cfg.use_relative_position_bias else None)))
             self._layers = layers
+            if self.fpn_params is not None:
+                F_ = self.fpn_params
+                C = F_.out_channels
+                self._fpn = _FpnPack(
+                    w_lat=[bf16(m[0].weight.reshape(C, -1)) for m in F_.inner_blocks],
+                    b_lat=[f32(m[0].bias) for m in F_.inner_blocks],
+                    w_out=[bf16(m[0].weight.permute(0, 2, 3, 1).reshape(C, -1)) for m in F_.layer_blocks],
+                    b_out=[f32(m[0].bias) for m in F_.layer_blocks], C=C)
         self._pack_key = key
         self._geoms.clear()  # resized tables and captured graphs hold the old weights
         self.device = dev
@@ -152,10 +176,10 @@ class Engine:
         new = new.permute(0, 2, 3, 1).reshape(nh * nw, -1)
         return torch.cat([new, table[old * old:]], dim=0).t().contiguous()
 
-    def _geometry(self, B, H, W, slot: int = 0) -> _Geometry:
+    def _geometry(self, B, H, W, slot: int = 0, head: str = "taps") -> _Geometry:
         """Workspaces / tables / graph for one (B, H, W).  ``slot`` > 0 gives an independent copy
         (own workspaces, own captured graph, own static outputs) for pipelined callers."""
-        key = (B, H, W) if slot == 0 else (B, H, W, slot)
+        key = (B, H, W) if (slot == 0 and head == "taps") else (B, H, W, slot, head)
         geo = self._geoms.get(key)
         if geo is not None:
             return geo
@@ -183,18 +207,29 @@ class Engine:
                         x=torch.empty(M, D, device=dev, dtype=torch.float32),
                         a=torch.empty(M, D, device=dev, dtype=torch.bfloat16),
                         big=torch.empty(M * wide, device=dev, dtype=torch.bfloat16),
-                        pos_bias=pos_bias, cls_pos=cls_pos, bias_tables=tables)
+                        pos_bias=pos_bias, cls_pos=cls_pos, bias_tables=tables, head=head)
+        if head == "fpn":
+            C = self._fpn.C
+            bf = dict(device=dev, dtype=torch.bfloat16)
+            geo.extra["tok"] = torch.empty(B * P, D, **bf)                        # tap tokens without CLS, bf16
+            geo.extra["lat"] = [torch.empty(B * P, C, **bf) for _ in TAP_SCALES]   # laterals on the token grid
+            geo.extra["inner"] = [torch.empty(B, *self._tap_hw(geo, s), C, **bf) for s in TAP_SCALES]
         self._geoms[key] = geo
         return geo
 
     # -------------------------------------------------------------------- launch sequence
+    @staticmethod
+    def _tap_hw(geo, s):
+        return int(math.floor(geo.Gh * s)), int(math.floor(geo.Gw * s))
+
     def _alloc_outputs(self, geo: _Geometry):
-        D = self.cfg.hidden_size
-        outs = []
-        for s in TAP_SCALES:
-            oh, ow = int(math.floor(geo.Gh * s)), int(math.floor(geo.Gw * s))
-            outs.append(torch.empty(geo.B, oh, ow, D, device=self.device, dtype=torch.bfloat16))
-        return outs
+        bf = dict(device=self.device, dtype=torch.bfloat16)
+        if geo.head == "fpn":   # p2..p5 of the FPN + "pool" (TV:231-249), C channels each
+            C = self._fpn.C
+            outs = [torch.empty(geo.B, *self._tap_hw(geo, s), C, **bf) for s in TAP_SCALES]
+            h5, w5 = self._tap_hw(geo, TAP_SCALES[-1])
+            return outs + [torch.empty(geo.B, (h5 + 1) // 2, (w5 + 1) // 2, C, **bf)]
+        return [torch.empty(geo.B, *self._tap_hw(geo, s), self.cfg.hidden_size, **bf) for s in TAP_SCALES]
 
     def _plan(self, geo: _Geometry, x: torch.Tensor, outs, stream: int):
         """The forward as an ordered list of (name, C-ABI function, args): one entry per
@@ -208,12 +243,23 @@ class Engine:
                  (x.data_ptr(), _DTYPE_CODE[x.dtype], self.w_patch.data_ptr(), geo.pos_bias.data_ptr(),
                   geo.cls_pos.data_ptr(), big, xr, B, geo.H, geo.W, D, stream))]
 
+        fpn = self._fpn if geo.head == "fpn" else None
+
         def emit_tap(layer_no):
             # hidden_states[layer_no] is the residual stream right now (HF:628-630, 654-655)
             for slot, idx in enumerate(self.tap_idx):
-                if idx == layer_no:
+                if idx != layer_no:
+                    continue
+                if fpn is None:
                     plan.append(("ldit_resample_taps", lib.ldit_resample_taps,
                                  (xr, outs[slot].data_ptr(), B, geo.Gh, geo.Gw, D, TAP_SCALES[slot], stream)))
+                else:
+                    # FPN head: the 1x1 lateral (TV:187) runs on the token grid, before R:57-59's resampling
+                    # (both linear, they commute): CLS-less bf16 copy of the tokens, then a GEMM to C channels
+                    tok, lat = geo.extra["tok"].data_ptr(), geo.extra["lat"][slot].data_ptr()
+                    plan.append(("ldit_resample_taps", lib.ldit_resample_taps, (xr, tok, B, geo.Gh, geo.Gw, D, 1.0, stream)))
+                    plan.append(("ldit_gemm_bias", lib.ldit_gemm_bias,
+                                 (tok, fpn.w_lat[slot].data_ptr(), fpn.b_lat[slot].data_ptr(), lat, B * geo.Gh * geo.Gw, fpn.C, D, stream)))
 
         emit_tap(0)
         for i, L in enumerate(self._layers):
@@ -230,6 +276,22 @@ class Engine:
                  (big, L.w2.data_ptr(), L.b2.data_ptr(), _ptr(L.lam2), xr, M, D, I, stream)),
             ]
             emit_tap(i + 1)
+        if fpn is not None:
+            # top-down pathway, coarsest level first (TV:181-193), then the 3x3 output convolutions and "pool"
+            C, inner = fpn.C, geo.extra["inner"]
+            for slot in range(len(TAP_SCALES) - 1, -1, -1):
+                top = inner[slot + 1] if slot + 1 < len(TAP_SCALES) else None
+                th, tw = (top.shape[1], top.shape[2]) if top is not None else (0, 0)
+                plan.append(("ldit_fpn_merge", lib.ldit_fpn_merge,
+                             (geo.extra["lat"][slot].data_ptr(), _ptr(top), inner[slot].data_ptr(), B, geo.Gh, geo.Gw, C,
+                              TAP_SCALES[slot], th, tw, stream)))
+            for slot in range(len(TAP_SCALES)):
+                h, w = inner[slot].shape[1], inner[slot].shape[2]
+                plan.append(("ldit_conv3x3_bias", lib.ldit_conv3x3_bias,
+                             (inner[slot].data_ptr(), fpn.w_out[slot].data_ptr(), fpn.b_out[slot].data_ptr(),
+                              outs[slot].data_ptr(), B, h, w, C, C, stream)))
+            h5, w5 = outs[3].shape[1], outs[3].shape[2]
+            plan.append(("ldit_subsample2", lib.ldit_subsample2, (outs[3].data_ptr(), outs[4].data_ptr(), B, h5, w5, C, stream)))
         return plan
 
     def _enqueue(self, geo: _Geometry, x: torch.Tensor, outs, stream: int, limit: int | None = None):
@@ -242,8 +304,8 @@ class Engine:
     @staticmethod
     def _as_feats(outs):
         feats = OrderedDict()
-        for i, o in enumerate(outs, start=2):
-            feats[f"p{i}"] = o.permute(0, 3, 1, 2)  # [B, D, oh, ow] view of channels-last memory
+        for name, o in zip(("p2", "p3", "p4", "p5", "pool"), outs):   # "pool" only with the FPN head (R:model.py:63)
+            feats[name] = o.permute(0, 3, 1, 2)  # [B, C, oh, ow] view of channels-last memory
         return feats
 
     def prepare_input(self, x: torch.Tensor) -> torch.Tensor:
@@ -262,33 +324,31 @@ class Engine:
             x = x[:, :, : H // 16 * 16, : W // 16 * 16]
         return x.contiguous()
 
-    def forward(self, x: torch.Tensor):
+    def forward(self, x: torch.Tensor, head: str = "taps"):
         self.refresh_weights()
         H0, W0 = x.shape[2], x.shape[3]
         x = self.prepare_input(x)
-        geo = self._geometry(x.shape[0], H0, W0) if (H0 % 16 == 0 and W0 % 16 == 0) else self._geometry_ragged(x, H0, W0)
+        geo = (self._geometry(x.shape[0], H0, W0, 0, head) if (H0 % 16 == 0 and W0 % 16 == 0)
+               else self._geometry_ragged(x, H0, W0, head))
         outs = self._alloc_outputs(geo)
         geo.launches = self._enqueue(geo, x, outs, torch.cuda.current_stream(self.device).cuda_stream)
         return self._as_feats(outs)
 
-    def _geometry_ragged(self, x, H0, W0):
+    def _geometry_ragged(self, x, H0, W0, head="taps"):
         # the position-table rule looks at the ORIGINAL height/width (HF:135), the conv at the cropped ones
-        key = (x.shape[0], H0, W0)
-        geo = self._geoms.get(key)
-        if geo is None:
-            geo = self._geometry(x.shape[0], H0, W0)
-            geo.H, geo.W = x.shape[2], x.shape[3]
+        geo = self._geometry(x.shape[0], H0, W0, 0, head)
+        geo.H, geo.W = x.shape[2], x.shape[3]
         return geo
 
     # ----------------------------------------------------------------------- CUDA graphs
-    def forward_graphed(self, x: torch.Tensor, slot: int = 0):
+    def forward_graphed(self, x: torch.Tensor, slot: int = 0, head: str = "taps"):
         """Replay a captured CUDA graph of the whole forward for this (B, H, W, dtype).
         Outputs are STATIC buffers overwritten by the next call with the same geometry (and slot)."""
         self.refresh_weights()
         if x.shape[2] % 16 or x.shape[3] % 16:
-            return self.forward(x)
+            return self.forward(x, head)
         x = self.prepare_input(x)
-        geo = self._geometry(x.shape[0], x.shape[2], x.shape[3], slot)
+        geo = self._geometry(x.shape[0], x.shape[2], x.shape[3], slot, head)
         if geo.graph is None or geo.graph_in.dtype != x.dtype:
             if geo.graph_in is None or geo.graph_in.dtype != x.dtype:
                 geo.graph_in = torch.empty_like(x)

@@ -105,3 +105,20 @@ def make_state_dict(cfg: DiTConfig, seed: int = 0, stress: bool = False) -> dict
             v = normal(shape, 0.2) if stress else np.zeros(shape, np.float32)
         sd[name] = torch.from_numpy(np.ascontiguousarray(v, dtype=np.float32))
     return sd
+
+
+def make_fpn_state_dict(in_channels: int, out_channels: int = 256, seed: int = 0, stress: bool = False) -> dict:
+    """torchvision ``FeaturePyramidNetwork([in_channels]*4, out_channels)`` state dict (TV:104-131).
+    ``stress=False`` follows its init (kaiming_uniform(a=1): U(-sqrt(3/fan_in), +), zero bias);
+    ``stress=True`` adds non-zero biases and larger weights so every fused term is exercised."""
+    rng = np.random.default_rng(seed)
+    sd = {}
+    for block, k, cin in (("inner_blocks", 1, in_channels), ("layer_blocks", 3, out_channels)):
+        bound = float(np.sqrt(3.0 / (cin * k * k))) * (1.5 if stress else 1.0)
+        for i in range(4):
+            w = rng.uniform(-bound, bound, (out_channels, cin, k, k)).astype(np.float32)
+            b = (rng.standard_normal(out_channels).astype(np.float32) * np.float32(0.1) if stress
+                 else np.zeros(out_channels, np.float32))
+            sd[f"{block}.{i}.0.weight"] = torch.from_numpy(w)
+            sd[f"{block}.{i}.0.bias"] = torch.from_numpy(b)
+    return sd

@@ -36,11 +36,11 @@ def build_case(name):
     return cfg, sd, x, load_golden(name), meta
 
 
-def compare_to_golden(feats, gold, meta, rel_fro, max_abs_rel):
+def compare_to_golden(feats, gold, meta, rel_fro, max_abs_rel, keys=("p2", "p3", "p4", "p5")):
     """Compare an OrderedDict of taps with a fixture.  Returns {tap: (rel_fro, max_abs/absmax)}."""
     import torch
     out = {}
-    for k in ("p2", "p3", "p4", "p5"):
+    for k in keys:
         v = feats[k].detach().float().cpu().contiguous().numpy()
         assert tuple(v.shape) == tuple(gold[k + "_shape"]), (k, v.shape, gold[k + "_shape"])
         if k in gold:
@@ -61,3 +61,20 @@ def cuda_device():
     if not torch.cuda.is_available():
         pytest.skip("no CUDA device")
     return torch.device("cuda:0")
+
+
+def fpn_golden_index():
+    with open(os.path.join(GOLDEN_DIR, "index_fpn.json")) as f:
+        return json.load(f)["cases"]
+
+
+def build_fpn_case(name):
+    """(cfg, backbone state dict, fpn state dict, x, golden arrays, meta) for a committed DiTWithFPN fixture."""
+    from layoutdit_b200.config import DiTConfig
+    from layoutdit_b200.synth import make_fpn_state_dict, make_state_dict, synthetic_pages
+    meta = fpn_golden_index()[name]
+    cfg = DiTConfig(**meta["config"])
+    sd = make_state_dict(cfg, meta["weight_seed"], meta["stress"])
+    fsd = make_fpn_state_dict(cfg.hidden_size, 256, meta["fpn_seed"], meta["stress"])
+    x = synthetic_pages(meta["batch"], meta["height"], meta["width"], meta["input_seed"])
+    return cfg, sd, fsd, x, load_golden(name), meta

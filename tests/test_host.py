@@ -105,3 +105,32 @@ def test_synthetic_pages_are_deterministic_and_in_range():
     a, b = synthetic_pages(2, 64, 96, 7), synthetic_pages(2, 64, 96, 7)
     assert torch.equal(a, b) and a.shape == (2, 3, 64, 96)
     assert float(a.min()) >= -1.0 and float(a.max()) <= 1.0
+
+
+def test_fpn_module_boundary_and_state_dict_names():
+    """R:dit_backbone.py:65-95: .backbone / .fpn / .out_channels and the reference's state_dict keys."""
+    from torchvision.ops import FeaturePyramidNetwork
+    from torchvision.ops.feature_pyramid_network import LastLevelMaxPool
+    from layoutdit_b200 import DiTWithFPN
+    from layoutdit_b200.synth import make_fpn_state_dict
+    cfg = DiTConfig(hidden_size=128, num_hidden_layers=3, num_attention_heads=2, intermediate_size=256, image_size=64)
+    m = DiTWithFPN(pretrained=False, config=cfg)
+    assert m.out_channels == 256 and m.backbone.hidden_size == 128
+    tv = FeaturePyramidNetwork([128] * 4, 256, extra_blocks=LastLevelMaxPool())
+    assert {k: tuple(v.shape) for k, v in m.fpn.state_dict().items()} == {k: tuple(v.shape) for k, v in tv.state_dict().items()}
+    keys = list(m.state_dict().keys())
+    assert "backbone.dit.embeddings.cls_token" in keys and "fpn.inner_blocks.0.0.weight" in keys
+    fsd = make_fpn_state_dict(128, 256, 1, True)
+    assert not m.fpn.load_state_dict(fsd, strict=True).missing_keys
+    with pytest.raises(_lib.LditError):   # CUDA only, fails loudly
+        m.eval()(torch.zeros(1, 3, 64, 64))
+
+
+def test_fpn_argument_validation_without_gpu():
+    lib = _lib.load()
+    buf = ctypes.create_string_buffer(64)
+    p16 = (ctypes.addressof(buf) + 15) & ~15
+    assert lib.ldit_conv3x3_bias(None, p16, None, p16, 1, 8, 8, 256, 256, None) == -1
+    assert lib.ldit_conv3x3_bias(p16, p16, None, p16, 1, 8, 8, 100, 256, None) == -2   # Cin not a multiple of 64
+    assert lib.ldit_fpn_merge(p16, None, p16, 1, 4, 4, 100, 2.0, 0, 0, None) == -2     # C not a multiple of 8
+    assert lib.ldit_subsample2(p16, p16 + 2, 1, 4, 4, 256, None) == -3

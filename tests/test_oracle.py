@@ -4,8 +4,8 @@ import numpy as np
 import pytest
 import torch
 
-from conftest import build_case, compare_to_golden, golden_index
-from oracle import dit_oracle, hf_reference
+from conftest import build_case, build_fpn_case, compare_to_golden, fpn_golden_index, golden_index
+from oracle import dit_oracle, fpn_oracle, hf_reference
 
 ALL = sorted(golden_index().keys())
 FAST = [n for n in ALL if n.startswith("tiny")] + ["base_224_w1"]
@@ -58,3 +58,34 @@ def test_tap_closed_forms():
 def test_tap_layer_indices():
     assert dit_oracle.tap_layer_indices(12) == [4, 6, 8, 12]
     assert dit_oracle.tap_layer_indices(24) == [8, 12, 16, 24]
+
+
+FPN_KEYS = ("p2", "p3", "p4", "p5", "pool")
+
+
+@pytest.mark.parametrize("name", sorted(fpn_golden_index().keys()))
+def test_fpn_oracle_matches_reference_fixture(name):
+    """oracle/fpn_oracle.py vs the outputs of the reference's own DiTWithFPN (oracle/make_golden_fpn.py)."""
+    cfg, sd, fsd, x, gold, meta = build_fpn_case(name)
+    feats = fpn_oracle.dit_with_fpn_forward(sd, fsd, cfg.to_dict(), x)
+    assert list(feats.keys()) == list(FPN_KEYS)
+    compare_to_golden(feats, gold, meta, rel_fro=3e-5, max_abs_rel=3e-4, keys=FPN_KEYS)
+
+
+def test_fpn_oracle_matches_installed_torchvision():
+    from torchvision.ops import FeaturePyramidNetwork
+    from torchvision.ops.feature_pyramid_network import LastLevelMaxPool
+    from collections import OrderedDict
+    from layoutdit_b200.synth import make_fpn_state_dict
+    fsd = make_fpn_state_dict(64, 256, 5, True)
+    fpn = FeaturePyramidNetwork([64] * 4, 256, extra_blocks=LastLevelMaxPool()).eval()
+    fpn.load_state_dict(fsd, strict=True)
+    g = torch.Generator().manual_seed(3)
+    feats = OrderedDict((f"p{i + 2}", torch.randn(2, 64, h, w, generator=g))
+                        for i, (h, w) in enumerate([(20, 28), (10, 14), (5, 7), (2, 3)]))
+    with torch.no_grad():
+        ref = fpn(feats)
+    got = fpn_oracle.fpn_forward(fsd, feats)
+    assert list(ref.keys()) == list(got.keys()) == list(FPN_KEYS)
+    for k in ref:
+        torch.testing.assert_close(got[k], ref[k], rtol=1e-4, atol=1e-4)
