@@ -513,6 +513,12 @@ int ldit_resample_taps(const void* x, void* out, int B, int Gh, int Gw, int D, f
   const int oh = static_cast<int>(floorf(Gh * scale)), ow = static_cast<int>(floorf(Gw * scale));
   if (oh <= 0 || ow <= 0) return LDIT_E_SHAPE;
   if (D / 8 * kTapPix > 1024 || B > 65535) return LDIT_E_SHAPE;
+  if (scale == 1.0f) {  // no interpolation (R:57 skips it): CLS-less fp32 -> bf16 copy
+    const size_t n = static_cast<size_t>(B) * Gh * Gw * (D / 8);
+    launch_kernel(cast_tokens_kernel, dim3(static_cast<unsigned>((n + 255) / 256)), dim3(256), 0, static_cast<cudaStream_t>(stream), 1,
+                  static_cast<const float*>(x), static_cast<__nv_bfloat16*>(out), B, Gh * Gw, D);
+    return check_launch();
+  }
   if ((scale == 4.0f || scale == 2.0f) && D / 8 * kUpCells <= 512) {  // cell-based integer up-sampling
     dim3 ublock(D / 8, kUpCells);
     dim3 ugrid((Gh * Gw + kUpCells - 1) / kUpCells, B);
@@ -536,6 +542,18 @@ int ldit_fpn_merge(const void* lat, const void* top, void* out, int B, int Gh, i
   if (!aligned16(lat) || !aligned16(top) || !aligned16(out)) return LDIT_E_ALIGN;
   const int oh = static_cast<int>(floorf(Gh * scale)), ow = static_cast<int>(floorf(Gw * scale));
   if (oh <= 0 || ow <= 0) return LDIT_E_SHAPE;
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  const __nv_bfloat16* lb = static_cast<const __nv_bfloat16*>(lat);
+  const __nv_bfloat16* tb = static_cast<const __nv_bfloat16*>(top);
+  __nv_bfloat16* ob = static_cast<__nv_bfloat16*>(out);
+  if (top && (scale == 4.0f || scale == 2.0f) && top_h * 2 == oh && top_w * 2 == ow && C / 8 <= 256) {  // cell-based up-sampling
+    const int cells = (256 / (C / 8)) < 4 ? (256 / (C / 8)) : 4;
+    dim3 ublock(C / 8, cells);
+    dim3 ugrid((Gh * Gw + cells - 1) / cells, B);
+    if (scale == 4.0f) launch_kernel(fpn_merge_up_kernel<4>, ugrid, ublock, 0, st, 1, lb, tb, ob, C, Gh, Gw);
+    else launch_kernel(fpn_merge_up_kernel<2>, ugrid, ublock, 0, st, 1, lb, tb, ob, C, Gh, Gw);
+    return check_launch();
+  }
   const int pix = (1024 / (C / 8)) < 8 ? (1024 / (C / 8)) : 8;   // output pixels per block
   dim3 block(C / 8, pix);
   dim3 grid((oh * ow + pix - 1) / pix, B);

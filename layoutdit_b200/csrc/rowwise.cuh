@@ -278,6 +278,84 @@ fpn_merge_kernel(const __nv_bfloat16* __restrict__ lat, const __nv_bfloat16* __r
   *reinterpret_cast<uint4*>(out + (static_cast<size_t>(b) * oh * ow + pix) * C + threadIdx.x * 8) = o;
 }
 
+// Integer up-sampling merge (S = 2 or 4) when the coarser level is exactly half the output size (always the
+// case on a DiT pyramid: levels are 4Gh, 2Gh, Gh): the cell scheme of upsample_taps_kernel -- one thread loads
+// the 3x3 lateral neighbourhood of source cell (y, x) and the (S/2)^2 coarser-level pixels above it once and
+// emits the S*S outputs of the cell, 13 (S=4) or 10 (S=2) 16-byte loads per S*S stores instead of 5 per store.
+// blockDim = (C/8, cells), gridDim = (ceil(Gh*Gw / cells), B).
+template <int S>
+__global__ void __launch_bounds__(256)
+fpn_merge_up_kernel(const __nv_bfloat16* __restrict__ lat, const __nv_bfloat16* __restrict__ top, __nv_bfloat16* __restrict__ out,
+                    int C, int Gh, int Gw) {
+  pdl_launch_dependents();
+  pdl_wait();
+  const int cell = blockIdx.x * blockDim.y + threadIdx.y;
+  if (cell >= Gh * Gw) return;
+  const int b = blockIdx.y;
+  const int y = cell / Gw, x = cell - y * Gw;
+  const int yy[3] = {max(y - 1, 0), y, min(y + 1, Gh - 1)};
+  const int xx[3] = {max(x - 1, 0), x, min(x + 1, Gw - 1)};
+  const __nv_bfloat16* base = lat + static_cast<size_t>(b) * Gh * Gw * C + threadIdx.x * 8;
+  float w[3][3][8];
+#pragma unroll
+  for (int r = 0; r < 3; ++r)
+#pragma unroll
+    for (int c = 0; c < 3; ++c) load8<__nv_bfloat16>(base + static_cast<size_t>(yy[r] * Gw + xx[c]) * C, w[r][c]);
+  constexpr int T = S / 2;                       // coarser-level pixels per cell and axis
+  const int th = Gh * T, tw = Gw * T;
+  float t[T][T][8];
+#pragma unroll
+  for (int r = 0; r < T; ++r)
+#pragma unroll
+    for (int c = 0; c < T; ++c)
+      load8<__nv_bfloat16>(top + ((static_cast<size_t>(b) * th + y * T + r) * tw + x * T + c) * C + threadIdx.x * 8, t[r][c]);
+  const int ow = Gw * S;
+  __nv_bfloat16* obase = out + ((static_cast<size_t>(b) * Gh * S + static_cast<size_t>(y) * S) * ow + static_cast<size_t>(x) * S) * C +
+                         threadIdx.x * 8;
+#pragma unroll
+  for (int a = 0; a < S; ++a) {
+    constexpr float inv = 1.0f / S;
+    const float fa = (a + 0.5f) * inv - 0.5f;
+    const int r0 = fa < 0.f ? 0 : 1;
+    const float ly = fa < 0.f ? (y == 0 ? 1.0f : 1.0f + fa) : fa;
+#pragma unroll
+    for (int bb = 0; bb < S; ++bb) {
+      const float fb = (bb + 0.5f) * inv - 0.5f;
+      const int c0 = fb < 0.f ? 0 : 1;
+      const float lx = fb < 0.f ? (x == 0 ? 1.0f : 1.0f + fb) : fb;
+      const float w00 = (1.f - ly) * (1.f - lx), w01 = (1.f - ly) * lx, w10 = ly * (1.f - lx), w11 = ly * lx;
+      float acc[8];
+#pragma unroll
+      for (int e = 0; e < 8; ++e)
+        acc[e] = (w00 * w[r0][c0][e] + w01 * w[r0][c0 + 1][e] + w10 * w[r0 + 1][c0][e] + w11 * w[r0 + 1][c0 + 1][e]) + t[a / 2][bb / 2][e];
+      uint4 o;
+      o.x = pack_bf16x2(acc[0], acc[1]); o.y = pack_bf16x2(acc[2], acc[3]);
+      o.z = pack_bf16x2(acc[4], acc[5]); o.w = pack_bf16x2(acc[6], acc[7]);
+      *reinterpret_cast<uint4*>(obase + (static_cast<size_t>(a) * ow + bb) * C) = o;
+    }
+  }
+}
+
+// Tokens without CLS, fp32 -> bf16: the scale-1 tap (R:dit_backbone.py:50-56, no interpolate at :57) and the
+// A operand of the FPN lateral GEMM.  One 16-byte store per thread, rows of D contiguous on both sides.
+__global__ void __launch_bounds__(256)
+cast_tokens_kernel(const float* __restrict__ xres, __nv_bfloat16* __restrict__ out, int B, int P, int D) {
+  pdl_launch_dependents();
+  pdl_wait();
+  const int d8 = D / 8;
+  const size_t idx = static_cast<size_t>(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (idx >= static_cast<size_t>(B) * P * d8) return;
+  const int c = static_cast<int>(idx % d8);
+  const size_t row = idx / d8;            // b * P + p
+  const size_t b = row / P;
+  const float4* src = reinterpret_cast<const float4*>(xres + (row + b + 1) * D) + 2 * c;   // token row b*(P+1) + 1 + p
+  const float4 lo = __ldg(src), hi = __ldg(src + 1);
+  uint4 o;
+  o.x = pack_bf16x2(lo.x, lo.y); o.y = pack_bf16x2(lo.z, lo.w);
+  o.z = pack_bf16x2(hi.x, hi.y); o.w = pack_bf16x2(hi.z, hi.w);
+  reinterpret_cast<uint4*>(out)[idx] = o;
+}
+
 // LastLevelMaxPool (TV:ops/feature_pyramid_network.py:231-249): max_pool2d(kernel 1, stride 2) == every second
 // pixel of every second row.  in [B, H, W, C] -> out [B, ceil(H/2), ceil(W/2), C], bf16, 16 bytes per thread.
 __global__ void __launch_bounds__(256)
