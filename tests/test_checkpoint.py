@@ -81,7 +81,7 @@ def test_layoutdit_whole_model_checkpoint(tmp_path):
     assert exported.keys() == owned.keys() and all(torch.equal(exported[k], owned[k]) for k in owned)
     # the reference's own resume call (R:model.py:70) on this file: nn.Module semantics, nothing matches the prefix
     res = DiTBackbone(pretrained=False, config=cfg).dit.load_state_dict(full, strict=False)
-    assert len(res.unexpected_keys) == len(full)
+    assert len(res.unexpected_keys) == len(full) - 1     # the legacy relative_position_index buffer is dropped silently (HF:674)
 
 
 def test_errors():
