@@ -72,6 +72,22 @@ int ldit_gemm_bias_scale_residual(const void* A, const void* W, const void* bias
 int ldit_patch_embed(const void* pixels, int pixel_dtype, const void* w, const void* pos_bias, const void* cls_pos,
                      void* scratch, void* x, int B, int H, int W, int D, void* stream);
 
+/* ldit_patch_embed with the detector's input transform fused into the patch gather (SURVEY.md section 8 row
+ * f3): GeneralizedRCNNTransform as configured at R:src/layoutdit/modeling/model.py:44-56 -- per page
+ * normalize (image - mean) / std, then F.interpolate(size=(H, W), mode="bilinear", align_corners=False)
+ * (TV:models/detection/transform.py normalize() / _resize_image_and_masks() with fixed_size), then batching --
+ * followed by BeitEmbeddings.forward as above.  The resized batch [B, 3, H, W] is never written.
+ *  pages    DEVICE array of B device pointers, page b = [3, page_hw[2b], page_hw[2b+1]] contiguous CHW of
+ *           dtype `pixel_dtype` (any size >= 1x1 per page, values as the reference feeds them: floats in [0, 1])
+ *  page_hw  DEVICE int32 [B, 2] = (height, width) of each page
+ *  max_page_w  host-known upper bound of the page widths: sizes the shared-memory row staging of the fast
+ *           gather (6 rows of max_page_w pixels must fit 200 KB); 0 = unknown, use the direct gather
+ *  mean*, std*  per-channel normalisation constants (the reference: 0.5 each)
+ * everything else as ldit_patch_embed; (H, W) = the fixed size the detector resizes to (224, 224). */
+int ldit_patch_embed_pages(const void* const* pages, const int* page_hw, int max_page_w, int pixel_dtype, float mean0, float mean1,
+                           float mean2, float std0, float std1, float std2, const void* w, const void* pos_bias, const void* cls_pos,
+                           void* scratch, void* x, int B, int H, int W, int D, void* stream);
+
 /* BeitSelfAttention core, HF:275-298 / F.scaled_dot_product_attention at HF:356-364, plus the
  * head merge HF:365-367.  qkv bf16 [B*N, 3D] (Q | K | V, heads contiguous, head_dim 64) ->
  * ctx bf16 [B*N, D].  bias_table: NULL, or f32 [heads, T] with T = (2Gh-1)(2Gw-1)+3 -- the

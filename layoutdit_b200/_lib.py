@@ -20,6 +20,7 @@ SIGNATURES = {
     "ldit_gemm_bias_gelu": (_i, [_vp, _vp, _vp, _vp, _i, _i, _i, _vp]),
     "ldit_gemm_bias_scale_residual": (_i, [_vp, _vp, _vp, _vp, _vp, _i, _i, _i, _vp]),
     "ldit_patch_embed": (_i, [_vp, _i, _vp, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _vp]),
+    "ldit_patch_embed_pages": (_i, [_vp, _vp, _i, _i, _f, _f, _f, _f, _f, _f, _vp, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _vp]),
     "ldit_attention": (_i, [_vp, _vp, _vp, _i, _i, _i, _i, _i, _vp]),
     "ldit_resample_taps": (_i, [_vp, _vp, _i, _i, _i, _i, _f, _vp]),
     "ldit_fpn_merge": (_i, [_vp, _vp, _vp, _i, _i, _i, _i, _f, _i, _i, _vp]),

@@ -273,6 +273,30 @@ int launch_conv_t(const void* in, const void* w, GemmArgs g, int B, int H, int W
   return launch_gemm_maps<BN, EPI_CONV_BIAS, 2>(tmA, tmB, tmC, g, st);
 }
 
+template <typename T>
+cudaError_t launch_pages_gather(const void* const* pages, const int* page_hw, __nv_bfloat16* a, int B, int H, int W, int max_page_w,
+                                const float* ms, cudaStream_t st) {
+  const int Gh = H / 16, Gw = W / 16;
+  const T* const* pp = reinterpret_cast<const T* const*>(pages);
+  // staging pitch: a multiple of 16 bytes; 6 rows must fit the 227 KB a block may opt into
+  const int pitch = (max_page_w + 15) / 16 * 16;
+  const size_t smem = static_cast<size_t>(6) * pitch * sizeof(T);
+  if (max_page_w > 0 && smem <= 200 * 1024 && B <= 65535) {
+    static size_t max_set = 0;
+    if (smem > max_set && smem > 48 * 1024) {
+      cudaError_t e = cudaFuncSetAttribute(pages_rows_im2col_kernel<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem));
+      if (e != cudaSuccess) return e;
+      max_set = smem;
+    }
+    return launch_kernel(pages_rows_im2col_kernel<T>, dim3(H, B), dim3(128), smem, st, 1, pp, page_hw, a, H, W, Gh, Gw, ms[0], ms[1],
+                         ms[2], ms[3], ms[4], ms[5], pitch);
+  }
+  const size_t threads = static_cast<size_t>(B) * 3 * H * (W / 8);
+  const unsigned blocks = static_cast<unsigned>((threads + 255) / 256);
+  return launch_kernel(pages_im2col_kernel<T>, dim3(blocks), dim3(256), 0, st, 1, pp, page_hw, a, B, H, W, Gh, Gw, ms[0], ms[1], ms[2],
+                       ms[3], ms[4], ms[5]);
+}
+
 }  // namespace
 
 extern "C" {
@@ -379,6 +403,38 @@ int ldit_patch_embed(const void* pixels, int pixel_dtype, const void* w, const v
       break;
     default: return LDIT_E_DTYPE;
   }
+  int rc = check_launch();
+  if (rc) return rc;
+  launch_kernel(cls_rows_kernel, dim3((B * (D / 4) + 255) / 256), dim3(256), 0, st, 1, static_cast<const float*>(cls_pos), static_cast<float*>(x), B, P + 1, D);
+  rc = check_launch();
+  if (rc) return rc;
+  GemmArgs g{};
+  g.M = B * P; g.N = D; g.K = 768;
+  g.out = x; g.ldo = D;
+  g.P = P;
+  g.posb = static_cast<const float*>(pos_bias);
+  return launch_gemm<EPI_PATCH>(scratch, w, g, st);
+}
+
+int ldit_patch_embed_pages(const void* const* pages, const int* page_hw, int max_page_w, int pixel_dtype, float mean0, float mean1,
+                           float mean2, float std0, float std1, float std2, const void* w, const void* pos_bias, const void* cls_pos,
+                           void* scratch, void* x, int B, int H, int W, int D, void* stream) {
+  if (!pages || !page_hw || !w || !pos_bias || !cls_pos || !scratch || !x) return LDIT_E_NULL;
+  if (B <= 0 || H < 16 || W < 16 || (H % 16) || (W % 16) || D <= 0 || (D % 32) || max_page_w < 0) return LDIT_E_SHAPE;
+  if (!(std0 != 0.f) || !(std1 != 0.f) || !(std2 != 0.f)) return LDIT_E_SHAPE;
+  if (!aligned16(scratch) || !aligned16(x) || !aligned16(cls_pos)) return LDIT_E_ALIGN;
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  const int P = (H / 16) * (W / 16);
+  __nv_bfloat16* a = static_cast<__nv_bfloat16*>(scratch);
+  const float ms[6] = {mean0, mean1, mean2, std0, std1, std2};
+  cudaError_t le;
+  switch (pixel_dtype) {
+    case LDIT_DTYPE_F32: le = launch_pages_gather<float>(pages, page_hw, a, B, H, W, max_page_w, ms, st); break;
+    case LDIT_DTYPE_F16: le = launch_pages_gather<__half>(pages, page_hw, a, B, H, W, max_page_w, ms, st); break;
+    case LDIT_DTYPE_BF16: le = launch_pages_gather<__nv_bfloat16>(pages, page_hw, a, B, H, W, max_page_w, ms, st); break;
+    default: return LDIT_E_DTYPE;
+  }
+  if (le != cudaSuccess) { (void)cudaGetLastError(); return static_cast<int>(le); }
   int rc = check_launch();
   if (rc) return rc;
   launch_kernel(cls_rows_kernel, dim3((B * (D / 4) + 255) / 256), dim3(256), 0, st, 1, static_cast<const float*>(cls_pos), static_cast<float*>(x), B, P + 1, D);

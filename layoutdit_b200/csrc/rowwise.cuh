@@ -109,6 +109,127 @@ im2col_kernel(const T* __restrict__ x, __nv_bfloat16* __restrict__ a, int B, int
   *reinterpret_cast<uint4*>(a + row * 768 + c * 256 + py * 16 + px) = o;
 }
 
+// Input transform fused into the patch gather.  The detector hands the backbone
+// GeneralizedRCNNTransform(pages) (R:src/layoutdit/modeling/model.py:44-56: fixed_size (224, 224), mean/std 0.5):
+// per page normalize (TV:models/detection/transform.py normalize(): (image - mean) / std), then
+// F.interpolate(size=fixed_size, mode="bilinear", align_corners=False) (_resize_image_and_masks), then batching.
+// This kernel reads the raw pages -- a device array of B pointers to [3, Hs_b, Ws_b] images of any size --
+// and writes the normalized, resized pixels straight into the patch-embed GEMM's A operand ([B*P, 768] bf16,
+// (c, py, px) columns): the resized fp32 batch is never materialised.  ATen's rule: ratio = in / out,
+// src = max(ratio * (dst + .5) - .5, 0), i0 = min(floor(src), in - 1), i1 = i0 + (i0 < in - 1), l = src - i0;
+// value = l0y (l0x p00 + l1x p01) + l1y (l0x p10 + l1x p11) on normalized pixels.
+// One thread = 8 consecutive output pixels of one output row and channel (one 16-byte store).
+template <typename T> __device__ __forceinline__ float load1(const T* p);
+template <> __device__ __forceinline__ float load1<float>(const float* p) { return __ldg(p); }
+template <> __device__ __forceinline__ float load1<__half>(const __half* p) { return __half2float(__ldg(p)); }
+template <> __device__ __forceinline__ float load1<__nv_bfloat16>(const __nv_bfloat16* p) { return __bfloat162float(__ldg(p)); }
+
+template <typename T>
+__global__ void __launch_bounds__(256)
+pages_im2col_kernel(const T* const* __restrict__ pages, const int* __restrict__ page_hw, __nv_bfloat16* __restrict__ a, int B, int H,
+                    int W, int Gh, int Gw, float m0, float m1, float m2, float s0, float s1, float s2) {
+  pdl_launch_dependents();
+  pdl_wait();
+  const int wchunks = (Gw * 16) / 8;
+  const size_t total = static_cast<size_t>(B) * 3 * (Gh * 16) * wchunks;
+  const size_t idx = static_cast<size_t>(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (idx >= total) return;
+  const int xc = static_cast<int>(idx % wchunks);
+  size_t t = idx / wchunks;
+  const int yy = static_cast<int>(t % (Gh * 16)); t /= (Gh * 16);
+  const int c = static_cast<int>(t % 3);
+  const int b = static_cast<int>(t / 3);
+  const int Hs = page_hw[2 * b], Ws = page_hw[2 * b + 1];
+  const float mean = c == 0 ? m0 : (c == 1 ? m1 : m2), sd = c == 0 ? s0 : (c == 1 ? s1 : s2);
+  const T* src = pages[b] + static_cast<size_t>(c) * Hs * Ws;
+  const float ry = static_cast<float>(Hs) / H, rx = static_cast<float>(Ws) / W;
+  const float sy = fmaxf(ry * (yy + 0.5f) - 0.5f, 0.f);
+  const int y0 = min(static_cast<int>(sy), Hs - 1);
+  const int y1 = y0 + (y0 < Hs - 1 ? 1 : 0);
+  const float l1y = sy - y0, l0y = 1.f - l1y;
+  const T* r0 = src + static_cast<size_t>(y0) * Ws;
+  const T* r1 = src + static_cast<size_t>(y1) * Ws;
+  float v[8];
+#pragma unroll
+  for (int i = 0; i < 8; ++i) {
+    const float sx = fmaxf(rx * (xc * 8 + i + 0.5f) - 0.5f, 0.f);
+    const int x0 = min(static_cast<int>(sx), Ws - 1);
+    const int x1 = x0 + (x0 < Ws - 1 ? 1 : 0);
+    const float l1x = sx - x0, l0x = 1.f - l1x;
+    const float p00 = (load1<T>(r0 + x0) - mean) / sd, p01 = (load1<T>(r0 + x1) - mean) / sd;
+    const float p10 = (load1<T>(r1 + x0) - mean) / sd, p11 = (load1<T>(r1 + x1) - mean) / sd;
+    v[i] = l0y * (l0x * p00 + l1x * p01) + l1y * (l0x * p10 + l1x * p11);
+  }
+  const int gy = yy >> 4, py = yy & 15, gx = xc >> 1, px = (xc & 1) * 8;
+  const size_t row = (static_cast<size_t>(b) * Gh + gy) * Gw + gx;
+  uint4 o;
+  o.x = pack_bf16x2(v[0], v[1]); o.y = pack_bf16x2(v[2], v[3]);
+  o.z = pack_bf16x2(v[4], v[5]); o.w = pack_bf16x2(v[6], v[7]);
+  *reinterpret_cast<uint4*>(a + row * 768 + c * 256 + py * 16 + px) = o;
+}
+
+// Same transform with the source rows staged in shared memory: a block owns one output row of one page (all
+// three channels); the two source rows each channel blends are copied in with coalesced (16-byte when the page
+// allows it) loads and the strided bilinear gather then runs out of shared memory.  The direct kernel above
+// issues 32 scattered 4-byte loads per thread (one sector each at a 1024 -> 224 stride); this one reads each
+// needed source row once, contiguously.  Arithmetic identical to the direct kernel.  max_w = row pitch of the
+// staging buffer (>= every page's width); dynamic smem = 6 * max_w * sizeof(T).
+template <typename T>
+__global__ void __launch_bounds__(128)
+pages_rows_im2col_kernel(const T* const* __restrict__ pages, const int* __restrict__ page_hw, __nv_bfloat16* __restrict__ a, int H,
+                         int W, int Gh, int Gw, float m0, float m1, float m2, float s0, float s1, float s2, int max_w) {
+  pdl_launch_dependents();
+  pdl_wait();
+  extern __shared__ __align__(16) uint8_t rows_raw[];
+  T* rows = reinterpret_cast<T*>(rows_raw);   // [c][r][max_w]
+  const int b = blockIdx.y, yy = blockIdx.x;
+  const int Hs = page_hw[2 * b], Ws = page_hw[2 * b + 1];
+  const float ry = static_cast<float>(Hs) / H, rx = static_cast<float>(Ws) / W;
+  const float sy = fmaxf(ry * (yy + 0.5f) - 0.5f, 0.f);
+  const int y0 = min(static_cast<int>(sy), Hs - 1);
+  const int y1 = y0 + (y0 < Hs - 1 ? 1 : 0);
+  const float l1y = sy - y0, l0y = 1.f - l1y;
+  const T* page = pages[b];
+  constexpr int VEC = 16 / sizeof(T);
+  const bool vec_ok = (reinterpret_cast<uintptr_t>(page) % 16 == 0) && (Ws % VEC == 0);
+#pragma unroll
+  for (int cr = 0; cr < 6; ++cr) {
+    const T* src = page + (static_cast<size_t>(cr >> 1) * Hs + ((cr & 1) ? y1 : y0)) * Ws;
+    T* dst = rows + cr * max_w;
+    if (vec_ok) {
+      for (int i = threadIdx.x; i < Ws / VEC; i += blockDim.x)
+        reinterpret_cast<uint4*>(dst)[i] = __ldg(reinterpret_cast<const uint4*>(src) + i);
+    } else {
+      for (int i = threadIdx.x; i < Ws; i += blockDim.x) dst[i] = src[i];
+    }
+  }
+  __syncthreads();
+  const int wchunks = (Gw * 16) / 8;
+  for (int t = threadIdx.x; t < 3 * wchunks; t += blockDim.x) {
+    const int c = t / wchunks, xc = t - c * wchunks;
+    const float mean = c == 0 ? m0 : (c == 1 ? m1 : m2), sd = c == 0 ? s0 : (c == 1 ? s1 : s2);
+    const T* r0 = rows + (2 * c) * max_w;
+    const T* r1 = r0 + max_w;
+    float v[8];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      const float sx = fmaxf(rx * (xc * 8 + i + 0.5f) - 0.5f, 0.f);
+      const int x0 = min(static_cast<int>(sx), Ws - 1);
+      const int x1 = x0 + (x0 < Ws - 1 ? 1 : 0);
+      const float l1x = sx - x0, l0x = 1.f - l1x;
+      const float p00 = (static_cast<float>(r0[x0]) - mean) / sd, p01 = (static_cast<float>(r0[x1]) - mean) / sd;
+      const float p10 = (static_cast<float>(r1[x0]) - mean) / sd, p11 = (static_cast<float>(r1[x1]) - mean) / sd;
+      v[i] = l0y * (l0x * p00 + l1x * p01) + l1y * (l0x * p10 + l1x * p11);
+    }
+    const int gy = yy >> 4, py = yy & 15, gx = xc >> 1, px = (xc & 1) * 8;
+    const size_t row = (static_cast<size_t>(b) * Gh + gy) * Gw + gx;
+    uint4 o;
+    o.x = pack_bf16x2(v[0], v[1]); o.y = pack_bf16x2(v[2], v[3]);
+    o.z = pack_bf16x2(v[4], v[5]); o.w = pack_bf16x2(v[6], v[7]);
+    *reinterpret_cast<uint4*>(a + row * 768 + c * 256 + py * 16 + px) = o;
+  }
+}
+
 // Token row 0 of every image: cls_token + position row 0 (HF:176-180); cls_pos = their sum.
 __global__ void __launch_bounds__(256)
 cls_rows_kernel(const float* __restrict__ cls_pos, float* __restrict__ xres, int B, int N, int D) {

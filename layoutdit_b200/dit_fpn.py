@@ -64,14 +64,24 @@ class DiTWithFPN(nn.Module):
         self.out_channels = 256
         self.use_cuda_graph = use_cuda_graph
 
+    def _engine(self):
+        eng = self.backbone._get_engine()
+        if eng.fpn_params is not self.fpn:
+            eng.fpn_params = self.fpn
+            eng._pack_key = None
+        return eng
+
+    def forward_pages(self, pages, size=(224, 224), mean=(0.5, 0.5, 0.5), std=(0.5, 0.5, 0.5)):
+        """Raw pages -> FPN maps: what ``FasterRCNN.forward`` computes up to its RPN (transform + backbone,
+        torchvision generalized_rcnn.py), with the transform fused into the patch gather."""
+        with torch.no_grad():
+            return self._engine().forward_pages(pages, size, mean, std, "fpn")
+
     def forward(self, x: torch.Tensor) -> "OrderedDict[str, torch.Tensor]":
         if self.training and torch.is_grad_enabled() and any(p.requires_grad for p in self.parameters()):
             raise NotImplementedError(
                 "layoutdit_b200.DiTWithFPN implements the inference forward only; call .eval() or wrap "
                 "the call in torch.no_grad()")
-        eng = self.backbone._get_engine()
-        if eng.fpn_params is not self.fpn:
-            eng.fpn_params = self.fpn
-            eng._pack_key = None
+        eng = self._engine()
         with torch.no_grad():
             return eng.forward_graphed(x, 0, "fpn") if self.use_cuda_graph else eng.forward(x, "fpn")

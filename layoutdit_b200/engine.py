@@ -77,6 +77,19 @@ class _Geometry:
 
 
 @dataclass
+class _PageList:
+    """Raw pages for ``ldit_patch_embed_pages``: device arrays of pointers and (H, W), plus the tensors they
+    point into (kept alive until the launch sequence has been enqueued)."""
+    ptrs: torch.Tensor       # int64 [B] device
+    hw: torch.Tensor         # int32 [B, 2] device
+    max_w: int               # widest page (sizes the row staging of the gather kernel)
+    dtype: torch.dtype
+    mean: tuple
+    std: tuple
+    keep: list
+
+
+@dataclass
 class _FpnPack:
     """torchvision FeaturePyramidNetwork weights (TV:ops/feature_pyramid_network.py:104-124) in kernel layout."""
     w_lat: list      # 4 x bf16 [C, D]       inner_blocks[i][0].weight[:, :, 0, 0]
@@ -231,17 +244,23 @@ class Engine:
             return outs + [torch.empty(geo.B, (h5 + 1) // 2, (w5 + 1) // 2, C, **bf)]
         return [torch.empty(geo.B, *self._tap_hw(geo, s), self.cfg.hidden_size, **bf) for s in TAP_SCALES]
 
-    def _plan(self, geo: _Geometry, x: torch.Tensor, outs, stream: int):
+    def _plan(self, geo: _Geometry, x, outs, stream: int):
         """The forward as an ordered list of (name, C-ABI function, args): one entry per
-        library call, in stream order."""
+        library call, in stream order.  ``x`` is the page batch tensor, or a ``_PageList`` (raw pages of
+        any size: the input transform is fused into the patch gather)."""
         lib, cfg = self.lib, self.cfg
         D, I, heads = cfg.hidden_size, cfg.intermediate_size, cfg.num_attention_heads
         M, N, B = geo.M, geo.N, geo.B
         xr, a, big = geo.x.data_ptr(), geo.a.data_ptr(), geo.big.data_ptr()
         eps = float(cfg.layer_norm_eps)
-        plan = [("ldit_patch_embed", lib.ldit_patch_embed,
-                 (x.data_ptr(), _DTYPE_CODE[x.dtype], self.w_patch.data_ptr(), geo.pos_bias.data_ptr(),
-                  geo.cls_pos.data_ptr(), big, xr, B, geo.H, geo.W, D, stream))]
+        if isinstance(x, _PageList):
+            plan = [("ldit_patch_embed_pages", lib.ldit_patch_embed_pages,
+                     (x.ptrs.data_ptr(), x.hw.data_ptr(), x.max_w, _DTYPE_CODE[x.dtype], *x.mean, *x.std, self.w_patch.data_ptr(),
+                      geo.pos_bias.data_ptr(), geo.cls_pos.data_ptr(), big, xr, B, geo.H, geo.W, D, stream))]
+        else:
+            plan = [("ldit_patch_embed", lib.ldit_patch_embed,
+                     (x.data_ptr(), _DTYPE_CODE[x.dtype], self.w_patch.data_ptr(), geo.pos_bias.data_ptr(),
+                      geo.cls_pos.data_ptr(), big, xr, B, geo.H, geo.W, D, stream))]
 
         fpn = self._fpn if geo.head == "fpn" else None
 
@@ -332,6 +351,42 @@ class Engine:
                else self._geometry_ragged(x, H0, W0, head))
         outs = self._alloc_outputs(geo)
         geo.launches = self._enqueue(geo, x, outs, torch.cuda.current_stream(self.device).cuda_stream)
+        return self._as_feats(outs)
+
+    def forward_pages(self, pages, size=(224, 224), mean=(0.5, 0.5, 0.5), std=(0.5, 0.5, 0.5), head: str = "taps"):
+        """Raw pages -> features: ``GeneralizedRCNNTransform`` as the detector configures it
+        (R:model.py:44-56: normalize, bilinear resize to ``fixed_size``, batch) fused into the patch gather,
+        then the backbone (and FPN for ``head="fpn"``).  ``pages``: a list of ``[3, H_i, W_i]`` CUDA tensors of
+        any sizes (one floating dtype), or one ``[B, 3, Hs, Ws]`` tensor."""
+        if isinstance(pages, torch.Tensor):
+            if pages.dim() != 4:
+                raise ValueError(f"expected [B, 3, H, W] pages or a list of [3, H, W] pages, got {tuple(pages.shape)}")
+            pages = list(pages.contiguous().unbind(0))
+        if not pages:
+            raise ValueError("empty page list")
+        keep = []
+        for p in pages:
+            if p.dim() != 3 or p.shape[0] != self.cfg.num_channels:
+                raise ValueError(f"images is expected to be a list of 3d tensors of shape [C, H, W], got {tuple(p.shape)}")
+            if not p.is_floating_point():
+                raise TypeError(f"Expected input images to be of floating type (in range [0, 1]), but found type {p.dtype} instead")
+            if not p.is_cuda:
+                raise _lib.LditError("DiTBackbone.forward_pages needs CUDA tensors (there is no CPU path)")
+            keep.append(p if p.dtype in _DTYPE_CODE else p.float())
+        dt = keep[0].dtype
+        keep = [p.to(dt).contiguous() for p in keep]
+        H, W = int(size[0]), int(size[1])
+        if H % 16 or W % 16 or H < 16 or W < 16:
+            raise ValueError("the fixed size must be a multiple of the 16x16 patch")
+        self.refresh_weights()
+        B = len(keep)
+        host = torch.tensor([p.data_ptr() for p in keep], dtype=torch.int64)
+        hw = torch.tensor([[p.shape[1], p.shape[2]] for p in keep], dtype=torch.int32)
+        pl = _PageList(ptrs=host.to(self.device), hw=hw.to(self.device), max_w=max(p.shape[2] for p in keep), dtype=dt,
+                       mean=tuple(float(v) for v in mean), std=tuple(float(v) for v in std), keep=keep)
+        geo = self._geometry(B, H, W, 0, head)
+        outs = self._alloc_outputs(geo)
+        geo.launches = self._enqueue(geo, pl, outs, torch.cuda.current_stream(self.device).cuda_stream)
         return self._as_feats(outs)
 
     def _geometry_ragged(self, x, H0, W0, head="taps"):

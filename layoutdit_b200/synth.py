@@ -122,3 +122,20 @@ def make_fpn_state_dict(in_channels: int, out_channels: int = 256, seed: int = 0
             sd[f"{block}.{i}.0.weight"] = torch.from_numpy(w)
             sd[f"{block}.{i}.0.bias"] = torch.from_numpy(b)
     return sd
+
+
+def raw_pages(sizes, seed: int = 0):
+    """Raw document pages as the dataset hands them to the detector: a list of ``[3, H, W]`` fp32 tensors in
+    [0, 1] (white paper, dark blocks, a little noise), one per ``(H, W)`` in ``sizes``."""
+    rng = np.random.default_rng(seed)
+    out = []
+    for (h, w) in sizes:
+        x = np.ones((3, h, w), dtype=np.float32)
+        for _ in range(int(rng.integers(4, 12))):
+            bh, bw = int(rng.integers(1, max(2, h // 3))), int(rng.integers(1, max(2, w // 2)))
+            y0, x0 = int(rng.integers(0, max(1, h - bh))), int(rng.integers(0, max(1, w - bw)))
+            x[:, y0:y0 + bh, x0:x0 + bw] = np.float32(rng.uniform(0.0, 0.4))
+        x += rng.standard_normal(x.shape, dtype=np.float32) * np.float32(0.01)
+        np.clip(x, 0.0, 1.0, out=x)
+        out.append(torch.from_numpy(x))
+    return out

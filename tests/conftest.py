@@ -78,3 +78,16 @@ def build_fpn_case(name):
     fsd = make_fpn_state_dict(cfg.hidden_size, 256, meta["fpn_seed"], meta["stress"])
     x = synthetic_pages(meta["batch"], meta["height"], meta["width"], meta["input_seed"])
     return cfg, sd, fsd, x, load_golden(name), meta
+
+
+def transform_golden_index():
+    with open(os.path.join(GOLDEN_DIR, "index_transform.json")) as f:
+        return json.load(f)["cases"]
+
+
+def build_transform_case(name):
+    """(raw pages, golden samples, shape, meta) for a committed input-transform fixture."""
+    from layoutdit_b200.synth import raw_pages
+    meta = transform_golden_index()[name]
+    gold = load_golden(name)
+    return raw_pages([tuple(s) for s in meta["sizes"]], meta["seed"]), gold["samples"], tuple(gold["shape"]), meta

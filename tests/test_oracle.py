@@ -4,8 +4,9 @@ import numpy as np
 import pytest
 import torch
 
-from conftest import build_case, build_fpn_case, compare_to_golden, fpn_golden_index, golden_index
-from oracle import dit_oracle, fpn_oracle, hf_reference
+from conftest import (build_case, build_fpn_case, build_transform_case, compare_to_golden, fpn_golden_index, golden_index,
+                      transform_golden_index)
+from oracle import dit_oracle, fpn_oracle, hf_reference, transform_oracle
 
 ALL = sorted(golden_index().keys())
 FAST = [n for n in ALL if n.startswith("tiny")] + ["base_224_w1"]
@@ -89,3 +90,12 @@ def test_fpn_oracle_matches_installed_torchvision():
     assert list(ref.keys()) == list(got.keys()) == list(FPN_KEYS)
     for k in ref:
         torch.testing.assert_close(got[k], ref[k], rtol=1e-4, atol=1e-4)
+
+
+@pytest.mark.parametrize("name", sorted(transform_golden_index().keys()))
+def test_transform_oracle_matches_reference_fixture(name):
+    """oracle/transform_oracle.py vs the transform inside the reference's own LayoutDetectionModel."""
+    pages, samples, shape, meta = build_transform_case(name)
+    got = transform_oracle.page_transform(pages)
+    assert tuple(got.shape) == shape
+    np.testing.assert_allclose(got.reshape(-1)[:: meta["stride"]].numpy(), samples, rtol=0, atol=2e-6)
