@@ -56,6 +56,29 @@ def measured_peaks():
     return dict(hbm_gbs=6650.0, bf16_tflops=1590.0, bf16_tflops_sustained=1400.0, source="fallback")
 
 
+def profiled_traffic(kernel_regex: str):
+    """dram__bytes_read.sum + dram__bytes_write.sum of one launch of the kernel, from the newest committed
+    `ncu --set full` summary under profiles/ (tools/summarize_profiles.py); None if there is none."""
+    import glob
+    import re
+    files = sorted(glob.glob(os.path.join(ROOT, "profiles", "*_ncu_full_summary.txt")), key=os.path.getmtime)
+    unit = {"byte": 1.0, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9}
+    for path in reversed(files):
+        blocks = open(path).read().split("kernel: ")
+        for blk in blocks[1:]:
+            if not re.search(kernel_regex, blk.splitlines()[0]):
+                continue
+            tot = 0.0
+            for key in ("dram__bytes_read.sum", "dram__bytes_write.sum"):
+                m = re.search(re.escape(key) + r"\s+([0-9.,]+)\s+(\w+)", blk)
+                if not m:
+                    break
+                tot += float(m.group(1).replace(",", "")) * unit.get(m.group(2), 1.0)
+            else:
+                return {"bytes": tot, "source": os.path.relpath(path, ROOT)}
+    return None
+
+
 class ClockSampler:
     """nvidia-smi clocks / throttle reasons sampled every 200 ms during the timed region."""
     Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
@@ -305,6 +328,8 @@ def main():
     peak = peaks["bf16_tflops_sustained"]                 # kernel timed inside a long step -> sustained figure
     fl_img = flops_per_image(cfg, H, W)
     model_tflops = fl_img * value / 1e12
+    # DRAM traffic of that kernel from the committed ncu --set full capture (same shape only: base224's fc1)
+    traffic = profiled_traffic(r"gemm_tcgen05_kernel<\d+, 1, 2>") if args.workload == "base224" else None
 
     if rank == 0:
         cpu = None
@@ -327,7 +352,10 @@ def main():
             "roofline": {"bound": "tensor", "kernel": f"gemm_tcgen05_kernel<EPI_BIAS_GELU> M={geo.M} N={I} K={D}",
                          "achieved": round(achieved, 1), "peak": peak, "unit": "TFLOP/s", "frac": round(achieved / peak, 4),
                          "frac_of_burst_peak": round(achieved / peaks["bf16_tflops"], 4), "peak_source": peaks["source"],
-                         "kernel_ms": round(k_ms, 4), "traffic": None},
+                         "kernel_ms": round(k_ms, 4), "traffic": None if traffic is None else round(traffic["bytes"]),
+                         "traffic_unit": "bytes per launch (dram read + write, ncu --set full)",
+                         "traffic_source": None if traffic is None else traffic["source"],
+                         "algorithmic_bytes": 2 * (geo.M * D + I * D + geo.M * I)},
             "e2e": {"value": round(e2e_value, 1), "unit": "images/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                     "ms_per_step": round(e2e_ms / args.steps, 4), "input_dtype": "float16 pinned host",
                     "result": "p5 tap (bf16) copied to pinned host"},

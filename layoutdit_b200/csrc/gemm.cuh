@@ -60,6 +60,9 @@ struct GemmArgs {
 #ifndef LDIT_KSTEP
 #define LDIT_KSTEP 1           // 2: producer / MMA loops take two ring slots per iteration (measured slower: coarser turnaround)
 #endif
+#ifndef LDIT_TAIL_RING
+#define LDIT_TAIL_RING 0       // 1: the last tile's epilogue stages its chunks in the (then idle) operand ring (measured: no gain, same-box A/B 2.68 vs 2.69 ms/step)
+#endif
 #ifndef LDIT_EPI_ROLLED
 #define LDIT_EPI_ROLLED 0      // 1: chunk loop not unrolled (no cross-chunk overlap inside a warp)
 #endif
@@ -113,6 +116,7 @@ struct GemmCfg {
   static constexpr int STAGES = (STAGES_FIT > 8 ? 8 : STAGES_FIT) & ~(LDIT_KSTEP - 1);  // even when the loops take slots in pairs
   static_assert(STAGES >= 3, "pipeline too shallow");
   static_assert(A_BYTES % 1024 == 0 && B_BYTES % 1024 == 0, "swizzle-128B tiles must stay 1 KB aligned");
+  static_assert(kGemmEpiWarps * CHUNKS * CHUNK_BYTES <= STAGES * STAGE_BYTES, "tail staging must fit the operand ring");
   static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + STAGING_BYTES + COLOP_BYTES + BAR_BYTES + 1024;  // + alignment slack
 };
 
@@ -411,6 +415,12 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
       if (tl) tl[4] = clock64();
       mbar_wait(&tfull_bar[acc], acc_phase);
       tcgen05_fence_after();
+      // Experiment knob LDIT_TAIL_RING: the last tile of a CTA overlaps nothing, so its epilogue is pure kernel
+      // tail; its MMAs have completed (tfull) and no further load will be issued, i.e. the operand ring is free,
+      // and every chunk can have a staging buffer of its own there (no per-chunk wait for the previous TMA
+      // store to have read the single regular buffer).  Measured: no change -- the tail is not bound by that wait.
+      const bool last_tile = LDIT_TAIL_RING && (tile + num_clusters >= num_tiles);
+      uint8_t* tail_stage = smem + static_cast<size_t>(warp) * kChunks * Cfg::CHUNK_BYTES;
       if (tl) tl[5] = clock64();
       const uint32_t taddr = tmem_base + acc * kAccStride + cgrp * Cfg::CG_COLS + (static_cast<uint32_t>(quarter * 32) << 16);
       uint32_t r[2][16];
@@ -446,7 +456,7 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
         else release_accumulator(acc);
 #endif
         if (g.dbg & 1) continue;
-        uint8_t* buf = my_stage + (gc & (LDIT_EPI_BUFS - 1)) * Cfg::CHUNK_BYTES;
+        uint8_t* buf = last_tile ? tail_stage + c * Cfg::CHUNK_BYTES : my_stage + (gc & (LDIT_EPI_BUFS - 1)) * Cfg::CHUNK_BYTES;
 
         if constexpr (!Cfg::OUT_F32) {
           float v[16];
@@ -476,7 +486,7 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
             o[j].z = pack_bf16x2(v[8 * j + 4], v[8 * j + 5]);
             o[j].w = pack_bf16x2(v[8 * j + 6], v[8 * j + 7]);
           }
-          if (lane == 0) tma_store_wait_read<LDIT_EPI_BUFS - 1>();  // the last store out of this buffer has finished reading it
+          if (lane == 0 && !last_tile) tma_store_wait_read<LDIT_EPI_BUFS - 1>();  // the last store out of this buffer has finished reading it
           __syncwarp();
           // bf16 rows of 32 B, 32B swizzle: 16-byte piece j of row `lane` sits at j ^ ((lane >> 2) & 1)
           if (!(g.dbg & 16)) {
@@ -500,7 +510,7 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
             }
           }
           if constexpr (EPI == EPI_SCALE_RESID) {
-            if (lane == 0) tma_store_wait_read<LDIT_EPI_BUFS - 1>();
+            if (lane == 0 && !last_tile) tma_store_wait_read<LDIT_EPI_BUFS - 1>();
           }
           __syncwarp();  // EPI_PATCH: every lane has finished reading this buffer (chunk gc-2) long ago; keeps the warp converged
           // fp32 rows of 64 B, 64B swizzle: 16-byte piece j of row `lane` sits at j ^ ((lane >> 1) & 3)

@@ -13,4 +13,8 @@ ncu --set full --clock-control none --import-source on -k regex:gemm_tcgen05 -s 
 ncu --set full --clock-control none --import-source on -k regex:attention_pp -s 12 -c 1 -o $out/attn_$tag $cmd > /dev/null 2>&1
 ncu --set full --clock-control none --import-source on -k regex:layernorm -s 24 -c 1 -o $out/ln_$tag $cmd > /dev/null 2>&1
 ncu --set full --clock-control none --import-source on -k regex:"im2col|taps" -s 5 -c 5 -o $out/rowwise_$tag $cmd > /dev/null 2>&1
+# FPN head (row f1): launch list of a DiTWithFPN forward, full capture of the 56x56 3x3 convolution; fused input transform (row f3)
+ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv --log-file $out/launches_fpn_$tag.csv python tools/fpn_one.py > $out/ncu_launches_fpn_$tag.log 2>&1
+ncu --set full --clock-control none --import-source on -k regex:gemm_tcgen05 -s 2 -c 1 -o $out/conv_$tag python tools/conv_one.py > /dev/null 2>&1
+ncu --set full --clock-control none --import-source on -k regex:pages_rows -s 4 -c 1 -o $out/pages_$tag python tools/transform_bench.py 1024 > /dev/null 2>&1
 ls -la $out
