@@ -177,6 +177,56 @@ def run_reference(args, rank):
     }), flush=True)
 
 
+def run_fpn_line(args, cfg, fac, B, H, W, dev, rank, world, peaks):
+    """Secondary line for SURVEY 8 row f1: DiTWithFPN forward (graph replay), device-resident pages, same timing rules."""
+    import torch.distributed as dist
+    from layoutdit_b200 import DiTWithFPN
+    from layoutdit_b200.config import flops_per_image
+    from layoutdit_b200.synth import make_fpn_state_dict, make_state_dict, synthetic_pages
+    model = DiTWithFPN(pretrained=False, config=cfg, state_dict=make_state_dict(cfg, 0, False),
+                       fpn_state_dict=make_fpn_state_dict(cfg.hidden_size, 256, 0, False), use_cuda_graph=args.graph).to(dev).eval()
+    x = synthetic_pages(B, H, W, 1234 + rank).to(dev)
+    flush = torch.empty(256 * 1024 * 1024, dtype=torch.uint8, device=dev)
+    feats = model(x)
+    eng = model.backbone._get_engine()
+    launches = eng._geometry(B, H, W, 0, "fpn").launches
+    for _ in range(args.warmup):
+        model(x)
+    if world > 1:
+        dist.barrier()
+    torch.cuda.synchronize(dev)
+    ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
+    for s_, e_ in ev:
+        flush.zero_()
+        s_.record(); model(x); e_.record()
+    if world > 1:
+        dist.barrier()
+    torch.cuda.synchronize(dev)
+    total_ms = torch.tensor([sum(a.elapsed_time(b) for a, b in ev)], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(total_ms, op=dist.ReduceOp.MAX)
+    total_ms = float(total_ms.item())
+    Gh, Gw, C = H // 16, W // 16, 256
+    pix = sum(int(Gh * s) * int(Gw * s) for s in (4.0, 2.0, 1.0, 0.5))
+    fpn_flops = 2.0 * 4 * Gh * Gw * cfg.hidden_size * C + 2.0 * pix * 9 * C * C      # laterals on the token grid + 3x3 convolutions
+    value = world * B * args.steps / (total_ms / 1e3)
+    if rank == 0:
+        print(json.dumps({
+            "metric": "DiT backbone + FPN forward throughput", "value": round(value, 1), "unit": "images/s", "n_gpus": world,
+            "steps": args.steps, "warmup": args.warmup, "ms_per_step": round(total_ms / args.steps, 4), "higher_is_better": True,
+            "scaling": "weak", "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
+            "config": {"workload": f"{args.workload}+fpn: {fac} backbone + FeaturePyramidNetwork(256) forward, batch {B} per GPU, {H}x{W}, "
+                                   f"random-init weights, p2..p5 + pool written", "global_batch": world * B,
+                       "l2": "256 MiB buffer written between timed steps (outside the events)", "parallelism": f"dp{world}",
+                       "timing": "CUDA-graph replay; per-step CUDA events summed; max over ranks"},
+            "flops_per_image": flops_per_image(cfg, H, W) + fpn_flops,
+            "model_tflops": round((flops_per_image(cfg, H, W) + fpn_flops) * value / 1e12, 1),
+            "gpu_launches": launches * args.steps, "launches_per_step": launches,
+            "outputs": {k: list(v.shape) for k, v in feats.items()}}), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -185,6 +235,9 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--workload", default="base224", choices=sorted(WORKLOADS))
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--head", default="taps", choices=["taps", "fpn"],
+                    help="taps (default, BASELINE.json's metric): DiTBackbone, four D-channel taps; fpn: DiTWithFPN "
+                         "(SURVEY 8 row f1: laterals, top-down merges, 3x3 convolutions, pool) -- device-resident value only")
     ap.add_argument("--no-graph", dest="graph", action="store_false",
                     help="enqueue the launch plan on the stream every step instead of replaying its captured CUDA graph "
                          "(same device time within noise once the launches carry the PDL attribute, but exposed to host jitter)")
@@ -212,6 +265,10 @@ def main():
     cfg = getattr(cfgmod, fac)()
     lib = _lib.load()
     peaks = measured_peaks()
+
+    if args.head == "fpn":
+        run_fpn_line(args, cfg, fac, B, H, W, dev, rank, world, peaks)
+        return
 
     # random-init weights of the named architecture (HF init, seed 0), synthetic pages
     model = DiTBackbone(pretrained=False, config=cfg, state_dict=make_state_dict(cfg, 0, False),
