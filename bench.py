@@ -174,7 +174,7 @@ def run_reference(args, rank):
         "cpu_baseline": {"value": round(v, 3), "unit": "images/s", "cores": cores, "kind": "port", "sample": sample},
         "e2e": {"value": round(v, 3), "unit": "images/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
-    }), flush=True)
+    }), file=_RESULT, flush=True)
 
 
 def run_fpn_line(args, cfg, fac, B, H, W, dev, rank, world, peaks):
@@ -222,12 +222,26 @@ def run_fpn_line(args, cfg, fac, B, H, W, dev, rank, world, peaks):
             "flops_per_image": flops_per_image(cfg, H, W) + fpn_flops,
             "model_tflops": round((flops_per_image(cfg, H, W) + fpn_flops) * value / 1e12, 1),
             "gpu_launches": launches * args.steps, "launches_per_step": launches,
-            "outputs": {k: list(v.shape) for k, v in feats.items()}}), flush=True)
+            "outputs": {k: list(v.shape) for k, v in feats.items()}}), file=_RESULT, flush=True)
     if world > 1:
         dist.destroy_process_group()
 
 
+_RESULT = sys.stdout   # where the ONE JSON line goes; main() re-points it at the real stdout
+
+
+def isolate_stdout():
+    """Keep stdout for the result line only: NCCL prints its version banner on fd 1 (and other libraries may chat
+    there too), which would precede the JSON line.  fd 1 is re-pointed at stderr; the JSON goes to a dup of the
+    original."""
+    global _RESULT
+    sys.stdout.flush()
+    _RESULT = os.fdopen(os.dup(1), "w")
+    os.dup2(2, 1)
+
+
 def main():
+    isolate_stdout()
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=30)
@@ -422,10 +436,18 @@ def main():
         }
         if cpu is not None:
             out["cpu_baseline"] = cpu
-        print(json.dumps(out), flush=True)
+        print(json.dumps(out), file=_RESULT, flush=True)
     if world > 1:
         dist.destroy_process_group()
 
 
 if __name__ == "__main__":
-    main()
+    import faulthandler
+    faulthandler.enable()          # a fatal signal in any rank leaves a Python stack in stderr instead of nothing
+    try:
+        main()
+    except BaseException:
+        import traceback
+        traceback.print_exc()
+        sys.stderr.flush()
+        raise
