@@ -162,3 +162,19 @@ def test_forward_host_pipeline_matches_forward(cuda_device):
     assert torch.equal(hosts[1], ref["p5"].flip(0).permute(0, 2, 3, 1).cpu())
     with pytest.raises(ValueError):
         m.forward_host(x.cuda())
+
+
+def test_large_page_1024x768(cuda_device):
+    """A 1024x768 page (N = 3073 tokens, 33 key/value tiles per attention item, position table interpolated
+    14x14 -> 64x48) against the oracle: the long-sequence end of the attention kernel and the resize rule on a
+    non-square grid."""
+    cfg = dit_base()
+    sd = make_state_dict(cfg, 1, True)
+    x = synthetic_pages(1, 1024, 768, 77)
+    got = _backbone(cfg, sd)(x.cuda())
+    ref = dit_oracle.dit_backbone_forward(sd, cfg.to_dict(), x)
+    for k in ref:
+        assert got[k].shape == ref[k].shape
+        e = _rel_fro(got[k].float(), ref[k])
+        print("1024x768", k, f"{e:.2e}")
+        assert e < REL_FRO
