@@ -122,6 +122,13 @@ int ldit_conv3x3_bias(const void* in, const void* w, const void* bias, void* out
  * out is [B, ceil(H/2), ceil(W/2), C]. */
 int ldit_subsample2(const void* in, void* out, int B, int H, int W, int C, void* stream);
 
+/* Weight preparation, once per (weights, H, W): resize a table of rows, src f32 [h*w, C] -> dst f32 [oh*ow, C]
+ * (+ add f32 [C] if not NULL), with ATen's rules for F.interpolate(size=(oh, ow), align_corners=False):
+ *  bicubic != 0: the position table at a non-native patch grid (HF interpolate_pos_encoding, HF:138-159);
+ *  bicubic == 0: bilinear, the relative-position bias table at a non-native window (HF:556-571).
+ * Equal sizes copy exactly.  Not part of the per-forward launch sequence. */
+int ldit_resize_rows(const void* src, void* dst, const void* add, int h, int w, int oh, int ow, int C, int bicubic, void* stream);
+
 /* Bytes of the im2col scratch ldit_patch_embed needs. */
 size_t ldit_patch_embed_scratch_bytes(int B, int H, int W);
 

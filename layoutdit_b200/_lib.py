@@ -26,6 +26,7 @@ SIGNATURES = {
     "ldit_fpn_merge": (_i, [_vp, _vp, _vp, _i, _i, _i, _i, _f, _i, _i, _vp]),
     "ldit_conv3x3_bias": (_i, [_vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _vp]),
     "ldit_subsample2": (_i, [_vp, _vp, _i, _i, _i, _i, _vp]),
+    "ldit_resize_rows": (_i, [_vp, _vp, _vp, _i, _i, _i, _i, _i, _i, _vp]),
     "ldit_patch_embed_scratch_bytes": (_c.c_size_t, [_i, _i, _i]),
     "ldit_set_gemm_tile_n": (None, [_i]),
     "ldit_set_gemm_cta_pair": (None, [_i]),

@@ -646,6 +646,21 @@ int ldit_conv3x3_bias(const void* in, const void* w, const void* bias, void* out
   return launch_conv_t<128>(in, w, g, B, H, W, Cin, st);
 }
 
+int ldit_resize_rows(const void* src, void* dst, const void* add, int h, int w, int oh, int ow, int C, int bicubic, void* stream) {
+  if (!src || !dst) return LDIT_E_NULL;
+  if (h <= 0 || w <= 0 || oh <= 0 || ow <= 0 || C <= 0) return LDIT_E_SHAPE;
+  const size_t n = static_cast<size_t>(oh) * ow * C;
+  const unsigned blocks = static_cast<unsigned>((n + 255) / 256);
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  const float* s = static_cast<const float*>(src);
+  const float* a = static_cast<const float*>(add);
+  float* d = static_cast<float*>(dst);
+  // plain launches (no programmatic serialization): weight preparation, outside the forward's launch chain
+  if (bicubic) resize_rows_kernel<true><<<blocks, 256, 0, st>>>(s, d, a, h, w, oh, ow, C);
+  else resize_rows_kernel<false><<<blocks, 256, 0, st>>>(s, d, a, h, w, oh, ow, C);
+  return check_launch();
+}
+
 int ldit_subsample2(const void* in, void* out, int B, int H, int W, int C, void* stream) {
   if (!in || !out) return LDIT_E_NULL;
   if (B <= 0 || H <= 0 || W <= 0 || C <= 0 || (C % 8)) return LDIT_E_SHAPE;

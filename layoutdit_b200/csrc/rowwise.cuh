@@ -230,6 +230,65 @@ pages_rows_im2col_kernel(const T* const* __restrict__ pages, const int* __restri
   }
 }
 
+// --------------------------------------------------------------- weight-preparation resizes
+// Once per (weights, H, W), never per forward: the position table at a non-native patch grid (HF
+// interpolate_pos_encoding, HF:138-159: F.interpolate(mode="bicubic", align_corners=False, size=...)) and the
+// relative-position bias table at a non-native window (HF:556-571: F.interpolate(mode="bilinear", size=...)).
+// src f32 [h*w, C] (C contiguous) -> dst f32 [oh*ow, C] (+ add[C] if given: the conv bias that rides on the
+// position rows).  ATen's rules for `size=`: ratio = in/out; bilinear: src = max(ratio (dst+.5) - .5, 0), two taps;
+// bicubic: src = ratio (dst+.5) - .5 (not clamped), four taps at floor(src)-1..+2 with clamped indices and the
+// cubic-convolution coefficients for A = -0.75.  Same size in and out is an exact copy (+ add).
+__device__ __forceinline__ void cubic_coeffs(float t, float (&w)[4]) {
+  constexpr float A = -0.75f;
+  const float x0 = t + 1.f, x1 = t, x2 = 1.f - t, x3 = 2.f - t;
+  w[0] = ((A * x0 - 5.f * A) * x0 + 8.f * A) * x0 - 4.f * A;
+  w[1] = ((A + 2.f) * x1 - (A + 3.f)) * x1 * x1 + 1.f;
+  w[2] = ((A + 2.f) * x2 - (A + 3.f)) * x2 * x2 + 1.f;
+  w[3] = ((A * x3 - 5.f * A) * x3 + 8.f * A) * x3 - 4.f * A;
+}
+
+template <bool CUBIC>
+__global__ void __launch_bounds__(256)
+resize_rows_kernel(const float* __restrict__ src, float* __restrict__ dst, const float* __restrict__ add, int h, int w, int oh,
+                   int ow, int C) {
+  const size_t idx = static_cast<size_t>(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (idx >= static_cast<size_t>(oh) * ow * C) return;
+  const int c = static_cast<int>(idx % C);
+  const int pix = static_cast<int>(idx / C);
+  const int oy = pix / ow, ox = pix - oy * ow;
+  const float ry = static_cast<float>(h) / oh, rx = static_cast<float>(w) / ow;
+  float acc = 0.f;
+  if (h == oh && w == ow) {
+    acc = src[idx];
+  } else if constexpr (CUBIC) {
+    const float sy = ry * (oy + 0.5f) - 0.5f, sx = rx * (ox + 0.5f) - 0.5f;
+    const int iy = static_cast<int>(floorf(sy)), ix = static_cast<int>(floorf(sx));
+    float wy[4], wx[4];
+    cubic_coeffs(sy - iy, wy);
+    cubic_coeffs(sx - ix, wx);
+#pragma unroll
+    for (int a = 0; a < 4; ++a) {
+      const int yy = min(max(iy - 1 + a, 0), h - 1);
+      float row = 0.f;
+#pragma unroll
+      for (int b = 0; b < 4; ++b) {
+        const int xx = min(max(ix - 1 + b, 0), w - 1);
+        row += wx[b] * src[(static_cast<size_t>(yy) * w + xx) * C + c];
+      }
+      acc += wy[a] * row;
+    }
+  } else {
+    const float sy = fmaxf(ry * (oy + 0.5f) - 0.5f, 0.f), sx = fmaxf(rx * (ox + 0.5f) - 0.5f, 0.f);
+    const int y0 = min(static_cast<int>(sy), h - 1), x0 = min(static_cast<int>(sx), w - 1);
+    const int y1 = y0 + (y0 < h - 1 ? 1 : 0), x1 = x0 + (x0 < w - 1 ? 1 : 0);
+    const float ly = sy - y0, lx = sx - x0;
+    const float* p = src + c;
+    acc = (1.f - ly) * ((1.f - lx) * p[(static_cast<size_t>(y0) * w + x0) * C] + lx * p[(static_cast<size_t>(y0) * w + x1) * C]) +
+          ly * ((1.f - lx) * p[(static_cast<size_t>(y1) * w + x0) * C] + lx * p[(static_cast<size_t>(y1) * w + x1) * C]);
+  }
+  dst[idx] = acc + (add != nullptr ? add[c] : 0.f);
+}
+
 // Token row 0 of every image: cls_token + position row 0 (HF:176-180); cls_pos = their sum.
 __global__ void __launch_bounds__(256)
 cls_rows_kernel(const float* __restrict__ cls_pos, float* __restrict__ xres, int B, int N, int D) {

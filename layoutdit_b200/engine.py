@@ -2,10 +2,10 @@
 workspaces, and the launch sequence over the C ABI (include/ldit.h).
 
 PyTorch is used here for device memory, streams and CUDA-graph capture only; every
-arithmetic step of the forward is a kernel in libldit_b200.so.  The two places a torch op
-touches numbers are weight-preparation steps executed once per (weights, H, W), never per
-forward: resizing the position table (HF:138-159) and the relative-position bias tables
-(HF:556-571) to the current patch grid.
+arithmetic step is a kernel in libldit_b200.so -- including the weight-preparation steps
+executed once per (weights, H, W): resizing the position table (HF:138-159) and the
+relative-position bias tables (HF:556-571) to the current patch grid (``ldit_resize_rows``).
+torch only casts, concatenates and transposes parameters into the kernels' layouts.
 """
 from __future__ import annotations
 
@@ -14,7 +14,6 @@ from collections import OrderedDict
 from dataclasses import dataclass, field
 
 import torch
-import torch.nn.functional as F
 
 from . import _lib
 from .config import DiTConfig
@@ -168,15 +167,25 @@ class Engine:
         self.device = dev
 
     # --------------------------------------------------------------- per-geometry state
-    def _resized_pos(self, Gh, Gw, H, W):
-        """HF ``interpolate_pos_encoding`` (HF:121-159): weight preparation, once per (H, W)."""
-        pos, g = self.pos, self.cfg.grid
-        if Gh * Gw == g * g and H == W:
-            return pos[0]
-        D = pos.shape[-1]
-        grid = pos[0, 1:].reshape(1, g, g, D).permute(0, 3, 1, 2)
-        grid = F.interpolate(grid, size=(Gh, Gw), mode="bicubic", align_corners=False)
-        return torch.cat([pos[0, :1], grid.permute(0, 2, 3, 1).reshape(Gh * Gw, D)], dim=0)
+    def _resize_rows(self, src, h, w, oh, ow, add=None, bicubic=False):
+        """``ldit_resize_rows``: src f32 [h*w, C] -> f32 [oh*ow, C] (+ add[C]).  Weight preparation."""
+        src = src.contiguous()
+        C = src.shape[-1]
+        dst = torch.empty(oh * ow, C, device=self.device, dtype=torch.float32)
+        _lib.check(self.lib.ldit_resize_rows(src.data_ptr(), dst.data_ptr(), _ptr(add), h, w, oh, ow, C, int(bicubic),
+                                             torch.cuda.current_stream(self.device).cuda_stream), "ldit_resize_rows")
+        return dst
+
+    def _pos_rows(self, Gh, Gw, H, W):
+        """Position rows 1..P for this grid + the conv bias, and cls_token + position row 0.
+        HF ``interpolate_pos_encoding`` (HF:121-159): native table when the patch count matches and the image is
+        square, else the patch rows resized bicubically g x g -> Gh x Gw, the CLS row kept.  Once per (H, W)."""
+        g, D = self.cfg.grid, self.cfg.hidden_size
+        native = Gh * Gw == g * g and H == W
+        patch_rows = self.pos[0, 1:]
+        pos_bias = self._resize_rows(patch_rows, *((Gh, Gw, Gh, Gw) if native else (g, g, Gh, Gw)), add=self.b_patch, bicubic=True)
+        cls_pos = self._resize_rows(self.pos[0, :1], 1, 1, 1, 1, add=self.cls).reshape(D)
+        return pos_bias, cls_pos
 
     def _resized_table(self, table, Gh, Gw):
         """First half of ``BeitRelativePositionBias.forward`` (HF:550-571), once per (H, W):
@@ -184,10 +193,8 @@ class Engine:
         g = self.cfg.grid
         old = 2 * g - 1
         nh, nw = 2 * Gh - 1, 2 * Gw - 1
-        sub = table[: old * old].reshape(1, old, old, -1).permute(0, 3, 1, 2)
-        new = F.interpolate(sub, size=(nh, nw), mode="bilinear")
-        new = new.permute(0, 2, 3, 1).reshape(nh * nw, -1)
-        return torch.cat([new, table[old * old:]], dim=0).t().contiguous()
+        new = self._resize_rows(table[: old * old], old, old, nh, nw)          # bilinear; exact copy at the native window
+        return torch.cat([new, table[old * old:]], dim=0).t().contiguous()    # data movement only
 
     def _geometry(self, B, H, W, slot: int = 0, head: str = "taps") -> _Geometry:
         """Workspaces / tables / graph for one (B, H, W).  ``slot`` > 0 gives an independent copy
@@ -204,9 +211,7 @@ class Engine:
         M = B * N
         with torch.no_grad():
             if self.pos is not None:
-                pos = self._resized_pos(Gh, Gw, H, W)
-                pos_bias = (pos[1:] + self.b_patch).contiguous()
-                cls_pos = (self.cls + pos[0]).contiguous()
+                pos_bias, cls_pos = self._pos_rows(Gh, Gw, H, W)
             else:
                 pos_bias = self.b_patch.expand(P, D).contiguous()
                 cls_pos = self.cls.clone()

@@ -199,3 +199,20 @@ def test_resample_taps(lib, B, Gh, Gw, D, scale):
     torch.testing.assert_close(got, ref, rtol=2 ** -8, atol=1e-6)
     # bit-exact against the bf16 rounding of the fp32 reference for the exact-weight scales
     assert (got == ref.to(torch.bfloat16).float()).float().mean() > 0.999
+
+
+# ------------------------------------------------------------------ weight-preparation resizes
+@pytest.mark.parametrize("h,w,oh,ow,C,cubic", [(14, 14, 32, 32, 768, True), (14, 14, 20, 14, 768, True), (4, 4, 6, 4, 128, True),
+                                                (14, 14, 7, 9, 64, True), (27, 27, 63, 63, 12, False), (7, 7, 11, 7, 2, False),
+                                                (27, 27, 13, 19, 12, False), (5, 5, 5, 5, 16, True), (1, 1, 1, 1, 768, False)])
+def test_resize_rows(lib, h, w, oh, ow, C, cubic):
+    """ldit_resize_rows vs F.interpolate(size=..., align_corners=False): HF:138-159 (bicubic) / HF:556-571 (bilinear)."""
+    g = torch.Generator(device="cuda").manual_seed(h * 100 + oh)
+    src = torch.randn(h * w, C, device="cuda", generator=g)
+    add = torch.randn(C, device="cuda", generator=g)
+    dst = torch.empty(oh * ow, C, device="cuda")
+    _lib.check(lib.ldit_resize_rows(src.data_ptr(), dst.data_ptr(), add.data_ptr(), h, w, oh, ow, C, int(cubic), _stream()), "resize")
+    img = src.reshape(1, h, w, C).permute(0, 3, 1, 2)
+    ref = img if (h, w) == (oh, ow) else F.interpolate(img, size=(oh, ow), mode="bicubic" if cubic else "bilinear", align_corners=False)
+    ref = ref.permute(0, 2, 3, 1).reshape(oh * ow, C) + add
+    torch.testing.assert_close(dst, ref, rtol=1e-5, atol=1e-5)
