@@ -386,7 +386,7 @@ def main():
     k_ev = []
     for _ in range(3):
         for name, fn, fargs in plan:
-            if name == "ldit_gemm_bias_gelu":
+            if name in ("ldit_gemm_bias_gelu", "ldit_mlp_fused"):
                 a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
                 a.record(stream); _lib.check(fn(*fargs), name); b.record(stream)
                 k_ev.append((a, b))
@@ -394,7 +394,8 @@ def main():
                 _lib.check(fn(*fargs), name)
     torch.cuda.synchronize(dev)
     k_ms = statistics.mean(sorted(a.elapsed_time(b) for a, b in k_ev)[: max(1, len(k_ev) * 3 // 4)])
-    k_flops = 2.0 * geo.M * I * D
+    fused_mlp = any(name == "ldit_mlp_fused" for name, _, _ in plan)
+    k_flops = (4.0 if fused_mlp else 2.0) * geo.M * I * D
     achieved = k_flops / (k_ms / 1e3) / 1e12
     peak = peaks["bf16_tflops_sustained"]                 # kernel timed inside a long step -> sustained figure
     fl_img = flops_per_image(cfg, H, W)
@@ -420,7 +421,8 @@ def main():
             "model_tflops": round(model_tflops, 1),
             "model_frac_of_peak": round(model_tflops / (world * peaks["bf16_tflops"]), 4),
             "flops_per_image": fl_img,
-            "roofline": {"bound": "tensor", "kernel": f"gemm_tcgen05_kernel<EPI_BIAS_GELU> M={geo.M} N={I} K={D}",
+            "roofline": {"bound": "tensor", "kernel": (f"mlp_tcgen05_kernel (fc1 + fc2 fused) M={geo.M} D={D} I={I}" if fused_mlp
+                                    else f"gemm_tcgen05_kernel<EPI_BIAS_GELU> M={geo.M} N={I} K={D}"),
                          "achieved": round(achieved, 1), "peak": peak, "unit": "TFLOP/s", "frac": round(achieved / peak, 4),
                          "frac_of_burst_peak": round(achieved / peaks["bf16_tflops"], 4), "peak_source": peaks["source"],
                          "kernel_ms": round(k_ms, 4), "traffic": None if traffic is None else round(traffic["bytes"]),

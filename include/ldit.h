@@ -60,6 +60,19 @@ int ldit_gemm_bias_gelu(const void* A, const void* W, const void* bias, void* ou
 int ldit_gemm_bias_scale_residual(const void* A, const void* W, const void* bias, const void* scale, void* x, int M, int N,
                                   int K, void* stream);
 
+/* BeitIntermediate + BeitOutput + layer scale + residual (HF:428-432, 441-445, 500-504) as ONE persistent kernel:
+ *   h bf16 [M, I] = gelu_erf(a bf16 [M, D] x W1 bf16 [I, D]^T + b1);   x f32 [M, D] += lam2 (.) (h x W2 bf16 [D, I]^T + b2)
+ * Same arithmetic as ldit_gemm_bias_gelu followed by ldit_gemm_bias_scale_residual, bit for bit; the two GEMMs
+ * share one balanced tile schedule and fc2 tiles start as soon as the rows of h they read are complete.
+ *  sched  DEVICE int32 [ldit_mlp_clusters(), stride]: the tile lists from ldit_mlp_schedule(M, D, I, ...) (host
+ *         function: call with host_sched == NULL to get `stride`, then with a buffer of clusters * stride ints)
+ *  ready  DEVICE int32 [2 * ceil(M / 256)], zero-initialised once by the caller; left zeroed by every call
+ * D and I must both be multiples of 192 or both multiples of 256 (else LDIT_E_SHAPE: use the two-call form). */
+int ldit_mlp_clusters(void);
+int ldit_mlp_schedule(int M, int D, int I, int* host_sched, int capacity);
+int ldit_mlp_fused(const void* a, const void* W1, const void* b1, void* h, const void* W2, const void* b2, const void* lam2,
+                   void* x, int M, int D, int I, const int* sched, int sched_stride, int* ready, void* stream);
+
 /* BeitEmbeddings.forward, HF:161-184 (Conv2d k16 s16 HF:218 + flatten/transpose HF:220 +
  * cat(cls) HF:176-177 + position add HF:179-180), as an im2col GEMM.
  *  pixels   [B, 3, H, W] of dtype `pixel_dtype` (LDIT_DTYPE_*), contiguous NCHW

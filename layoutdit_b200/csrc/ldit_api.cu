@@ -4,13 +4,16 @@
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
+#include <algorithm>
 #include <utility>
+#include <vector>
 
 #include "../../include/ldit.h"
 #include "attention_mma.cuh"
 #include "attention_tc.cuh"
 #include "attention_tc2.cuh"
 #include "gemm.cuh"
+#include "mlp_fused.cuh"
 #include "rowwise.cuh"
 
 using namespace ldit;
@@ -297,6 +300,92 @@ cudaError_t launch_pages_gather(const void* const* pages, const int* page_hw, __
                        ms[3], ms[4], ms[5]);
 }
 
+// ---- fused MLP (mlp_fused.cuh): tile width and per-pair tile lists
+int mlp_bn(int D, int I) {
+  if (D % 192 == 0 && I % 192 == 0) return 192;
+  if (D % 256 == 0 && I % 256 == 0) return 256;
+  return 0;
+}
+
+// Every CTA pair gets its fc1 tiles first (dealt in row-block order, round by round), then its fc2 tiles.  The number
+// of fc2 tiles per pair differs by at most one; a pair with one more fc2 tile gets w fewer fc1 tiles (w = cost of an
+// fc2 tile in fc1 tiles), so that all lists take equally long; fc2 tiles go to the (pair, k-th fc2 slot) positions in
+// order of their start time, i.e. the earliest free pairs take the earliest (long finished) row blocks.
+int build_mlp_schedule(int M, int D, int I, int bn, int clusters, std::vector<int>& out) {
+  const int mbs = (M + 2 * kBM - 1) / (2 * kBM), nb1 = I / bn, nb2 = D / bn;
+  const int T1 = mbs * nb1, T2 = mbs * nb2, C = clusters;
+  static const int mlp_dbg = [] { const char* e = getenv("LDIT_MLP_DBG"); return e ? atoi(e) : 0; }();
+  if (mlp_dbg & 2) {   // experiments only: plain round-robin over fc1 then fc2, the order two separate launches produce
+    std::vector<std::vector<int>> lists(C);
+    for (int t = 0; t < T1; ++t) lists[t % C].push_back(t);
+    for (int t = 0; t < T2; ++t) lists[t % C].push_back(T1 + t);
+    size_t stride = 1;
+    for (auto& l : lists) stride = std::max(stride, l.size() + 1);
+    out.assign(static_cast<size_t>(C) * stride, -1);
+    for (int c = 0; c < C; ++c) std::copy(lists[c].begin(), lists[c].end(), out.begin() + c * stride);
+    return static_cast<int>(stride);
+  }
+  const double w = 1.15 * static_cast<double>(I) / D;
+  std::vector<int> n2(C, T2 / C), q1(C, 0);
+  for (int c = 0; c < T2 % C; ++c) n2[c] += 1;
+  const double lstar = (T1 + w * T2) / C;
+  long sum = 0;
+  for (int c = 0; c < C; ++c) { q1[c] = std::max(0, static_cast<int>(lstar - w * n2[c] + 0.5)); sum += q1[c]; }
+  while (sum > T1) {   // take from the longest list
+    int best = -1;
+    for (int c = 0; c < C; ++c) if (q1[c] > 0 && (best < 0 || q1[c] + w * n2[c] > q1[best] + w * n2[best])) best = c;
+    if (best < 0) break;
+    --q1[best]; --sum;
+  }
+  while (sum < T1) {   // give to the shortest list
+    int best = 0;
+    for (int c = 1; c < C; ++c) if (q1[c] + w * n2[c] < q1[best] + w * n2[best]) best = c;
+    ++q1[best]; ++sum;
+  }
+  std::vector<std::vector<int>> lists(C);
+  std::vector<int> given(C, 0);
+  for (int next = 0; next < T1;) {
+    for (int c = 0; c < C && next < T1; ++c)
+      if (given[c] < q1[c]) { lists[c].push_back(next++); ++given[c]; }
+  }
+  struct Slot { double start; int c; };
+  std::vector<Slot> slots;
+  for (int c = 0; c < C; ++c)
+    for (int k = 0; k < n2[c]; ++k) slots.push_back({q1[c] + k * w, c});
+  std::stable_sort(slots.begin(), slots.end(), [](const Slot& a, const Slot& b) { return a.start < b.start; });
+  for (int j = 0; j < T2; ++j) lists[slots[j].c].push_back(T1 + j);
+  size_t stride = 1;
+  for (auto& l : lists) stride = std::max(stride, l.size() + 1);
+  out.assign(static_cast<size_t>(C) * stride, -1);
+  for (int c = 0; c < C; ++c) std::copy(lists[c].begin(), lists[c].end(), out.begin() + c * stride);
+  return static_cast<int>(stride);
+}
+
+template <int BN>
+int launch_mlp_t(const void* a, const void* W1, void* h, const void* W2, void* x, MlpArgs g, cudaStream_t st) {
+  using Cfg = MlpCfg<BN>;
+  static bool attr_set = false;
+  if (!attr_set) {
+    cudaError_t e = cudaFuncSetAttribute(mlp_tcgen05_kernel<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES);
+    if (e != cudaSuccess) return static_cast<int>(e);
+    attr_set = true;
+  }
+  CUtensorMap tmA1, tmB1, tmC1, tmA2, tmB2, tmC2;
+  int rc = make_tmap_bf16_2d(&tmA1, a, g.M, g.D, kBM);
+  if (!rc) rc = make_tmap_bf16_2d(&tmB1, W1, g.I, g.D, Cfg::B_ROWS);
+  if (!rc) rc = make_tmap_2d(&tmC1, h, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, g.M, g.I, g.I, 32, kEpiCols, CU_TENSOR_MAP_SWIZZLE_32B);
+  if (!rc) rc = make_tmap_bf16_2d(&tmA2, h, g.M, g.I, kBM);
+  if (!rc) rc = make_tmap_bf16_2d(&tmB2, W2, g.D, g.I, Cfg::B_ROWS);
+  if (!rc) rc = make_tmap_2d(&tmC2, x, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, g.M, g.D, g.D, 32, kEpiCols, CU_TENSOR_MAP_SWIZZLE_64B);
+  if (rc) return rc;
+  const int grid = (num_sms() / 2) * 2;
+  cudaError_t e = launch_kernel(mlp_tcgen05_kernel<BN>, dim3(grid), dim3(kGemmThreads), Cfg::SMEM_BYTES, st, 2, tmA1, tmB1, tmC1, tmA2,
+                                tmB2, tmC2, g);
+  g_launches.fetch_add(1, std::memory_order_relaxed);
+  if (e != cudaSuccess) { (void)cudaGetLastError(); return static_cast<int>(e); }
+  return static_cast<int>(cudaGetLastError());
+}
+
 }  // namespace
 
 extern "C" {
@@ -378,6 +467,48 @@ int ldit_gemm_bias_scale_residual(const void* A, const void* W, const void* bias
   g.scale = static_cast<const float*>(scale);
   g.out = x; g.ldo = N;
   return launch_gemm<EPI_SCALE_RESID>(A, W, g, static_cast<cudaStream_t>(stream));
+}
+
+int ldit_mlp_clusters(void) { return num_sms() / 2; }
+
+int ldit_mlp_schedule(int M, int D, int I, int* host_sched, int capacity) {
+  if (M <= 0 || D <= 0 || I <= 0) return LDIT_E_SHAPE;
+  const int bn = mlp_bn(D, I);
+  if (!bn) return LDIT_E_SHAPE;
+  std::vector<int> sched;
+  const int stride = build_mlp_schedule(M, D, I, bn, ldit_mlp_clusters(), sched);
+  if (host_sched != nullptr) {
+    if (capacity < static_cast<int>(sched.size())) return LDIT_E_SHAPE;
+    std::copy(sched.begin(), sched.end(), host_sched);
+  }
+  return stride;
+}
+
+int ldit_mlp_fused(const void* a, const void* W1, const void* b1, void* h, const void* W2, const void* b2, const void* lam2,
+                   void* x, int M, int D, int I, const int* sched, int sched_stride, int* ready, void* stream) {
+  if (!a || !W1 || !h || !W2 || !x || !sched || !ready) return LDIT_E_NULL;
+  if (M <= 0 || D <= 0 || I <= 0 || (D % 8) || (I % 8) || sched_stride <= 0) return LDIT_E_SHAPE;
+  if (!aligned16(a) || !aligned16(W1) || !aligned16(b1) || !aligned16(h) || !aligned16(W2) || !aligned16(b2) || !aligned16(lam2) ||
+      !aligned16(x))
+    return LDIT_E_ALIGN;
+  const int bn = mlp_bn(D, I);
+  if (!bn) return LDIT_E_SHAPE;
+  MlpArgs g{};
+  g.M = M; g.D = D; g.I = I;
+  g.b1 = static_cast<const float*>(b1);
+  g.b2 = static_cast<const float*>(b2);
+  g.lam2 = static_cast<const float*>(lam2);
+  g.nb1 = I / bn; g.nb2 = D / bn;
+  g.num_m_blocks = (M + 2 * kBM - 1) / (2 * kBM);
+  g.tiles1 = g.num_m_blocks * g.nb1;
+  g.sched = sched; g.sched_stride = sched_stride;
+  g.ready = ready;
+  g.ready_target = 4 * 2 * I;
+  static const int mlp_dbg = [] { const char* e = getenv("LDIT_MLP_DBG"); return e ? atoi(e) : 0; }();
+  g.dbg = mlp_dbg;
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  if (bn == 192) return launch_mlp_t<192>(a, W1, h, W2, x, g, st);
+  return launch_mlp_t<256>(a, W1, h, W2, x, g, st);
 }
 
 size_t ldit_patch_embed_scratch_bytes(int B, int H, int W) {

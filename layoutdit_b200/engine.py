@@ -10,6 +10,7 @@ torch only casts, concatenates and transposes parameters into the kernels' layou
 from __future__ import annotations
 
 import math
+import os
 from collections import OrderedDict
 from dataclasses import dataclass, field
 
@@ -109,6 +110,8 @@ class Engine:
         self._layers: list[_LayerPack] = []
         self._geoms: dict = {}
         self.tap_idx = tap_layer_indices(cfg.num_hidden_layers)
+        # fc1 + fc2 of a layer as one persistent kernel with a balanced tile schedule (ldit_mlp_fused)
+        self.mlp_fused = os.environ.get("LDIT_MLP_FUSED", "0") != "0"
 
     # ------------------------------------------------------------------ weight packing
     def _weights_key(self):
@@ -226,6 +229,13 @@ class Engine:
                         a=torch.empty(M, D, device=dev, dtype=torch.bfloat16),
                         big=torch.empty(M * wide, device=dev, dtype=torch.bfloat16),
                         pos_bias=pos_bias, cls_pos=cls_pos, bias_tables=tables, head=head)
+        if self.mlp_fused:
+            stride = int(self.lib.ldit_mlp_schedule(M, D, I, None, 0))
+            if stride > 0:   # shapes the fused kernel is built for; otherwise the two-call form is used
+                host = torch.empty(int(self.lib.ldit_mlp_clusters()) * stride, dtype=torch.int32)
+                _lib.check(min(0, int(self.lib.ldit_mlp_schedule(M, D, I, host.data_ptr(), host.numel()))), "ldit_mlp_schedule")
+                geo.extra["mlp_sched"] = (host.to(dev), stride)
+                geo.extra["mlp_ready"] = torch.zeros(2 * ((M + 255) // 256), device=dev, dtype=torch.int32)
         if head == "fpn":
             C = self._fpn.C
             bf = dict(device=dev, dtype=torch.bfloat16)
@@ -295,10 +305,18 @@ class Engine:
                 ("ldit_gemm_bias_scale_residual", lib.ldit_gemm_bias_scale_residual,
                  (a, L.wo.data_ptr(), L.bo.data_ptr(), _ptr(L.lam1), xr, M, D, D, stream)),
                 ("ldit_layernorm", lib.ldit_layernorm, (xr, L.ln2_w.data_ptr(), L.ln2_b.data_ptr(), a, M, D, eps, stream)),
-                ("ldit_gemm_bias_gelu", lib.ldit_gemm_bias_gelu, (a, L.w1.data_ptr(), L.b1.data_ptr(), big, M, I, D, stream)),
-                ("ldit_gemm_bias_scale_residual", lib.ldit_gemm_bias_scale_residual,
-                 (big, L.w2.data_ptr(), L.b2.data_ptr(), _ptr(L.lam2), xr, M, D, I, stream)),
             ]
+            if "mlp_sched" in geo.extra:
+                sched, stride = geo.extra["mlp_sched"]
+                plan.append(("ldit_mlp_fused", lib.ldit_mlp_fused,
+                             (a, L.w1.data_ptr(), L.b1.data_ptr(), big, L.w2.data_ptr(), L.b2.data_ptr(), _ptr(L.lam2), xr, M, D, I,
+                              sched.data_ptr(), stride, geo.extra["mlp_ready"].data_ptr(), stream)))
+            else:
+                plan += [
+                    ("ldit_gemm_bias_gelu", lib.ldit_gemm_bias_gelu, (a, L.w1.data_ptr(), L.b1.data_ptr(), big, M, I, D, stream)),
+                    ("ldit_gemm_bias_scale_residual", lib.ldit_gemm_bias_scale_residual,
+                     (big, L.w2.data_ptr(), L.b2.data_ptr(), _ptr(L.lam2), xr, M, D, I, stream)),
+                ]
             emit_tap(i + 1)
         if fpn is not None:
             # top-down pathway, coarsest level first (TV:181-193), then the 3x3 output convolutions and "pool"

@@ -216,3 +216,35 @@ def test_resize_rows(lib, h, w, oh, ow, C, cubic):
     ref = img if (h, w) == (oh, ow) else F.interpolate(img, size=(oh, ow), mode="bicubic" if cubic else "bilinear", align_corners=False)
     ref = ref.permute(0, 2, 3, 1).reshape(oh * ow, C) + add
     torch.testing.assert_close(dst, ref, rtol=1e-5, atol=1e-5)
+
+
+# ------------------------------------------------------------------------- fused MLP (fc1 + fc2)
+@pytest.mark.parametrize("M,D,I", [(12608, 768, 3072), (12608, 1024, 4096), (197, 768, 3072), (3000, 768, 3072), (32800, 768, 3072)])
+def test_mlp_fused_matches_the_two_gemms_bit_for_bit(lib, M, D, I):
+    """ldit_mlp_fused (one persistent kernel, balanced tile lists, fc2 tiles gated on per-row-block readiness counters)
+    against ldit_gemm_bias_gelu + ldit_gemm_bias_scale_residual: identical h and x, counters re-armed, repeatedly."""
+    import ctypes
+    g = torch.Generator(device="cuda").manual_seed(M + D)
+    a = torch.randn(M, D, device="cuda", generator=g).to(torch.bfloat16)
+    W1 = (torch.randn(I, D, device="cuda", generator=g) * 0.05).to(torch.bfloat16)
+    W2 = (torch.randn(D, I, device="cuda", generator=g) * 0.05).to(torch.bfloat16)
+    b1, b2, lam = torch.randn(I, device="cuda", generator=g), torch.randn(D, device="cuda", generator=g), torch.rand(D, device="cuda", generator=g)
+    x0 = torch.randn(M, D, device="cuda", generator=g)
+    st = _stream()
+    h_ref, x_ref = torch.empty(M, I, device="cuda", dtype=torch.bfloat16), x0.clone()
+    _lib.check(lib.ldit_gemm_bias_gelu(a.data_ptr(), W1.data_ptr(), b1.data_ptr(), h_ref.data_ptr(), M, I, D, st), "fc1")
+    _lib.check(lib.ldit_gemm_bias_scale_residual(h_ref.data_ptr(), W2.data_ptr(), b2.data_ptr(), lam.data_ptr(), x_ref.data_ptr(), M, D, I, st), "fc2")
+    stride = lib.ldit_mlp_schedule(M, D, I, None, 0)
+    assert stride > 0
+    host = torch.empty(lib.ldit_mlp_clusters() * stride, dtype=torch.int32)
+    assert lib.ldit_mlp_schedule(M, D, I, host.data_ptr(), host.numel()) == stride
+    sched = host.cuda()
+    ready = torch.zeros(2 * ((M + 255) // 256), device="cuda", dtype=torch.int32)
+    for rep in range(3):
+        h, x = torch.full((M, I), float("nan"), device="cuda", dtype=torch.bfloat16), x0.clone()
+        _lib.check(lib.ldit_mlp_fused(a.data_ptr(), W1.data_ptr(), b1.data_ptr(), h.data_ptr(), W2.data_ptr(), b2.data_ptr(), lam.data_ptr(),
+                                      x.data_ptr(), M, D, I, sched.data_ptr(), stride, ready.data_ptr(), st), "mlp")
+        torch.cuda.synchronize()
+        assert torch.equal(h, h_ref), f"h differs (rep {rep})"
+        assert torch.equal(x, x_ref), f"x differs (rep {rep})"
+        assert int(ready.abs().sum()) == 0, "counters not re-armed"
