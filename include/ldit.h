@@ -156,6 +156,13 @@ void ldit_set_gemm_cta_pair(int ctas);
  * prologue overlaps the tail of its predecessor in the stream; 0: plain stream order.  Also LDIT_PDL. */
 void ldit_set_pdl(int on);
 
+/* Opt-in: every kernel enqueued after this call carries an L2 access-policy window (persisting) over
+ * [ptr, ptr + bytes) -- meant for the fp32 residual stream x, which LayerNorms, reduce-add epilogues and taps
+ * revisit all forward long while larger activations stream through L2 in between.  Grows the device-wide
+ * persisting-L2 set-aside (cudaLimitPersistingL2CacheSize) to min(bytes, device maximum) the first time.
+ * (NULL, 0) switches it off for subsequent launches.  Host-side state, like the other knobs. */
+int ldit_set_l2_persist(void* ptr, size_t bytes);
+
 /* Tuning knob: 0 (default) = persistent ping-pong tcgen05/TMEM attention kernel; 1 = the
  * warp-level mma.sync variant and 2 = the one-tile-per-CTA tcgen05 variant, both kept for
  * comparison.  Also settable with LDIT_ATTN_IMPL. */
