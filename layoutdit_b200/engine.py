@@ -9,6 +9,7 @@ torch only casts, concatenates and transposes parameters into the kernels' layou
 """
 from __future__ import annotations
 
+import dataclasses
 import math
 import os
 from collections import OrderedDict
@@ -204,11 +205,18 @@ class Engine:
         return torch.cat([new, table[old * old:]], dim=0).t().contiguous()    # data movement only
 
     def _geometry(self, B, H, W, slot: int = 0, head: str = "taps") -> _Geometry:
-        """Workspaces / tables / graph for one (B, H, W).  ``slot`` > 0 gives an independent copy
-        (own workspaces, own captured graph, own static outputs) for pipelined callers."""
+        """Workspaces / tables / graph for one (B, H, W).  ``slot`` > 0 gives pipelined callers their own captured
+        graph, graph input and static outputs; the workspaces (x, a, big, tables) are those of slot 0 -- every
+        forward of this engine runs on the caller's one compute stream, so they are never live in two forwards at
+        once, and sharing them keeps the L2 working set (and the persistence window) that of a single forward."""
         key = (B, H, W) if (slot == 0 and head == "taps") else (B, H, W, slot, head)
         geo = self._geoms.get(key)
         if geo is not None:
+            return geo
+        if slot != 0:
+            base = self._geometry(B, H, W, 0, head)
+            geo = dataclasses.replace(base, graph=None, graph_in=None, graph_out=None, launches=0, extra=dict(base.extra))
+            self._geoms[key] = geo
             return geo
         cfg, dev = self.cfg, self.device
         D, I = cfg.hidden_size, cfg.intermediate_size
@@ -348,13 +356,10 @@ class Engine:
         """Size of the L2 persistence window for this geometry, 0 = none.  The set-aside comes out of the 126 MB L2
         every other buffer lives in, so it only pays while it stays a modest part of it (measured: 58 MB over x and a
         at base224 -3.4 % step time; 77 MB at large224 +3.5 %; 79 of x's 100 MB at base512 +37 %): x and a when they
-        fit 64 MB, else x alone when it does; the slots of the host-fed pipeline, which alternate between two residual
-        streams, persist x only and only up to 40 MB each."""
+        fit 64 MB, else x alone when it does."""
         if not self.l2_persist:
             return 0
         xb = geo.x.numel() * 4
-        if geo.extra.get("slot", 0) != 0:
-            return xb if xb <= 40 << 20 else 0
         if xb * 3 // 2 <= 64 << 20:
             return xb * 3 // 2
         return xb if xb <= 64 << 20 else 0
