@@ -162,6 +162,9 @@ void ldit_set_pdl(int on);
  * persisting-L2 set-aside (cudaLimitPersistingL2CacheSize) to min(bytes, device maximum) the first time.
  * (NULL, 0) switches it off for subsequent launches.  Host-side state, like the other knobs. */
 int ldit_set_l2_persist(void* ptr, size_t bytes);
+/* Same with the set-aside capped at `set_aside_cap` bytes (0 = no cap): a window larger than the set-aside persists
+ * only the fraction of its lines that fits (hitRatio = set-aside / window). */
+int ldit_set_l2_persist_capped(void* ptr, size_t bytes, size_t set_aside_cap);
 
 /* Tuning knob: 0 (default) = persistent ping-pong tcgen05/TMEM attention kernel; 1 = the
  * warp-level mma.sync variant and 2 = the one-tile-per-CTA tcgen05 variant, both kept for

@@ -36,6 +36,7 @@ SIGNATURES = {
     "ldit_set_attention_impl": (None, [_i]),
     "ldit_set_pdl": (None, [_i]),
     "ldit_set_l2_persist": (_i, [_vp, _c.c_size_t]),
+    "ldit_set_l2_persist_capped": (_i, [_vp, _c.c_size_t, _c.c_size_t]),
     "ldit_debug_attention_timeline": (None, [_vp]),
     "ldit_debug_gemm_timeline": (None, [_vp]),
     "ldit_launch_count": (_c.c_ulonglong, []),

@@ -433,7 +433,9 @@ void ldit_debug_attention_timeline(void* device_buffer) { g_attn_dbg = static_ca
 void ldit_set_attention_impl(int impl) { g_attn_impl.store((impl == 1 || impl == 2) ? impl : 0); }
 void ldit_set_pdl(int on) { g_pdl.store(on ? 1 : 0); }
 
-int ldit_set_l2_persist(void* ptr, size_t bytes) {
+int ldit_set_l2_persist(void* ptr, size_t bytes) { return ldit_set_l2_persist_capped(ptr, bytes, 0); }
+
+int ldit_set_l2_persist_capped(void* ptr, size_t bytes, size_t set_aside_cap) {
   if (ptr == nullptr || bytes == 0) {
     g_persist_ptr = nullptr;
     g_persist_bytes = 0;
@@ -445,6 +447,7 @@ int ldit_set_l2_persist(void* ptr, size_t bytes) {
   if (e == cudaSuccess) e = cudaDeviceGetAttribute(&max_window, cudaDevAttrMaxAccessPolicyWindowSize, dev);
   if (e != cudaSuccess) { (void)cudaGetLastError(); return static_cast<int>(e); }
   size_t want = bytes < static_cast<size_t>(max_persist) ? bytes : static_cast<size_t>(max_persist);
+  if (set_aside_cap > 0 && want > set_aside_cap) want = set_aside_cap;
   static size_t limit_set = 0;
   if (want > limit_set) {   // the set-aside is a device-wide limit: only ever grown, and only on request
     e = cudaDeviceSetLimit(cudaLimitPersistingL2CacheSize, want);
@@ -454,7 +457,8 @@ int ldit_set_l2_persist(void* ptr, size_t bytes) {
   g_persist_ptr = ptr;
   g_persist_bytes = bytes < static_cast<size_t>(max_window) ? bytes : static_cast<size_t>(max_window);
   // a window larger than the set-aside would thrash inside it: persist only the fraction that fits
-  g_persist_ratio = g_persist_bytes <= limit_set ? 1.0f : static_cast<float>(limit_set) / static_cast<float>(g_persist_bytes);
+  const size_t avail = (set_aside_cap > 0 && set_aside_cap < limit_set) ? set_aside_cap : limit_set;
+  g_persist_ratio = g_persist_bytes <= avail ? 1.0f : static_cast<float>(avail) / static_cast<float>(g_persist_bytes);
   return LDIT_OK;
 }
 void ldit_set_gemm_cta_pair(int ctas) { g_cta_pair.store(ctas == 1 ? 1 : 2); }

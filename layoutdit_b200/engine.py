@@ -117,6 +117,8 @@ class Engine:
         # On by default (LDIT_L2_PERSIST=0 switches it off): measured -3 % step time at base224.  Process-level side
         # effect: grows the device's persisting-L2 set-aside to the window size (at most the device maximum, 79 MB).
         self.l2_persist = os.environ.get("LDIT_L2_PERSIST", "1") != "0"
+        self._persist_cap = int(os.environ.get("LDIT_L2_PERSIST_CAP_MB", "64")) << 20
+        self._persist_partial = os.environ.get("LDIT_L2_PERSIST_PARTIAL", "0") != "0"   # experiment: partial window for x > cap
 
     # ------------------------------------------------------------------ weight packing
     def _weights_key(self):
@@ -360,16 +362,19 @@ class Engine:
         if not self.l2_persist:
             return 0
         xb = geo.x.numel() * 4
-        if xb * 3 // 2 <= 64 << 20:
+        cap = self._persist_cap
+        if xb * 3 // 2 <= cap:
             return xb * 3 // 2
-        return xb if xb <= 64 << 20 else 0
+        if xb <= cap or self._persist_partial:
+            return xb          # a window larger than the cap persists the fraction cap / window of its lines
+        return 0
 
     def _enqueue(self, geo: _Geometry, x: torch.Tensor, outs, stream: int, limit: int | None = None):
         """Enqueue the whole forward on ``stream``.  Returns the number of kernels launched."""
         n0 = self.lib.ldit_launch_count()
         persist = self._persist_bytes(geo)
         if persist:   # keep the residual stream (and the LayerNorm / context buffer behind it) resident in L2
-            _lib.check(self.lib.ldit_set_l2_persist(geo.x.data_ptr(), persist), "ldit_set_l2_persist")
+            _lib.check(self.lib.ldit_set_l2_persist_capped(geo.x.data_ptr(), persist, self._persist_cap), "ldit_set_l2_persist")
         try:
             for name, fn, args in self._plan(geo, x, outs, stream)[:limit]:
                 _lib.check(fn(*args), name)
