@@ -46,6 +46,7 @@ struct GemmArgs {
   int P;               // EPI_PATCH: patches per image; GEMM row b*P+p -> token row b*(P+1)+1+p
   const float* posb;   // EPI_PATCH: [P, N] fp32 = position rows 1..P + conv bias
   int num_m_blocks, num_n_blocks;
+  int m_reverse;       // 1: row blocks are visited last-to-first (consume a just-written A operand freshest-first, see ldit_api.cu)
   // EPI_CONV_BIAS (3x3 convolution, stride 1, zero padding 1, over a channels-last image [B, H, W, Cin] as an
   // implicit GEMM): a CTA's 128 rows are a cv_th x cv_tw patch of output pixels, a CTA pair covers two patches
   // side by side; an image is cv_ty x cv_tx pair tiles; K = 9 taps x Cin in (ky, kx, cin) order, cv_cblocks = Cin/64
@@ -241,7 +242,8 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
     uint32_t phase = 0;
     int pti = 0;
     for (int tile = cluster_id; tile < num_tiles; tile += num_clusters, ++pti) {
-      const int m0 = (tile / g.num_n_blocks) * Cfg::TILE_M + static_cast<int>(rank) * kBM;
+      const int mblk = g.m_reverse ? g.num_m_blocks - 1 - tile / g.num_n_blocks : tile / g.num_n_blocks;
+      const int m0 = mblk * Cfg::TILE_M + static_cast<int>(rank) * kBM;
       const int n0 = (tile % g.num_n_blocks) * BN + static_cast<int>(rank) * Cfg::B_ROWS;
       int cvx = 0, cvy = 0, cvb = 0, cv_c = 0, cv_kx = 0, cv_ky = 0;   // EPI_CONV_BIAS: patch origin, running (ky, kx, channel block)
       if constexpr (EPI == EPI_CONV_BIAS) {
@@ -371,7 +373,7 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
 
     int ti = 0;
     for (int tile = cluster_id; tile < num_tiles; tile += num_clusters, ++ti) {
-      const int row0 = (tile / g.num_n_blocks) * Cfg::TILE_M + row_in_tile;
+      const int row0 = (g.m_reverse ? g.num_m_blocks - 1 - tile / g.num_n_blocks : tile / g.num_n_blocks) * Cfg::TILE_M + row_in_tile;
       const int col0 = (tile % g.num_n_blocks) * BN + cgrp * Cfg::CG_COLS;
       int cvx = 0, cvy = 0, cvb = 0;   // EPI_CONV_BIAS: first pixel of this warp's 32 rows (32 / cv_tw image rows of cv_tw pixels)
       if constexpr (EPI == EPI_CONV_BIAS) {

@@ -511,6 +511,11 @@ int ldit_gemm_bias_scale_residual(const void* A, const void* W, const void* bias
   g.bias = static_cast<const float*>(bias);
   g.scale = static_cast<const float*>(scale);
   g.out = x; g.ldo = N;
+  // Experiment knob LDIT_FC2_REVERSE=1: a long-K residual GEMM (fc2) visits its row blocks last-to-first, so that of an
+  // A operand the previous GEMM has just written front to back, and that is larger than what L2 keeps of it (77 MB at
+  // base224), the rows still resident are consumed first.  Measured neutral (2.62 vs 2.64 ms/step): off.
+  static const int rev = [] { const char* e = getenv("LDIT_FC2_REVERSE"); return e ? atoi(e) : 0; }();
+  g.m_reverse = (rev && K > N) ? 1 : 0;
   return launch_gemm<EPI_SCALE_RESID>(A, W, g, static_cast<cudaStream_t>(stream));
 }
 
