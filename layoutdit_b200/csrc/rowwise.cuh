@@ -12,8 +12,11 @@ namespace ldit {
 // lives in registers: mean, then the centred second moment (eps is ~0, so the one-pass
 // E[x^2]-E[x]^2 form is not safe), all in fp32.  fp32 residual stream in, bf16 out
 // (the next kernel is a bf16 GEMM).
+#ifndef LDIT_LN_MINBLOCKS
+#define LDIT_LN_MINBLOCKS 1
+#endif
 template <int VPL>  // float4 per lane: D = 128 * VPL
-__global__ void __launch_bounds__(256)
+__global__ void __launch_bounds__(256, LDIT_LN_MINBLOCKS)
 layernorm_kernel(const float* __restrict__ x, const float* __restrict__ gamma, const float* __restrict__ beta,
                  __nv_bfloat16* __restrict__ y, int rows, float eps) {
   pdl_launch_dependents();
