@@ -134,3 +134,51 @@ def test_fpn_argument_validation_without_gpu():
     assert lib.ldit_conv3x3_bias(p16, p16, None, p16, 1, 8, 8, 100, 256, None) == -2   # Cin not a multiple of 64
     assert lib.ldit_fpn_merge(p16, None, p16, 1, 4, 4, 100, 2.0, 0, 0, None) == -2     # C not a multiple of 8
     assert lib.ldit_subsample2(p16, p16 + 2, 1, 4, 4, 256, None) == -3
+
+
+def test_fused_mlp_schedule_is_a_balanced_partition():
+    """ldit_mlp_schedule (host function): every fc1 / fc2 tile exactly once, a pair's fc1 tiles before its fc2 tiles,
+    both in increasing order, lists no longer than two separate launches would make them."""
+    import numpy as np
+    lib = _lib.load()
+    C = lib.ldit_mlp_clusters()
+    assert C >= 1
+    for (M, D, I) in [(12608, 768, 3072), (32800, 768, 3072), (12608, 1024, 4096), (197, 768, 3072), (1, 768, 3072)]:
+        stride = lib.ldit_mlp_schedule(M, D, I, None, 0)
+        assert stride > 0
+        buf = np.full(C * stride, -7, dtype=np.int32)
+        assert lib.ldit_mlp_schedule(M, D, I, buf.ctypes.data, buf.size) == stride
+        assert lib.ldit_mlp_schedule(M, D, I, buf.ctypes.data, buf.size - 1) == -2      # capacity too small
+        s = buf.reshape(C, stride)
+        bn = 192 if D % 192 == 0 and I % 192 == 0 else 256
+        mbs = (M + 255) // 256
+        T1, T2 = mbs * (I // bn), mbs * (D // bn)
+        assert sorted(s[s >= 0].tolist()) == list(range(T1 + T2))
+        w = 1.15 * I / D
+        longest = 0.0
+        for c in range(C):
+            row = s[c]
+            n = int((row >= 0).sum())
+            assert (row[:n] >= 0).all() and (row[n:] == -1).all()
+            l = row[:n]
+            second = l >= T1
+            assert (np.diff(second.astype(int)) >= 0).all()                  # fc1 tiles first
+            assert (np.diff(l[~second]) > 0).all() and (np.diff(l[second]) > 0).all()
+            longest = max(longest, float((~second).sum() + w * second.sum()))
+        separate = -(-T1 // C) + w * -(-T2 // C)
+        assert longest <= separate + 1e-6
+    assert lib.ldit_mlp_schedule(34, 128, 256, None, 0) == -2                            # widths the kernel is not built for
+
+
+def test_l2_persistence_window_policy():
+    """Engine._persist_bytes: x + a up to the cap, else x alone, else nothing."""
+    import types
+    from layoutdit_b200.engine import Engine
+    eng = Engine.__new__(Engine)
+    eng.l2_persist, eng._persist_cap, eng._persist_partial = True, 64 << 20, False
+    geo = lambda rows, D: types.SimpleNamespace(x=torch.empty(rows, D, device="meta"), extra={})
+    assert eng._persist_bytes(geo(12608, 768)) == 12608 * 768 * 6          # base224: x and a (58 MB)
+    assert eng._persist_bytes(geo(12608, 1024)) == 12608 * 1024 * 4        # large224: x alone (52 MB)
+    assert eng._persist_bytes(geo(32800, 768)) == 0                        # base512: x is 100 MB
+    eng.l2_persist = False
+    assert eng._persist_bytes(geo(12608, 768)) == 0
