@@ -246,7 +246,6 @@ class Engine:
                         a=xa[M * D * 4:].view(torch.bfloat16).view(M, D),
                         big=torch.empty(M * wide, device=dev, dtype=torch.bfloat16),
                         pos_bias=pos_bias, cls_pos=cls_pos, bias_tables=tables, head=head)
-        geo.extra["slot"] = slot
         if self.mlp_fused:
             stride = int(self.lib.ldit_mlp_schedule(M, D, I, None, 0))
             if stride > 0:   # shapes the fused kernel is built for; otherwise the two-call form is used
