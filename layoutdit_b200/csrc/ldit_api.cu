@@ -445,13 +445,23 @@ int ldit_set_l2_persist_capped(void* ptr, size_t bytes, size_t set_aside_cap) {
   cudaError_t e = cudaGetDevice(&dev);
   if (e == cudaSuccess) e = cudaDeviceGetAttribute(&max_persist, cudaDevAttrMaxPersistingL2CacheSize, dev);
   if (e == cudaSuccess) e = cudaDeviceGetAttribute(&max_window, cudaDevAttrMaxAccessPolicyWindowSize, dev);
-  if (e != cudaSuccess) { (void)cudaGetLastError(); return static_cast<int>(e); }
+  if (e != cudaSuccess || max_persist <= 0 || max_window <= 0) {   // no persisting L2 on this device / partition: window stays off
+    (void)cudaGetLastError();
+    g_persist_ptr = nullptr;
+    g_persist_bytes = 0;
+    return e != cudaSuccess ? static_cast<int>(e) : LDIT_OK;
+  }
   size_t want = bytes < static_cast<size_t>(max_persist) ? bytes : static_cast<size_t>(max_persist);
   if (set_aside_cap > 0 && want > set_aside_cap) want = set_aside_cap;
   static size_t limit_set = 0;
   if (want > limit_set) {   // the set-aside is a device-wide limit: only ever grown, and only on request
     e = cudaDeviceSetLimit(cudaLimitPersistingL2CacheSize, want);
-    if (e != cudaSuccess) { (void)cudaGetLastError(); return static_cast<int>(e); }
+    if (e != cudaSuccess) {   // e.g. under MPS: leave the window off, report, and let the caller carry on without it
+      (void)cudaGetLastError();
+      g_persist_ptr = nullptr;
+      g_persist_bytes = 0;
+      return static_cast<int>(e);
+    }
     limit_set = want;
   }
   g_persist_ptr = ptr;

@@ -373,7 +373,8 @@ class Engine:
         n0 = self.lib.ldit_launch_count()
         persist = self._persist_bytes(geo)
         if persist:   # keep the residual stream (and the LayerNorm / context buffer behind it) resident in L2
-            _lib.check(self.lib.ldit_set_l2_persist_capped(geo.x.data_ptr(), persist, self._persist_cap), "ldit_set_l2_persist")
+            if self.lib.ldit_set_l2_persist_capped(geo.x.data_ptr(), persist, self._persist_cap) != 0:
+                self.l2_persist, persist = False, 0     # an optimisation the device refused (MPS, MIG slice ...): run without it
         try:
             for name, fn, args in self._plan(geo, x, outs, stream)[:limit]:
                 _lib.check(fn(*args), name)
