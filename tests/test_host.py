@@ -182,3 +182,23 @@ def test_l2_persistence_window_policy():
     assert eng._persist_bytes(geo(32800, 768)) == 0                        # base512: x is 100 MB
     eng.l2_persist = False
     assert eng._persist_bytes(geo(12608, 768)) == 0
+
+
+def test_argument_validation_of_the_widened_entry_points_without_gpu():
+    lib = _lib.load()
+    buf = ctypes.create_string_buffer(256)
+    p16 = (ctypes.addressof(buf) + 15) & ~15
+    # fused transform: page table / sizes are required, H and W multiples of 16, non-zero std
+    assert lib.ldit_patch_embed_pages(None, p16, 0, 0, .5, .5, .5, .5, .5, .5, p16, p16, p16, p16, p16, 1, 224, 224, 768, None) == -1
+    assert lib.ldit_patch_embed_pages(p16, p16, 0, 0, .5, .5, .5, .5, .5, .5, p16, p16, p16, p16, p16, 1, 220, 224, 768, None) == -2
+    assert lib.ldit_patch_embed_pages(p16, p16, 0, 0, .5, .5, .5, 0., .5, .5, p16, p16, p16, p16, p16, 1, 224, 224, 768, None) == -2
+    assert lib.ldit_patch_embed_pages(p16, p16, 0, 9, .5, .5, .5, .5, .5, .5, p16, p16, p16, p16, p16, 1, 224, 224, 768, None) == -4
+    # weight-preparation resize
+    assert lib.ldit_resize_rows(None, p16, None, 14, 14, 20, 20, 768, 1, None) == -1
+    assert lib.ldit_resize_rows(p16, p16, None, 14, 0, 20, 20, 768, 1, None) == -2
+    # fused MLP: schedule and counters are required; widths must be multiples of 192 or of 256
+    assert lib.ldit_mlp_fused(p16, p16, p16, p16, p16, p16, None, p16, 128, 768, 3072, None, 4, p16, None) == -1
+    assert lib.ldit_mlp_fused(p16, p16, p16, p16, p16, p16, None, p16, 128, 128, 320, p16, 4, p16, None) == -2
+    assert lib.ldit_mlp_fused(p16, p16, p16, p16 + 4, p16, p16, None, p16, 128, 768, 3072, p16, 4, p16, None) == -3
+    # L2 window: clearing never fails, also without a device
+    assert lib.ldit_set_l2_persist(None, 0) == 0
