@@ -12,6 +12,7 @@
 #include "attention_mma.cuh"
 #include "attention_tc.cuh"
 #include "attention_tc2.cuh"
+#include "attention_v3.cuh"
 #include "gemm.cuh"
 #include "mlp_fused.cuh"
 #include "rowwise.cuh"
@@ -430,7 +431,7 @@ const char* ldit_error_string(int code) {
 void ldit_set_gemm_tile_n(int bn) { g_forced_bn.store((bn == 128 || bn == 192 || bn == 256) ? bn : 0); }
 void ldit_debug_gemm_timeline(void* device_buffer) { g_gemm_tl = static_cast<long long*>(device_buffer); }
 void ldit_debug_attention_timeline(void* device_buffer) { g_attn_dbg = static_cast<long long*>(device_buffer); }
-void ldit_set_attention_impl(int impl) { g_attn_impl.store((impl == 1 || impl == 2) ? impl : 0); }
+void ldit_set_attention_impl(int impl) { g_attn_impl.store((impl >= 1 && impl <= 3) ? impl : 0); }
 void ldit_set_pdl(int on) { g_pdl.store(on ? 1 : 0); }
 
 int ldit_set_l2_persist(void* ptr, size_t bytes) { return ldit_set_l2_persist_capped(ptr, bytes, 0); }
@@ -481,13 +482,15 @@ int ldit_layernorm(const void* x, const void* gamma, const void* beta, void* y, 
   if (rows <= 0 || D <= 0 || (D % 128) || D > 2048) return LDIT_E_SHAPE;
   if (!aligned16(x) || !aligned16(gamma) || !aligned16(beta) || !aligned16(y)) return LDIT_E_ALIGN;
   cudaStream_t st = static_cast<cudaStream_t>(stream);
-  const int blocks = (rows + 7) / 8;
+  const int lnw = ln_warps(D / 128);
+  const int want = (rows + lnw - 1) / lnw;          // persistent: two blocks per SM, rows dealt evenly
+  const int blocks = want < 2 * num_sms() ? want : 2 * num_sms();
   const float* xf = static_cast<const float*>(x);
   const float* gf = static_cast<const float*>(gamma);
   const float* bf = static_cast<const float*>(beta);
   __nv_bfloat16* yb = static_cast<__nv_bfloat16*>(y);
 #define LDIT_LN_CASE(V) \
-  case V: launch_kernel(layernorm_kernel<V>, dim3(blocks), dim3(256), 0, st, 1, xf, gf, bf, yb, rows, eps); break;
+  case V: launch_kernel(layernorm_kernel<V>, dim3(blocks), dim3(lnw * 32), 0, st, 1, xf, gf, bf, yb, rows, eps); break;
   switch (D / 128) {
     LDIT_LN_CASE(1) LDIT_LN_CASE(2) LDIT_LN_CASE(3) LDIT_LN_CASE(4) LDIT_LN_CASE(5) LDIT_LN_CASE(6) LDIT_LN_CASE(7)
     LDIT_LN_CASE(8) LDIT_LN_CASE(9) LDIT_LN_CASE(10) LDIT_LN_CASE(11) LDIT_LN_CASE(12) LDIT_LN_CASE(13)
@@ -651,8 +654,46 @@ int ldit_attention(const void* qkv, void* ctx, const void* bias_table, int B, in
   if (impl < 0) {
     const char* e = getenv("LDIT_ATTN_IMPL");
     impl = e ? atoi(e) : 0;
-    if (impl != 1 && impl != 2) impl = 0;
+    if (impl < 1 || impl > 3) impl = 0;
     g_attn_impl.store(impl);
+  }
+  if (impl == 3) {
+    AttnV3Args a{};
+    a.bias_table = static_cast<const float*>(bias_table);
+    a.B = B; a.N = N; a.heads = heads; a.D = D; a.Gh = Gh; a.Gw = Gw; a.T = T;
+    a.n_ktiles = (N + kA3KT - 1) / kA3KT;
+    a.n_qpairs = (N + 255) / 256;
+    a.num_items = B * heads * a.n_qpairs;
+    a.scale_log2e = scale_log2e;
+    a.dbg = g_attn_dbg;
+    CUtensorMap tmQ, tmKV, tmO;
+    int rc = make_tmap_qkv_3d(&tmQ, qkv, B, N, 3 * D, 128);
+    if (rc) return rc;
+    rc = make_tmap_qkv_3d(&tmKV, qkv, B, N, 3 * D, kA3KT);
+    if (rc) return rc;
+    rc = make_tmap_rows_3d(&tmO, ctx, B, N, D, 32);   // ctx as [B, N, D]: box 32 rows x 64 cols
+    if (rc) return rc;
+    size_t smem = 1024 + kA3SmemTiles + (kA3NumBars + 2) * 8;
+    if (bias_table) smem += (2 * static_cast<size_t>(T) + N) * 4;
+    if (smem > 227 * 1024) return LDIT_E_SHAPE;
+    const int per_sm = smem <= 113 * 1024 ? 2 : 1;   // the kernel is sized to be resident twice per SM
+    const int slots = per_sm * num_sms();
+    const int grid = a.num_items < slots ? a.num_items : slots;
+    static size_t max_set[2] = {0, 0};
+    const int bi = bias_table ? 1 : 0;
+    if (smem > max_set[bi]) {
+      cudaError_t e = bi ? cudaFuncSetAttribute(attention_v3_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem))
+                         : cudaFuncSetAttribute(attention_v3_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem));
+      if (e != cudaSuccess) return static_cast<int>(e);
+      // two CTAs per SM need a ~200 KB carve-out: ask for the largest one instead of leaving it to the driver's heuristic
+      e = bi ? cudaFuncSetAttribute(attention_v3_kernel<true>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared)
+             : cudaFuncSetAttribute(attention_v3_kernel<false>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
+      if (e != cudaSuccess) return static_cast<int>(e);
+      max_set[bi] = smem;
+    }
+    if (bi) launch_kernel(attention_v3_kernel<true>, dim3(grid), dim3(kA3Threads), smem, st, 1, tmQ, tmKV, tmO, a);
+    else launch_kernel(attention_v3_kernel<false>, dim3(grid), dim3(kA3Threads), smem, st, 1, tmQ, tmKV, tmO, a);
+    return check_launch();
   }
   if (impl == 0) {
     AttnP2Args a{};

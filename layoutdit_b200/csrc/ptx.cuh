@@ -70,12 +70,35 @@ __device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
 }
 // Bounded wait: a protocol bug must surface as a launch failure, never as a hung GPU
 // (a hang costs the whole box).  2 s is ~1000x any legitimate wait in these kernels.
+// (A suspend-time hint on try_wait was measured and rejected: waiting warps then wake up later, which costs the
+// GEMM's producer / issuer / epilogue hand-offs more than the polling instructions cost anybody -- 2.56 vs 2.47 ms/step.)
 __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
   if (mbar_try_wait(bar, parity)) return;
   const uint64_t t0 = global_timer_ns();
   uint32_t spins = 0;
   while (!mbar_try_wait(bar, parity)) {
     if ((++spins & 0x3FF) == 0 && global_timer_ns() - t0 > 2000000000ull) __trap();
+  }
+}
+
+// Wait of a warp whose wake-up latency does not matter (a TMA producer waiting for a free ring slot several
+// tiles ahead of need): try_wait with a suspend-time hint, so that it sleeps in hardware instead of competing
+// for issue slots with the working warps of its SM sub-partition.
+__device__ __forceinline__ void mbar_wait_relaxed(uint64_t* bar, uint32_t parity) {
+  if (mbar_try_wait(bar, parity)) return;
+  const uint64_t t0 = global_timer_ns();
+  uint32_t spins = 0;
+  for (;;) {
+    uint32_t ok;
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2, %3;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t}"
+        : "=r"(ok)
+        : "r"(smem_u32(bar)), "r"(parity), "r"(2000u)
+        : "memory");
+    if (ok) return;
+    if ((++spins & 0x3F) == 0 && global_timer_ns() - t0 > 2000000000ull) __trap();
   }
 }
 

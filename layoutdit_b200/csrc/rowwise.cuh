@@ -12,50 +12,69 @@ namespace ldit {
 // lives in registers: mean, then the centred second moment (eps is ~0, so the one-pass
 // E[x^2]-E[x]^2 form is not safe), all in fp32.  fp32 residual stream in, bf16 out
 // (the next kernel is a bf16 GEMM).
-#ifndef LDIT_LN_MINBLOCKS
-#define LDIT_LN_MINBLOCKS 1
-#endif
+// Persistent: the 85 rows an SM owns at base224 do not fit its register file at once (85 x 3 KB), so a
+// one-row-per-warp grid runs in 1.3 waves of fully exposed load latency.  Here two blocks of 8-16 warps per SM
+// each walk their rows with the NEXT row's loads already in flight while the current one is reduced,
+// normalised and stored; rows are dealt so that every block gets the same number (+-1).
+// Warps per block by row width, so that two rows of registers per lane fit without spills at two blocks per SM.
+__host__ __device__ constexpr int ln_warps(int vpl) { return vpl <= 4 ? 16 : (vpl <= 6 ? 10 : (vpl <= 8 ? 8 : 4)); }
 template <int VPL>  // float4 per lane: D = 128 * VPL
-__global__ void __launch_bounds__(256, LDIT_LN_MINBLOCKS)
+__global__ void __launch_bounds__(ln_warps(VPL) * 32, 2)
 layernorm_kernel(const float* __restrict__ x, const float* __restrict__ gamma, const float* __restrict__ beta,
                  __nv_bfloat16* __restrict__ y, int rows, float eps) {
   pdl_launch_dependents();
   pdl_wait();
   constexpr int D = 128 * VPL;
-  const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
-  if (warp >= rows) return;
-  const float4* xr = reinterpret_cast<const float4*>(x + static_cast<size_t>(warp) * D);
-  float4 v[VPL];
-  float sum = 0.f;
-#pragma unroll
-  for (int i = 0; i < VPL; ++i) {
-    v[i] = xr[lane + 32 * i];
-    sum += (v[i].x + v[i].y) + (v[i].z + v[i].w);
-  }
-#pragma unroll
-  for (int o = 16; o > 0; o >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, o);
-  const float mean = sum * (1.0f / D);
-  float sq = 0.f;
-#pragma unroll
-  for (int i = 0; i < VPL; ++i) {
-    v[i].x -= mean; v[i].y -= mean; v[i].z -= mean; v[i].w -= mean;
-    sq += (v[i].x * v[i].x + v[i].y * v[i].y) + (v[i].z * v[i].z + v[i].w * v[i].w);
-  }
-#pragma unroll
-  for (int o = 16; o > 0; o >>= 1) sq += __shfl_xor_sync(0xffffffffu, sq, o);
-  const float rstd = rsqrtf(sq * (1.0f / D) + eps);
-  uint2* yr = reinterpret_cast<uint2*>(y + static_cast<size_t>(warp) * D);
+  constexpr int kLnWarps = ln_warps(VPL);
+  const int stride = gridDim.x * kLnWarps;
+  int row = blockIdx.x + gridDim.x * warp;
+  if (row >= rows) return;
   const float4* g4 = reinterpret_cast<const float4*>(gamma);
   const float4* b4 = reinterpret_cast<const float4*>(beta);
+  float4 v[VPL], nx[VPL];
+  {
+    const float4* xr = reinterpret_cast<const float4*>(x + static_cast<size_t>(row) * D);
 #pragma unroll
-  for (int i = 0; i < VPL; ++i) {
-    const float4 g = __ldg(g4 + lane + 32 * i);
-    const float4 b = __ldg(b4 + lane + 32 * i);
-    uint2 o;
-    o.x = pack_bf16x2(fmaf(v[i].x * rstd, g.x, b.x), fmaf(v[i].y * rstd, g.y, b.y));
-    o.y = pack_bf16x2(fmaf(v[i].z * rstd, g.z, b.z), fmaf(v[i].w * rstd, g.w, b.w));
-    yr[lane + 32 * i] = o;
+    for (int i = 0; i < VPL; ++i) v[i] = xr[lane + 32 * i];
+  }
+  for (; row < rows; row += stride) {
+    const int nrow = row + stride;
+    if (nrow < rows) {
+      const float4* xr = reinterpret_cast<const float4*>(x + static_cast<size_t>(nrow) * D);
+#pragma unroll
+      for (int i = 0; i < VPL; ++i) nx[i] = xr[lane + 32 * i];
+    }
+    float sum = 0.f;
+#pragma unroll
+    for (int i = 0; i < VPL; ++i) sum += (v[i].x + v[i].y) + (v[i].z + v[i].w);
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, o);
+    const float mean = sum * (1.0f / D);
+    float sq = 0.f;
+#pragma unroll
+    for (int i = 0; i < VPL; ++i) {
+      v[i].x -= mean; v[i].y -= mean; v[i].z -= mean; v[i].w -= mean;
+      sq += (v[i].x * v[i].x + v[i].y * v[i].y) + (v[i].z * v[i].z + v[i].w * v[i].w);
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) sq += __shfl_xor_sync(0xffffffffu, sq, o);
+    const float rstd = rsqrtf(sq * (1.0f / D) + eps);
+    uint2* yr = reinterpret_cast<uint2*>(y + static_cast<size_t>(row) * D);
+#pragma unroll
+    for (int i = 0; i < VPL; ++i) {
+      const float4 g = __ldg(g4 + lane + 32 * i);
+      const float4 b = __ldg(b4 + lane + 32 * i);
+      uint2 o;
+      o.x = pack_bf16x2(fmaf(v[i].x * rstd, g.x, b.x), fmaf(v[i].y * rstd, g.y, b.y));
+      o.y = pack_bf16x2(fmaf(v[i].z * rstd, g.z, b.z), fmaf(v[i].w * rstd, g.w, b.w));
+      yr[lane + 32 * i] = o;
+    }
+    if (nrow < rows) {
+#pragma unroll
+      for (int i = 0; i < VPL; ++i) v[i] = nx[i];
+    }
   }
 }
 

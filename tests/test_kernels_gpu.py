@@ -159,7 +159,7 @@ def _dense_bias(table_t, Gh, Gw):
     return table_t[:, idx.to(table_t.device)].unsqueeze(0)
 
 
-@pytest.mark.parametrize("impl", [0, 1, 2])
+@pytest.mark.parametrize("impl", [0, 1, 2, 3])
 @pytest.mark.parametrize("with_bias", [False, True])
 @pytest.mark.parametrize("B,heads,Gh,Gw", [(2, 2, 4, 4), (3, 12, 14, 14), (2, 4, 14, 20), (1, 3, 32, 32), (2, 2, 5, 7),
                                            (1, 2, 13, 16), (2, 1, 1, 1)])
