@@ -112,13 +112,32 @@ def infer_config(dit_sd: dict, patch_size: int = 16, **overrides) -> DiTConfig:
     return DiTConfig(**kw)
 
 
+# never evaluated by the backbone and absent from the real microsoft/dit-* files: those are
+# BeitForMaskedImageModeling exports, built with BeitModel(add_pooling_layer=False) (HF:799)
+OPTIONAL_DIT_KEYS = ("pooler.layernorm.weight", "pooler.layernorm.bias")
+
+
+def load_dit_state_dict(dit, sd: dict, strict: bool = True):
+    """``dit.load_state_dict`` with HF ``from_pretrained`` semantics for the pooler: ``pooler.layernorm.*`` may be
+    missing (it keeps its initial value, HF warns "newly initialized"); every other mismatch raises when ``strict``."""
+    res = dit.load_state_dict(sd, strict=False)
+    missing = [k for k in res.missing_keys if k not in OPTIONAL_DIT_KEYS]
+    unexpected = [k for k in res.unexpected_keys if not k.endswith(_IGNORED_SUFFIX)]
+    if strict and (missing or unexpected):
+        raise RuntimeError(f"Error(s) in loading state_dict for {type(dit).__name__}: "
+                           f"Missing key(s): {missing}. Unexpected key(s): {unexpected}.")
+    return res
+
+
 def load_checkpoint(module, src, strict: bool = True):
     """Load ``src`` (a path or a state dict in any of the formats above) into a ``DiTBackbone`` or
     ``DiTWithFPN``.  Returns the :class:`SplitCheckpoint` (``.other`` lists what was not consumed)."""
     sd = read_state_dict(src) if isinstance(src, (str, os.PathLike)) else src
     parts = split_checkpoint(sd)
     backbone = module.backbone if hasattr(module, "backbone") else module
-    backbone.dit.load_state_dict(parts.dit, strict=strict)
+    load_dit_state_dict(backbone.dit, parts.dit, strict=strict)
+    if hasattr(backbone, "pretrained"):
+        backbone.pretrained = False   # real weights are in: nothing left to fetch
     if hasattr(module, "fpn"):
         if parts.fpn:
             module.fpn.load_state_dict(parts.fpn, strict=strict)

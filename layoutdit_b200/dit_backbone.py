@@ -17,6 +17,8 @@ in bf16; the forward is inference-only (no autograd graph is recorded).
 """
 from __future__ import annotations
 
+import os
+import warnings
 from collections import OrderedDict
 
 import torch
@@ -39,13 +41,26 @@ class DiTBackbone(nn.Module):
             config = DiTConfig.from_hf(config)
         self.config = config
         self.dit = DiTParameters(config)
+        # pretrained=True: the reference downloads microsoft/dit-base here (R:dit_backbone.py:27-29).  There is
+        # no network on the target boxes, so the weights must come from the caller: `state_dict=` (HF BeitModel
+        # keys, bare or prefixed), `pretrained="/path/to/checkpoint"`, the environment variable
+        # LDIT_PRETRAINED_PATH, or `.dit.load_state_dict(...)` afterwards exactly as R:model.py:65-70 does.
+        # Asking for pretrained weights and getting random ones silently would be the worst outcome, hence the warning.
+        from . import checkpoint as _ckpt
+        path = pretrained if isinstance(pretrained, (str, os.PathLike)) else None
         if state_dict is not None:
-            self.dit.load_state_dict(state_dict, strict=True)
-        # pretrained=True: the reference downloads microsoft/dit-base here
-        # (R:dit_backbone.py:27-29).  There is no network on the target boxes: pass
-        # `state_dict=` (HF BeitModel keys) or call `.dit.load_state_dict(...)` afterwards,
-        # exactly as R:model.py:65-70 does.
-        self.pretrained = pretrained
+            _ckpt.load_dit_state_dict(self.dit, _ckpt.split_checkpoint(state_dict).dit, strict=True)
+            pretrained = False
+        elif pretrained:
+            path = path or os.environ.get("LDIT_PRETRAINED_PATH")
+            if path:
+                _ckpt.load_dit_state_dict(self.dit, _ckpt.split_checkpoint(_ckpt.read_state_dict(path)).dit, strict=True)
+                pretrained = False
+            else:
+                warnings.warn("DiTBackbone(pretrained=True): no weights were given (state_dict=, pretrained=<path> or "
+                              "LDIT_PRETRAINED_PATH) and the hub is unreachable -- the module holds RANDOM-INIT weights "
+                              "until .dit.load_state_dict(...) is called", RuntimeWarning, stacklevel=2)
+        self.pretrained = bool(pretrained)   # True = still waiting for real weights
         d = config.num_hidden_layers
         self.layer_idxs = tap_layer_indices(d)
         self.scales = list(TAP_SCALES)

@@ -94,3 +94,57 @@ def test_errors():
         checkpoint.load_checkpoint(DiTBackbone(pretrained=False, config=cfg), sd, strict=True)
     parts = checkpoint.load_checkpoint(DiTBackbone(pretrained=False, config=cfg), sd, strict=False)
     assert parts.dit_prefix == ""
+
+
+def test_real_dit_checkpoint_layout_without_pooler_loads(tmp_path):
+    """microsoft/dit-base|large are BeitForMaskedImageModeling exports: BeitModel(add_pooling_layer=False) under
+    ``beit.`` plus top-level ``layernorm.*`` / ``lm_head.*`` and NO ``pooler.*`` (HF:799).  All three entry points
+    (ctor, load_checkpoint, build_from_checkpoint) must take that file."""
+    cfg = DiTConfig(**TINY)
+    sd = make_state_dict(cfg, 5, True)
+    mim = {"beit." + k: v for k, v in sd.items() if not k.startswith("pooler.")}
+    mim["layernorm.weight"] = torch.ones(cfg.hidden_size)
+    mim["layernorm.bias"] = torch.zeros(cfg.hidden_size)
+    mim["lm_head.weight"] = torch.zeros(8192, cfg.hidden_size)
+    mim["lm_head.bias"] = torch.zeros(8192)
+    path = str(tmp_path / "pytorch_model.bin")
+    torch.save(mim, path)
+    m1 = DiTBackbone(pretrained=False, config=cfg, state_dict=mim)
+    m2 = DiTBackbone(pretrained=False, config=cfg)
+    parts = checkpoint.load_checkpoint(m2, path)                  # strict=True by default
+    m3 = checkpoint.build_from_checkpoint(path)
+    assert sorted(parts.other) == ["layernorm.bias", "layernorm.weight", "lm_head.bias", "lm_head.weight"]
+    for m in (m1, m2, m3):
+        got = m.dit.state_dict()
+        for k, v in sd.items():
+            if not k.startswith("pooler."):
+                assert torch.equal(got[k], v), k
+        assert m.pretrained is False
+    # a genuinely missing tensor still raises
+    broken = {k: v for k, v in mim.items() if "layer.1.output.dense.weight" not in k}
+    with pytest.raises(RuntimeError, match="Missing"):
+        checkpoint.load_checkpoint(DiTBackbone(pretrained=False, config=cfg), broken)
+
+
+def test_pretrained_without_weights_warns_and_a_path_is_honoured(tmp_path, monkeypatch):
+    """R:dit_backbone.py:27-29 downloads the weights when pretrained=True; offline that must not degrade silently."""
+    cfg = DiTConfig(**TINY)
+    monkeypatch.delenv("LDIT_PRETRAINED_PATH", raising=False)
+    with pytest.warns(RuntimeWarning, match="RANDOM-INIT"):
+        m = DiTBackbone(config=cfg)                               # pretrained=True is the reference's default
+    assert m.pretrained is True
+    with pytest.warns(RuntimeWarning, match="RANDOM-INIT"):
+        DiTWithFPN(pretrained=True, config=cfg)
+    sd = make_state_dict(cfg, 9, True)
+    path = str(tmp_path / "dit.pth")
+    torch.save(sd, path)
+    import warnings
+    with warnings.catch_warnings():
+        warnings.simplefilter("error")
+        a = DiTBackbone(pretrained=path, config=cfg)
+        monkeypatch.setenv("LDIT_PRETRAINED_PATH", path)
+        b = DiTBackbone(pretrained=True, config=cfg)
+        c = DiTBackbone(pretrained=True, config=cfg, state_dict=sd)
+    for m in (a, b, c):
+        assert m.pretrained is False
+        assert torch.equal(m.dit.state_dict()["encoder.layer.0.lambda_1"], sd["encoder.layer.0.lambda_1"])
