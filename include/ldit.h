@@ -34,6 +34,7 @@ extern "C" {
 #define LDIT_E_ALIGN (-3)      /* pointer / pitch alignment */
 #define LDIT_E_DTYPE (-4)      /* unknown dtype code */
 #define LDIT_E_NO_DRIVER (-5)  /* cuTensorMapEncodeTiled not resolvable (no CUDA driver) */
+#define LDIT_E_UNSUPPORTED (-6) /* experimental entry point / variant not compiled into this build */
 
 #define LDIT_DTYPE_F32 0
 #define LDIT_DTYPE_F16 1
@@ -67,7 +68,9 @@ int ldit_gemm_bias_scale_residual(const void* A, const void* W, const void* bias
  *  sched  DEVICE int32 [ldit_mlp_clusters(), stride]: the tile lists from ldit_mlp_schedule(M, D, I, ...) (host
  *         function: call with host_sched == NULL to get `stride`, then with a buffer of clusters * stride ints)
  *  ready  DEVICE int32 [2 * ceil(M / 256)], zero-initialised once by the caller; left zeroed by every call
- * D and I must both be multiples of 192 or both multiples of 256 (else LDIT_E_SHAPE: use the two-call form). */
+ * D and I must both be multiples of 192 or both multiples of 256 (else LDIT_E_SHAPE: use the two-call form).
+ * EXPERIMENTAL (measured 14-21 % slower than the two launches): only in -DLDIT_EXPERIMENTAL builds, otherwise
+ * ldit_mlp_schedule / ldit_mlp_fused return LDIT_E_UNSUPPORTED. */
 int ldit_mlp_clusters(void);
 int ldit_mlp_schedule(int M, int D, int I, int* host_sched, int capacity);
 int ldit_mlp_fused(const void* a, const void* W1, const void* b1, void* h, const void* W2, const void* b2, const void* lam2,
@@ -156,25 +159,32 @@ void ldit_set_gemm_cta_pair(int ctas);
  * prologue overlaps the tail of its predecessor in the stream; 0: plain stream order.  Also LDIT_PDL. */
 void ldit_set_pdl(int on);
 
-/* Opt-in: every kernel enqueued after this call carries an L2 access-policy window (persisting) over
- * [ptr, ptr + bytes) -- meant for the fp32 residual stream x, which LayerNorms, reduce-add epilogues and taps
- * revisit all forward long while larger activations stream through L2 in between.  Grows the device-wide
- * persisting-L2 set-aside (cudaLimitPersistingL2CacheSize) to min(bytes, device maximum) the first time.
- * (NULL, 0) switches it off for subsequent launches.  Host-side state, like the other knobs. */
-int ldit_set_l2_persist(void* ptr, size_t bytes);
-/* Same with the set-aside capped at `set_aside_cap` bytes (0 = no cap): a window larger than the set-aside persists
- * only the fraction of its lines that fits (hitRatio = set-aside / window). */
-int ldit_set_l2_persist_capped(void* ptr, size_t bytes, size_t set_aside_cap);
+/* Opt-in: every kernel enqueued ON `stream` after this call carries an L2 access-policy window (persisting) over
+ * [ptr, ptr + bytes) -- meant for the fp32 residual stream x, which LayerNorms, reduce-add epilogues and taps revisit
+ * all forward long while larger activations stream through L2 in between.  The window is host-side state keyed by
+ * the stream (two engines, streams or devices in one process do not see each other's); (stream, NULL, 0, 0) removes
+ * it.  `set_aside_cap` caps the persisting-L2 set-aside this call may request (0 = no cap): a window larger than the
+ * set-aside persists only the fraction of its lines that fits (hitRatio = set-aside / window).  Side effect: grows
+ * the device-wide cudaLimitPersistingL2CacheSize of the current device to min(bytes, cap, device maximum); it is never
+ * shrunk again.  Returns a cudaError_t if the device refuses (MPS, MIG): the window is then off, the caller may go on. */
+int ldit_set_l2_window(void* stream, void* ptr, size_t bytes, size_t set_aside_cap);
 
-/* Tuning knob: 0 (default) = persistent ping-pong tcgen05/TMEM attention kernel; 1 = the
- * warp-level mma.sync variant and 2 = the one-tile-per-CTA tcgen05 variant, both kept for
- * comparison.  Also settable with LDIT_ATTN_IMPL. */
+/* Bytes of workspace one forward needs for B pages of H x W at hidden size D / MLP width I, as the host module lays it
+ * out in ONE allocation: residual stream x f32 [M, D], then a bf16 [M, D] (x and a contiguous: they form the L2 window),
+ * then the wide buffer bf16 [M, max(3D, I, 768)] (QKV, MLP hidden and im2col scratch have disjoint lifetimes);
+ * M = B ((H/16)(W/16) + 1); each part rounded up to 1 KB.  Outputs (taps / FPN maps) are the caller's. */
+size_t ldit_workspace_bytes(int B, int H, int W, int D, int I);
+
+/* Attention variant: 0 (default) = attention_v3 (two CTAs per SM, double-buffered scores).  1 = warp-level mma.sync,
+ * 2 = one-tile-per-CTA tcgen05, 4 = the round-1 ping-pong tcgen05 kernel: superseded, only in -DLDIT_EXPERIMENTAL
+ * builds (ldit_attention returns LDIT_E_UNSUPPORTED otherwise).  Also settable with LDIT_ATTN_IMPL. */
 void ldit_set_attention_impl(int impl);
+/* 1 if the library was built with -DLDIT_EXPERIMENTAL (superseded attention variants, ldit_mlp_fused), else 0. */
+int ldit_has_experimental(void);
 
-/* Experiments only: when non-NULL, the default attention kernel records clock64() stamps of its
- * softmax phases into this device buffer of gridDim*2*16*8 int64.  NULL switches it off. */
+/* Diagnosis builds only (-DLDIT_A3_TIMELINE / -DLDIT_DEBUG_HOOKS): device buffers the attention / GEMM kernels record
+ * clock64() stamps into.  In the product build these calls do nothing: no debug path is compiled into the kernels. */
 void ldit_debug_attention_timeline(void* device_buffer);
-/* Same for the GEMM kernels: (num_SMs/2)*16*8 int64 (issuer and epilogue stamps per tile). */
 void ldit_debug_gemm_timeline(void* device_buffer);
 
 /* Number of kernels the library has enqueued since load / last reset (for gpu_launches). */

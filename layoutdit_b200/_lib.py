@@ -35,8 +35,9 @@ SIGNATURES = {
     "ldit_set_gemm_cta_pair": (None, [_i]),
     "ldit_set_attention_impl": (None, [_i]),
     "ldit_set_pdl": (None, [_i]),
-    "ldit_set_l2_persist": (_i, [_vp, _c.c_size_t]),
-    "ldit_set_l2_persist_capped": (_i, [_vp, _c.c_size_t, _c.c_size_t]),
+    "ldit_set_l2_window": (_i, [_vp, _vp, _c.c_size_t, _c.c_size_t]),
+    "ldit_workspace_bytes": (_c.c_size_t, [_i, _i, _i, _i, _i]),
+    "ldit_has_experimental": (_i, []),
     "ldit_debug_attention_timeline": (None, [_vp]),
     "ldit_debug_gemm_timeline": (None, [_vp]),
     "ldit_launch_count": (_c.c_ulonglong, []),

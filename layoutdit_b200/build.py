@@ -28,10 +28,15 @@ def needs_build() -> bool:
     return any(os.path.getmtime(d) > t for d in deps)
 
 
-def build(force: bool = False, verbose: bool = False) -> str:
-    if not force and not needs_build():
+def build(force: bool = False, verbose: bool = False, extra_flags=(), out: str | None = None) -> str:
+    """Product build by default.  ``extra_flags``: e.g. ``["-DLDIT_EXPERIMENTAL"]`` (superseded attention variants and the
+    fused fc1+fc2 kernel), ``["-DLDIT_DEBUG_HOOKS"]`` (GEMM timeline / LDIT_GEMM_DBG), ``["-DLDIT_A3_TIMELINE"]``;
+    also read from the environment variable LDIT_BUILD_FLAGS.  ``out``: write a variant somewhere else (A/B builds)."""
+    extra_flags = list(extra_flags) + os.environ.get("LDIT_BUILD_FLAGS", "").split()
+    target = out or LIB
+    if not force and not extra_flags and out is None and not needs_build():
         return LIB
-    cmd = [_nvcc(), *NVCC_FLAGS, "-o", LIB] + [os.path.join(CSRC, s) for s in SOURCES]
+    cmd = [_nvcc(), *NVCC_FLAGS, *extra_flags, "-o", target] + [os.path.join(CSRC, s) for s in SOURCES]
     if verbose:
         cmd.insert(1, "-Xptxas=-v")
     r = subprocess.run(cmd, capture_output=True, text=True)
@@ -39,7 +44,7 @@ def build(force: bool = False, verbose: bool = False) -> str:
         raise RuntimeError("nvcc failed:\n" + r.stdout + r.stderr)
     if verbose:
         print(r.stderr)
-    return LIB
+    return target
 
 
 if __name__ == "__main__":

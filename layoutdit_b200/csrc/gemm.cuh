@@ -51,9 +51,19 @@ struct GemmArgs {
   // implicit GEMM): a CTA's 128 rows are a cv_th x cv_tw patch of output pixels, a CTA pair covers two patches
   // side by side; an image is cv_ty x cv_tx pair tiles; K = 9 taps x Cin in (ky, kx, cin) order, cv_cblocks = Cin/64
   int cv_tw, cv_th, cv_tx, cv_ty, cv_cblocks;
-  int dbg;             // experiments only (LDIT_GEMM_DBG): bit 0 = epilogue drains TMEM but stores nothing
-  long long* tl;       // experiments only: clock64 timeline [cluster][16 tiles][8] (leader CTA), or nullptr
+#ifdef LDIT_DEBUG_HOOKS   // diagnosis builds only (tools/gemm_timeline.py, LDIT_GEMM_DBG): never in the product library
+  int dbg;             // bit 0 = epilogue drains TMEM but stores nothing, ...
+  long long* tl;       // clock64 timeline [cluster][16 tiles][8] (leader CTA), or nullptr
+#endif
 };
+
+#ifdef LDIT_DEBUG_HOOKS
+#define LDIT_DBG(g, bit) ((g).dbg & (bit))
+#define LDIT_TL(g) ((g).tl)
+#else
+#define LDIT_DBG(g, bit) false
+#define LDIT_TL(g) static_cast<long long*>(nullptr)
+#endif
 
 #ifndef LDIT_EPI_BUFS
 #define LDIT_EPI_BUFS 1        // staging buffers per epilogue warp (1: the smem goes to the operand ring instead)
@@ -253,7 +263,7 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
         cvx = ((r - ty * g.cv_tx) * 2 + static_cast<int>(rank)) * g.cv_tw;
         cvy = ty * g.cv_th;
       }
-      long long* ptl = (g.tl != nullptr && rank == 0 && lane == 0 && pti < 16) ? g.tl + (static_cast<size_t>(cluster_id) * 16 + pti) * 16 : nullptr;
+      long long* ptl = (LDIT_TL(g) != nullptr && rank == 0 && lane == 0 && pti < 16) ? LDIT_TL(g) + (static_cast<size_t>(cluster_id) * 16 + pti) * 16 : nullptr;
       long long wempty = 0;
       for (int kb = 0; kb < nkb; kb += kstep) {
         const long long w0 = ptl ? clock64() : 0;
@@ -297,7 +307,7 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
       uint32_t acc_phase = 0;
       int ti = 0;
       for (int tile = cluster_id; tile < num_tiles; tile += num_clusters, ++ti) {
-        long long* tl = (g.tl != nullptr && lane == 0 && ti < 16) ? g.tl + (static_cast<size_t>(cluster_id) * 16 + ti) * 16 : nullptr;
+        long long* tl = (LDIT_TL(g) != nullptr && lane == 0 && ti < 16) ? LDIT_TL(g) + (static_cast<size_t>(cluster_id) * 16 + ti) * 16 : nullptr;
         if (tl) tl[0] = clock64();
         mbar_wait(&tempty_bar[acc], acc_phase ^ 1);
         tcgen05_fence_after();
@@ -383,8 +393,8 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
         cvx = ((r - ty * g.cv_tx) * 2 + static_cast<int>(rank)) * g.cv_tw;
         cvy = ty * g.cv_th + quarter * (32 / g.cv_tw);
       }
-      long long* tl = (g.tl != nullptr && rank == 0 && warp == 0 && lane == 0 && ti < 16)
-                          ? g.tl + (static_cast<size_t>(cluster_id) * 16 + ti) * 16 : nullptr;
+      long long* tl = (LDIT_TL(g) != nullptr && rank == 0 && warp == 0 && lane == 0 && ti < 16)
+                          ? LDIT_TL(g) + (static_cast<size_t>(cluster_id) * 16 + ti) * 16 : nullptr;
 
       // EPI_PATCH: this lane reads back rows (lane >> 2) + 8 i, 16-byte piece lane & 3
       size_t p_orow[4];
@@ -457,7 +467,7 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
         if (c + 1 < kChunks) tmem_ld_32x32b_x16(taddr + (c + 1) * kEpiCols, r[(c + 1) & 1]);
         else release_accumulator(acc);
 #endif
-        if (g.dbg & 1) continue;
+        if (LDIT_DBG(g, 1)) continue;
         uint8_t* buf = last_tile ? tail_stage + c * Cfg::CHUNK_BYTES : my_stage + (gc & (LDIT_EPI_BUFS - 1)) * Cfg::CHUNK_BYTES;
 
         if constexpr (!Cfg::OUT_F32) {
@@ -470,7 +480,7 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
                       v[4 * j + 2], v[4 * j + 3]);
           }
           if constexpr (EPI == EPI_BIAS_GELU) {
-            if (!(g.dbg & 8)) {
+            if (!LDIT_DBG(g, 8)) {
 #pragma unroll
               for (int e = 0; e < 16; e += 2) {
                 gelu_erf_pair(v[e], v[e + 1], gelu_k);
@@ -491,7 +501,7 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
           if (lane == 0 && !last_tile) tma_store_wait_read<LDIT_EPI_BUFS - 1>();  // the last store out of this buffer has finished reading it
           __syncwarp();
           // bf16 rows of 32 B, 32B swizzle: 16-byte piece j of row `lane` sits at j ^ ((lane >> 2) & 1)
-          if (!(g.dbg & 16)) {
+          if (!LDIT_DBG(g, 16)) {
 #pragma unroll
             for (int j = 0; j < 2; ++j)
               *reinterpret_cast<uint4*>(buf + lane * 32 + ((j ^ ((lane >> 2) & 1)) << 4)) = o[j];
@@ -540,8 +550,8 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
         } else {
           fence_proxy_async_smem();  // generic-proxy smem writes -> visible to the TMA engine
           __syncwarp();
-          if (lane == 0 && col_ok && !(g.dbg & 2)) {
-            if constexpr (EPI == EPI_SCALE_RESID) { if (g.dbg & 32) tma_store_2d(&tmC, buf, col, row0); else tma_reduce_add_2d(&tmC, buf, col, row0); }
+          if (lane == 0 && col_ok && !LDIT_DBG(g, 2)) {
+            if constexpr (EPI == EPI_SCALE_RESID) { if (LDIT_DBG(g, 32)) tma_store_2d(&tmC, buf, col, row0); else tma_reduce_add_2d(&tmC, buf, col, row0); }
             else if constexpr (EPI == EPI_CONV_BIAS) tma_store_4d(&tmC, buf, col, cvx, cvy, cvb);   // pixels past the image edge are clipped
             else tma_store_2d(&tmC, buf, col, row0);
             tma_store_commit();

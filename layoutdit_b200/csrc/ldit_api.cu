@@ -8,14 +8,23 @@
 #include <utility>
 #include <vector>
 
+#include <map>
+#include <mutex>
+#include <unordered_map>
+
 #include "../../include/ldit.h"
+#include "attention_v3.cuh"
+#include "gemm.cuh"
+#include "rowwise.cuh"
+// Superseded / experimental kernels (round-1 attention variants, the fused fc1+fc2 kernel): measured slower than the
+// product path, kept for A/B only.  They are compiled in with -DLDIT_EXPERIMENTAL; without it their entry points
+// return LDIT_E_UNSUPPORTED.
+#ifdef LDIT_EXPERIMENTAL
 #include "attention_mma.cuh"
 #include "attention_tc.cuh"
 #include "attention_tc2.cuh"
-#include "attention_v3.cuh"
-#include "gemm.cuh"
 #include "mlp_fused.cuh"
-#include "rowwise.cuh"
+#endif
 
 using namespace ldit;
 
@@ -40,19 +49,60 @@ EncodeTiledFn encode_fn() {
   return fn;
 }
 
+// Encoded tensor maps are a pure function of (pointer, dtype, dims, strides, box, swizzle): the workspaces and weights
+// of a forward keep their addresses from call to call, so the ~1 us driver call per map (3 per GEMM, 140 per forward)
+// is paid once.  Bounded; cleared wholesale when full (a stale entry can only be hit by an identical request, for
+// which it is still correct).
+struct TmapKey {
+  uint64_t w[8];
+  bool operator==(const TmapKey& o) const { return memcmp(w, o.w, sizeof(w)) == 0; }
+};
+struct TmapKeyHash {
+  size_t operator()(const TmapKey& k) const {
+    uint64_t h = 1469598103934665603ull;
+    for (uint64_t v : k.w) { h ^= v; h *= 1099511628211ull; }
+    return static_cast<size_t>(h);
+  }
+};
+std::mutex g_tmap_mu;
+std::unordered_map<TmapKey, CUtensorMap, TmapKeyHash> g_tmap_cache;
+
+int encode_cached(CUtensorMap* tm, CUtensorMapDataType dt, uint32_t rank, const void* ptr, const cuuint64_t* dims,
+                  const cuuint64_t* strides, const cuuint32_t* box, CUtensorMapSwizzle swz) {
+  TmapKey key{};
+  key.w[0] = reinterpret_cast<uint64_t>(ptr);
+  key.w[1] = (static_cast<uint64_t>(dt) << 40) | (static_cast<uint64_t>(rank) << 32) | static_cast<uint64_t>(swz);
+  for (uint32_t i = 0; i < rank; ++i) {
+    key.w[2] = key.w[2] * 0x9E3779B97F4A7C15ull + dims[i];
+    key.w[3] = key.w[3] * 0x9E3779B97F4A7C15ull + (i + 1 < rank ? strides[i] : 0);
+    key.w[4] = key.w[4] * 1000003ull + box[i];
+    key.w[5 + (i % 3)] ^= dims[i] << (13 * (i / 3)) ^ (static_cast<uint64_t>(box[i]) << 40);
+  }
+  {
+    std::lock_guard<std::mutex> lk(g_tmap_mu);
+    auto it = g_tmap_cache.find(key);
+    if (it != g_tmap_cache.end()) { *tm = it->second; return 0; }
+  }
+  EncodeTiledFn fn = encode_fn();
+  if (!fn) return LDIT_E_NO_DRIVER;
+  cuuint32_t estr[5] = {1, 1, 1, 1, 1};
+  CUresult r = fn(tm, dt, rank, const_cast<void*>(ptr), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, swz,
+                  CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) return 10000 + static_cast<int>(r);
+  std::lock_guard<std::mutex> lk(g_tmap_mu);
+  if (g_tmap_cache.size() >= 8192) g_tmap_cache.clear();
+  g_tmap_cache.emplace(key, *tm);
+  return 0;
+}
+
 // 2-D row-major tensor [rows, cols], box [box_rows, box_cols], out-of-bounds elements read as
 // zero (loads) / are clipped (stores).
 int make_tmap_2d(CUtensorMap* tm, const void* ptr, CUtensorMapDataType dt, int esize, uint64_t rows, uint64_t cols,
                  uint64_t pitch_elems, uint32_t box_rows, uint32_t box_cols, CUtensorMapSwizzle swz) {
-  EncodeTiledFn fn = encode_fn();
-  if (!fn) return LDIT_E_NO_DRIVER;
   cuuint64_t dims[2] = {cols, rows};
   cuuint64_t strides[1] = {pitch_elems * esize};
   cuuint32_t box[2] = {box_cols, box_rows};
-  cuuint32_t estr[2] = {1, 1};
-  CUresult r = fn(tm, dt, 2, const_cast<void*>(ptr), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, swz,
-                  CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
-  return r == CUDA_SUCCESS ? 0 : 10000 + static_cast<int>(r);
+  return encode_cached(tm, dt, 2, ptr, dims, strides, box, swz);
 }
 
 // bf16 GEMM operand: box [box_rows, 64 cols] = 128-byte rows, 128-byte swizzle
@@ -67,43 +117,70 @@ int make_tmap_rows_3d(CUtensorMap* tm, const void* ptr, uint64_t B, uint64_t N, 
   return make_tmap_qkv_3d(tm, ptr, B, N, cols, box_rows);
 }
 int make_tmap_qkv_3d(CUtensorMap* tm, const void* ptr, uint64_t B, uint64_t N, uint64_t cols, uint32_t box_rows) {
-  EncodeTiledFn fn = encode_fn();
-  if (!fn) return LDIT_E_NO_DRIVER;
   cuuint64_t dims[3] = {cols, N, B};
   cuuint64_t strides[2] = {cols * 2, N * cols * 2};
   cuuint32_t box[3] = {64, box_rows, 1};
-  cuuint32_t estr[3] = {1, 1, 1};
-  CUresult r = fn(tm, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 3, const_cast<void*>(ptr), dims, strides, box, estr,
-                  CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
-                  CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
-  return r == CUDA_SUCCESS ? 0 : 10000 + static_cast<int>(r);
+  return encode_cached(tm, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 3, ptr, dims, strides, box, CU_TENSOR_MAP_SWIZZLE_128B);
 }
 
 // channels-last image [B, H, W, C] bf16 as a 4-D tensor (C fastest): box [1, box_h, box_w, box_c]
 int make_tmap_nhwc_4d(CUtensorMap* tm, const void* ptr, uint64_t B, uint64_t H, uint64_t W, uint64_t C, uint32_t box_c,
                       uint32_t box_w, uint32_t box_h, CUtensorMapSwizzle swz) {
-  EncodeTiledFn fn = encode_fn();
-  if (!fn) return LDIT_E_NO_DRIVER;
   cuuint64_t dims[4] = {C, W, H, B};
   cuuint64_t strides[3] = {C * 2, W * C * 2, H * W * C * 2};
   cuuint32_t box[4] = {box_c, box_w, box_h, 1};
-  cuuint32_t estr[4] = {1, 1, 1, 1};
-  CUresult r = fn(tm, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, const_cast<void*>(ptr), dims, strides, box, estr,
-                  CU_TENSOR_MAP_INTERLEAVE_NONE, swz, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
-  return r == CUDA_SUCCESS ? 0 : 10000 + static_cast<int>(r);
+  return encode_cached(tm, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, ptr, dims, strides, box, swz);
 }
 
-long long* g_gemm_tl = nullptr;   // experiments only: device buffer for the GEMM timeline
-long long* g_attn_dbg = nullptr;  // experiments only: device buffer for the attention timeline
-std::atomic<int> g_attn_impl{-1};  // 0 = persistent ping-pong tcgen05 (default), 1 = mma.sync, 2 = one-tile-per-CTA tcgen05
+#ifdef LDIT_DEBUG_HOOKS
+long long* g_gemm_tl = nullptr;   // diagnosis builds only: device buffer for the GEMM timeline
+#endif
+long long* g_attn_dbg = nullptr;  // -DLDIT_A3_TIMELINE builds only: device buffer for the attention timeline
+std::atomic<int> g_attn_impl{-1};  // 0 = attention_v3 (default); 1, 2, 4 = the superseded variants (-DLDIT_EXPERIMENTAL)
+
+// Per-device host state (function attributes, SM count and the persisting-L2 limit are per device / context; the
+// library may be driven for several devices from one process).
+struct DeviceState {
+  int sms = 0;
+  size_t persist_limit = 0;
+  std::map<const void*, size_t> smem_attr;   // kernel -> largest dynamic smem size set so far
+};
+std::mutex g_dev_mu;
+std::map<int, DeviceState> g_dev;
+
+DeviceState& dev_state_locked(int* dev_out = nullptr) {   // caller holds g_dev_mu
+  int dev = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess) { (void)cudaGetLastError(); dev = 0; }
+  if (dev_out) *dev_out = dev;
+  DeviceState& d = g_dev[dev];
+  if (d.sms == 0) {
+    int n = 148;
+    if (cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess) { (void)cudaGetLastError(); n = 148; }
+    d.sms = n > 0 ? n : 148;
+  }
+  return d;
+}
 
 int num_sms() {
-  static int sms = [] {
-    int dev = 0, n = 148;
-    if (cudaGetDevice(&dev) == cudaSuccess) cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev);
-    return n > 0 ? n : 148;
-  }();
-  return sms;
+  std::lock_guard<std::mutex> lk(g_dev_mu);
+  return dev_state_locked().sms;
+}
+
+// cudaFuncAttributeMaxDynamicSharedMemorySize (and, optionally, the largest shared-memory carve-out) for `kernel` on the
+// current device, once per (device, kernel, size growth)
+template <typename K>
+cudaError_t ensure_smem(K kernel, size_t bytes, bool max_carveout = false) {
+  std::lock_guard<std::mutex> lk(g_dev_mu);
+  DeviceState& d = dev_state_locked();
+  size_t& have = d.smem_attr[reinterpret_cast<const void*>(kernel)];
+  if (bytes <= have) return cudaSuccess;
+  cudaError_t e = cudaSuccess;
+  if (bytes > 48 * 1024) e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(bytes));
+  if (e == cudaSuccess && max_carveout)
+    e = cudaFuncSetAttribute(kernel, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
+  if (e != cudaSuccess) { (void)cudaGetLastError(); return e; }
+  have = bytes;
+  return cudaSuccess;
 }
 
 std::atomic<int> g_pdl{-1};  // programmatic dependent launch: -1 = read LDIT_PDL once; 0 off; 1 on (default)
@@ -117,12 +194,14 @@ bool pdl_enabled() {
   return v != 0;
 }
 
-// Optional L2 persistence window (ldit_set_l2_persist): every launch carries an access-policy window over the
-// fp32 residual stream, the one buffer the whole forward keeps coming back to (LayerNorm reads, TMA reduce-adds,
-// taps) while 58-77 MB activations stream through the same L2 between two visits.
-void* g_persist_ptr = nullptr;
-size_t g_persist_bytes = 0;
-float g_persist_ratio = 1.0f;   // fraction of the window that is given the persisting property (set-aside / window when the window is larger)
+// Optional L2 persistence window (ldit_set_l2_window): every launch ON THAT STREAM carries an access-policy window
+// over the fp32 residual stream, the one buffer the whole forward keeps coming back to (LayerNorm reads, TMA
+// reduce-adds, taps) while 58-77 MB activations stream through the same L2 between two visits.  Keyed by stream, so
+// two engines (or two devices) driven from one process do not see each other's window.
+struct L2Window { void* ptr; size_t bytes; float ratio; };
+std::mutex g_win_mu;
+std::map<cudaStream_t, L2Window> g_windows;
+std::atomic<int> g_num_windows{0};
 
 // Every kernel goes through here: cluster dimension + programmatic stream serialization (the
 // kernel may start its prologue while its predecessor in the stream drains; see ptx.cuh).
@@ -135,14 +214,22 @@ cudaError_t launch_kernel(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_
   cfg.stream = st;
   cudaLaunchAttribute attr[3];
   int n = 0;
-  if (g_persist_ptr != nullptr && g_persist_bytes > 0) {
-    attr[n].id = cudaLaunchAttributeAccessPolicyWindow;
-    attr[n].val.accessPolicyWindow.base_ptr = g_persist_ptr;
-    attr[n].val.accessPolicyWindow.num_bytes = g_persist_bytes;
-    attr[n].val.accessPolicyWindow.hitRatio = g_persist_ratio;
-    attr[n].val.accessPolicyWindow.hitProp = cudaAccessPropertyPersisting;
-    attr[n].val.accessPolicyWindow.missProp = cudaAccessPropertyNormal;
-    ++n;
+  if (g_num_windows.load(std::memory_order_relaxed) > 0) {
+    L2Window w{nullptr, 0, 1.0f};
+    {
+      std::lock_guard<std::mutex> lk(g_win_mu);
+      auto it = g_windows.find(st);
+      if (it != g_windows.end()) w = it->second;
+    }
+    if (w.ptr != nullptr && w.bytes > 0) {
+      attr[n].id = cudaLaunchAttributeAccessPolicyWindow;
+      attr[n].val.accessPolicyWindow.base_ptr = w.ptr;
+      attr[n].val.accessPolicyWindow.num_bytes = w.bytes;
+      attr[n].val.accessPolicyWindow.hitRatio = w.ratio;
+      attr[n].val.accessPolicyWindow.hitProp = cudaAccessPropertyPersisting;
+      attr[n].val.accessPolicyWindow.missProp = cudaAccessPropertyNormal;
+      ++n;
+    }
   }
   if (cluster > 1) {
     attr[n].id = cudaLaunchAttributeClusterDimension;
@@ -186,6 +273,11 @@ int gemm_ctas() {
 
 // Tile width: minimise (rounds of the persistent schedule) x (tile width); ties go to the
 // wider tile (fewer operand bytes per FLOP).  Widths that divide N are preferred.
+// (Tried and rejected, same-box A/B: computing the ragged last row block -- 64 rows at M = 64 x 197 -- with "swapped"
+// tiles C^T = W . A^T whose MMA N dimension carries the 64 tokens, so that QKV needs 8 schedule rounds instead of 9 and
+// the residual GEMMs 2 x 256 instead of 3 x 192 columns.  A swapped tile streams 256 weight rows for a quarter of the
+// math: at K = 768 it is L2-bandwidth-bound and takes ~0.7 of a regular tile, not 0.25-0.33, so the clusters that take
+// the tails finish last: 2.72 vs 2.62 ms/step.)
 int pick_bn(int M, int N, int ctas) {
   int forced = g_forced_bn.load(std::memory_order_relaxed);
   if (forced < 0) {
@@ -236,16 +328,15 @@ int launch_gemm_t(const void* A, const void* W, GemmArgs g, cudaStream_t st) {
 template <int BN, int EPI, int CTAS>
 int launch_gemm_maps(const CUtensorMap& tmA, const CUtensorMap& tmB, const CUtensorMap& tmC, GemmArgs g, cudaStream_t st) {
   using Cfg = GemmCfg<BN, EPI, CTAS>;
-  static bool attr_set = false;
-  if (!attr_set) {
-    cudaError_t e = cudaFuncSetAttribute(gemm_tcgen05_kernel<BN, EPI, CTAS>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                         Cfg::SMEM_BYTES);
+  {
+    cudaError_t e = ensure_smem(gemm_tcgen05_kernel<BN, EPI, CTAS>, Cfg::SMEM_BYTES);
     if (e != cudaSuccess) return static_cast<int>(e);
-    attr_set = true;
   }
+#ifdef LDIT_DEBUG_HOOKS
   static const int dbg = [] { const char* e = getenv("LDIT_GEMM_DBG"); return e ? atoi(e) : 0; }();
   g.dbg = dbg;
   g.tl = g_gemm_tl;
+#endif
   g.num_n_blocks = (g.N + BN - 1) / BN;
   const int tiles = g.num_m_blocks * g.num_n_blocks;
   const int units = num_sms() / CTAS;
@@ -302,12 +393,8 @@ cudaError_t launch_pages_gather(const void* const* pages, const int* page_hw, __
   const int pitch = (max_page_w + 15) / 16 * 16;
   const size_t smem = static_cast<size_t>(6) * pitch * sizeof(T);
   if (max_page_w > 0 && smem <= 200 * 1024 && B <= 65535) {
-    static size_t max_set = 0;
-    if (smem > max_set && smem > 48 * 1024) {
-      cudaError_t e = cudaFuncSetAttribute(pages_rows_im2col_kernel<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem));
-      if (e != cudaSuccess) return e;
-      max_set = smem;
-    }
+    cudaError_t e = ensure_smem(pages_rows_im2col_kernel<T>, smem);
+    if (e != cudaSuccess) return e;
     return launch_kernel(pages_rows_im2col_kernel<T>, dim3(H, B), dim3(128), smem, st, 1, pp, page_hw, a, H, W, Gh, Gw, ms[0], ms[1],
                          ms[2], ms[3], ms[4], ms[5], pitch);
   }
@@ -317,6 +404,7 @@ cudaError_t launch_pages_gather(const void* const* pages, const int* page_hw, __
                        ms[3], ms[4], ms[5]);
 }
 
+#ifdef LDIT_EXPERIMENTAL
 // ---- fused MLP (mlp_fused.cuh): tile width and per-pair tile lists
 int mlp_bn(int D, int I) {
   if (D % 192 == 0 && I % 192 == 0) return 192;
@@ -381,11 +469,9 @@ int build_mlp_schedule(int M, int D, int I, int bn, int clusters, std::vector<in
 template <int BN>
 int launch_mlp_t(const void* a, const void* W1, void* h, const void* W2, void* x, MlpArgs g, cudaStream_t st) {
   using Cfg = MlpCfg<BN>;
-  static bool attr_set = false;
-  if (!attr_set) {
-    cudaError_t e = cudaFuncSetAttribute(mlp_tcgen05_kernel<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES);
+  {
+    cudaError_t e = ensure_smem(mlp_tcgen05_kernel<BN>, Cfg::SMEM_BYTES);
     if (e != cudaSuccess) return static_cast<int>(e);
-    attr_set = true;
   }
   CUtensorMap tmA1, tmB1, tmC1, tmA2, tmB2, tmC2;
   int rc = make_tmap_bf16_2d(&tmA1, a, g.M, g.D, kBM);
@@ -403,6 +489,8 @@ int launch_mlp_t(const void* a, const void* W1, void* h, const void* W2, void* x
   return static_cast<int>(cudaGetLastError());
 }
 
+#endif  // LDIT_EXPERIMENTAL
+
 }  // namespace
 
 extern "C" {
@@ -418,6 +506,7 @@ const char* ldit_error_string(int code) {
     case LDIT_E_ALIGN: return "pointer or pitch not 16-byte aligned";
     case LDIT_E_DTYPE: return "unknown dtype code";
     case LDIT_E_NO_DRIVER: return "cuTensorMapEncodeTiled unavailable (no CUDA driver)";
+    case LDIT_E_UNSUPPORTED: return "entry point not compiled into this build (experimental kernel: rebuild with -DLDIT_EXPERIMENTAL)";
     default: break;
   }
   if (code >= 10000) {
@@ -429,48 +518,80 @@ const char* ldit_error_string(int code) {
 }
 
 void ldit_set_gemm_tile_n(int bn) { g_forced_bn.store((bn == 128 || bn == 192 || bn == 256) ? bn : 0); }
-void ldit_debug_gemm_timeline(void* device_buffer) { g_gemm_tl = static_cast<long long*>(device_buffer); }
+void ldit_debug_gemm_timeline(void* device_buffer) {
+#ifdef LDIT_DEBUG_HOOKS
+  g_gemm_tl = static_cast<long long*>(device_buffer);
+#else
+  (void)device_buffer;   // the product build carries no timeline hooks
+#endif
+}
 void ldit_debug_attention_timeline(void* device_buffer) { g_attn_dbg = static_cast<long long*>(device_buffer); }
-void ldit_set_attention_impl(int impl) { g_attn_impl.store((impl >= 1 && impl <= 3) ? impl : 0); }
+int ldit_has_experimental(void) {
+#ifdef LDIT_EXPERIMENTAL
+  return 1;
+#else
+  return 0;
+#endif
+}
+void ldit_set_attention_impl(int impl) { g_attn_impl.store((impl == 1 || impl == 2 || impl == 4) ? impl : 0); }
 void ldit_set_pdl(int on) { g_pdl.store(on ? 1 : 0); }
 
-int ldit_set_l2_persist(void* ptr, size_t bytes) { return ldit_set_l2_persist_capped(ptr, bytes, 0); }
-
-int ldit_set_l2_persist_capped(void* ptr, size_t bytes, size_t set_aside_cap) {
-  if (ptr == nullptr || bytes == 0) {
-    g_persist_ptr = nullptr;
-    g_persist_bytes = 0;
-    return LDIT_OK;
-  }
+int ldit_set_l2_window(void* stream, void* ptr, size_t bytes, size_t set_aside_cap) {
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  auto drop = [&] {
+    std::lock_guard<std::mutex> lk(g_win_mu);
+    if (g_windows.erase(st)) g_num_windows.fetch_sub(1);
+  };
+  if (ptr == nullptr || bytes == 0) { drop(); return LDIT_OK; }
   int dev = 0, max_persist = 0, max_window = 0;
   cudaError_t e = cudaGetDevice(&dev);
   if (e == cudaSuccess) e = cudaDeviceGetAttribute(&max_persist, cudaDevAttrMaxPersistingL2CacheSize, dev);
   if (e == cudaSuccess) e = cudaDeviceGetAttribute(&max_window, cudaDevAttrMaxAccessPolicyWindowSize, dev);
   if (e != cudaSuccess || max_persist <= 0 || max_window <= 0) {   // no persisting L2 on this device / partition: window stays off
     (void)cudaGetLastError();
-    g_persist_ptr = nullptr;
-    g_persist_bytes = 0;
+    drop();
     return e != cudaSuccess ? static_cast<int>(e) : LDIT_OK;
   }
   size_t want = bytes < static_cast<size_t>(max_persist) ? bytes : static_cast<size_t>(max_persist);
   if (set_aside_cap > 0 && want > set_aside_cap) want = set_aside_cap;
-  static size_t limit_set = 0;
-  if (want > limit_set) {   // the set-aside is a device-wide limit: only ever grown, and only on request
-    e = cudaDeviceSetLimit(cudaLimitPersistingL2CacheSize, want);
-    if (e != cudaSuccess) {   // e.g. under MPS: leave the window off, report, and let the caller carry on without it
-      (void)cudaGetLastError();
-      g_persist_ptr = nullptr;
-      g_persist_bytes = 0;
-      return static_cast<int>(e);
+  size_t limit = 0;
+  {
+    std::lock_guard<std::mutex> lk(g_dev_mu);
+    DeviceState& d = dev_state_locked();
+    if (want > d.persist_limit) {   // the set-aside is a device-wide limit: only ever grown, and only on request
+      e = cudaDeviceSetLimit(cudaLimitPersistingL2CacheSize, want);
+      if (e != cudaSuccess) {   // e.g. under MPS: leave the window off, report, and let the caller carry on without it
+        (void)cudaGetLastError();
+        limit = static_cast<size_t>(-1);
+      } else {
+        d.persist_limit = want;
+      }
     }
-    limit_set = want;
+    if (limit == 0) limit = d.persist_limit;
   }
-  g_persist_ptr = ptr;
-  g_persist_bytes = bytes < static_cast<size_t>(max_window) ? bytes : static_cast<size_t>(max_window);
+  if (limit == static_cast<size_t>(-1)) { drop(); return static_cast<int>(e); }
+  L2Window w;
+  w.ptr = ptr;
+  w.bytes = bytes < static_cast<size_t>(max_window) ? bytes : static_cast<size_t>(max_window);
   // a window larger than the set-aside would thrash inside it: persist only the fraction that fits
-  const size_t avail = (set_aside_cap > 0 && set_aside_cap < limit_set) ? set_aside_cap : limit_set;
-  g_persist_ratio = g_persist_bytes <= avail ? 1.0f : static_cast<float>(avail) / static_cast<float>(g_persist_bytes);
+  const size_t avail = (set_aside_cap > 0 && set_aside_cap < limit) ? set_aside_cap : limit;
+  w.ratio = w.bytes <= avail ? 1.0f : static_cast<float>(avail) / static_cast<float>(w.bytes);
+  std::lock_guard<std::mutex> lk(g_win_mu);
+  if (g_windows.find(st) == g_windows.end()) g_num_windows.fetch_add(1);
+  g_windows[st] = w;
   return LDIT_OK;
+}
+
+size_t ldit_workspace_bytes(int B, int H, int W, int D, int I) {
+  if (B <= 0 || H < 16 || W < 16 || D <= 0 || I <= 0) return 0;
+  const size_t M = static_cast<size_t>(B) * ((H / 16) * (W / 16) + 1);
+  size_t wide = static_cast<size_t>(3) * D;
+  if (static_cast<size_t>(I) > wide) wide = I;
+  if (wide < 768) wide = 768;
+  // residual stream x (f32 [M, D]) + LayerNorm output / context a (bf16 [M, D]) + wide buffer (bf16 [M, max(3D, I, 768)]:
+  // QKV, MLP hidden, im2col scratch -- disjoint lifetimes); each rounded up to 1 KB so the three can share one allocation
+  auto up = [](size_t v) { return (v + 1023) / 1024 * 1024; };
+  return up(M * D * 4) + up(M * D * 2) + up(M * wide * 2);
 }
 void ldit_set_gemm_cta_pair(int ctas) { g_cta_pair.store(ctas == 1 ? 1 : 2); }
 
@@ -532,6 +653,7 @@ int ldit_gemm_bias_scale_residual(const void* A, const void* W, const void* bias
   return launch_gemm<EPI_SCALE_RESID>(A, W, g, static_cast<cudaStream_t>(stream));
 }
 
+#ifdef LDIT_EXPERIMENTAL
 int ldit_mlp_clusters(void) { return num_sms() / 2; }
 
 int ldit_mlp_schedule(int M, int D, int I, int* host_sched, int capacity) {
@@ -573,6 +695,12 @@ int ldit_mlp_fused(const void* a, const void* W1, const void* b1, void* h, const
   if (bn == 192) return launch_mlp_t<192>(a, W1, h, W2, x, g, st);
   return launch_mlp_t<256>(a, W1, h, W2, x, g, st);
 }
+#else   // !LDIT_EXPERIMENTAL: the fused fc1 + fc2 kernel (measured 14-21 % slower than two launches) is not built
+int ldit_mlp_clusters(void) { return num_sms() / 2; }
+int ldit_mlp_schedule(int, int, int, int*, int) { return LDIT_E_UNSUPPORTED; }
+int ldit_mlp_fused(const void*, const void*, const void*, void*, const void*, const void*, const void*, void*, int, int, int,
+                   const int*, int, int*, void*) { return LDIT_E_UNSUPPORTED; }
+#endif
 
 size_t ldit_patch_embed_scratch_bytes(int B, int H, int W) {
   if (B <= 0 || H < 16 || W < 16) return 0;
@@ -647,17 +775,17 @@ int ldit_attention(const void* qkv, void* ctx, const void* bias_table, int B, in
   if (B <= 0 || heads <= 0 || Gh <= 0 || Gw <= 0 || N != Gh * Gw + 1) return LDIT_E_SHAPE;
   if (!aligned16(qkv) || !aligned16(ctx) || !aligned16(bias_table)) return LDIT_E_ALIGN;
   cudaStream_t st = static_cast<cudaStream_t>(stream);
-  const int D = heads * kAttDh;
+  const int D = heads * 64;
   const int T = (2 * Gh - 1) * (2 * Gw - 1) + 3;
   const float scale_log2e = 0.125f * 1.4426950408889634f;
   int impl = g_attn_impl.load(std::memory_order_relaxed);
   if (impl < 0) {
     const char* e = getenv("LDIT_ATTN_IMPL");
     impl = e ? atoi(e) : 0;
-    if (impl < 1 || impl > 3) impl = 0;
+    if (impl != 1 && impl != 2 && impl != 4) impl = 0;
     g_attn_impl.store(impl);
   }
-  if (impl == 3) {
+  if (impl == 0) {
     AttnV3Args a{};
     a.bias_table = static_cast<const float*>(bias_table);
     a.B = B; a.N = N; a.heads = heads; a.D = D; a.Gh = Gh; a.Gw = Gw; a.T = T;
@@ -679,23 +807,17 @@ int ldit_attention(const void* qkv, void* ctx, const void* bias_table, int B, in
     const int per_sm = smem <= 113 * 1024 ? 2 : 1;   // the kernel is sized to be resident twice per SM
     const int slots = per_sm * num_sms();
     const int grid = a.num_items < slots ? a.num_items : slots;
-    static size_t max_set[2] = {0, 0};
-    const int bi = bias_table ? 1 : 0;
-    if (smem > max_set[bi]) {
-      cudaError_t e = bi ? cudaFuncSetAttribute(attention_v3_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem))
-                         : cudaFuncSetAttribute(attention_v3_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem));
-      if (e != cudaSuccess) return static_cast<int>(e);
-      // two CTAs per SM need a ~200 KB carve-out: ask for the largest one instead of leaving it to the driver's heuristic
-      e = bi ? cudaFuncSetAttribute(attention_v3_kernel<true>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared)
-             : cudaFuncSetAttribute(attention_v3_kernel<false>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
-      if (e != cudaSuccess) return static_cast<int>(e);
-      max_set[bi] = smem;
-    }
-    if (bi) launch_kernel(attention_v3_kernel<true>, dim3(grid), dim3(kA3Threads), smem, st, 1, tmQ, tmKV, tmO, a);
+    // two CTAs per SM need a ~200 KB carve-out: ask for the largest one instead of leaving it to the driver's heuristic
+    cudaError_t e = bias_table ? ensure_smem(attention_v3_kernel<true>, smem, true) : ensure_smem(attention_v3_kernel<false>, smem, true);
+    if (e != cudaSuccess) return static_cast<int>(e);
+    if (bias_table) launch_kernel(attention_v3_kernel<true>, dim3(grid), dim3(kA3Threads), smem, st, 1, tmQ, tmKV, tmO, a);
     else launch_kernel(attention_v3_kernel<false>, dim3(grid), dim3(kA3Threads), smem, st, 1, tmQ, tmKV, tmO, a);
     return check_launch();
   }
-  if (impl == 0) {
+#ifndef LDIT_EXPERIMENTAL
+  return LDIT_E_UNSUPPORTED;   // impl 1 / 2 / 4: the superseded round-1 kernels, only in -DLDIT_EXPERIMENTAL builds
+#else
+  if (impl == 4) {
     AttnP2Args a{};
     a.ctx = static_cast<__nv_bfloat16*>(ctx);
     a.bias_table = static_cast<const float*>(bias_table);
@@ -718,17 +840,12 @@ int ldit_attention(const void* qkv, void* ctx, const void* bias_table, int B, in
     if (smem > 227 * 1024) return LDIT_E_SHAPE;
     const int grid = a.num_items < num_sms() ? a.num_items : num_sms();
     const int nch = a.kv_tile / 16;
-    static size_t max_set[2][7] = {};
     const int bi = bias_table ? 1 : 0;
     cudaError_t e = cudaSuccess;
 #define LDIT_ATTN_CASE(NCH)                                                                                             \
   case NCH:                                                                                                             \
-    if (smem > max_set[bi][NCH]) {                                                                                      \
-      e = bi ? cudaFuncSetAttribute(attention_pp_kernel<true, NCH>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)  \
-             : cudaFuncSetAttribute(attention_pp_kernel<false, NCH>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); \
-      if (e != cudaSuccess) return static_cast<int>(e);                                                                 \
-      max_set[bi][NCH] = smem;                                                                                          \
-    }                                                                                                                   \
+    e = bi ? ensure_smem(attention_pp_kernel<true, NCH>, smem) : ensure_smem(attention_pp_kernel<false, NCH>, smem);     \
+    if (e != cudaSuccess) return static_cast<int>(e);                                                                   \
     if (bi) launch_kernel(attention_pp_kernel<true, NCH>, dim3(grid), dim3(kA2Threads), smem, st, 1, tmQ, tmKV, tmO, a);                               \
     else launch_kernel(attention_pp_kernel<false, NCH>, dim3(grid), dim3(kA2Threads), smem, st, 1, tmQ, tmKV, tmO, a);                                 \
     break;
@@ -757,13 +874,9 @@ int ldit_attention(const void* qkv, void* ctx, const void* bias_table, int B, in
     if (bias_table) smem += (static_cast<size_t>(T) + N) * 4;
     if (smem > 110 * 1024) return LDIT_E_SHAPE;
     dim3 grid((N + kAtcQ - 1) / kAtcQ, heads, B);
-    static size_t max_set[2] = {0, 0};
-    const int bi = bias_table ? 1 : 0;
-    if (smem > max_set[bi]) {
-      cudaError_t e = bias_table ? cudaFuncSetAttribute(attention_tc_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem))
-                                 : cudaFuncSetAttribute(attention_tc_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem));
+    {
+      cudaError_t e = bias_table ? ensure_smem(attention_tc_kernel<true>, smem) : ensure_smem(attention_tc_kernel<false>, smem);
       if (e != cudaSuccess) return static_cast<int>(e);
-      max_set[bi] = smem;
     }
     if (bias_table) launch_kernel(attention_tc_kernel<true>, dim3(grid), dim3(kAtcThreads), smem, st, 1, tmQ, tmKV, a);
     else launch_kernel(attention_tc_kernel<false>, dim3(grid), dim3(kAtcThreads), smem, st, 1, tmQ, tmKV, a);
@@ -781,17 +894,16 @@ int ldit_attention(const void* qkv, void* ctx, const void* bias_table, int B, in
   if (bias_table) {
     smem += static_cast<size_t>(a.T) * 4 + static_cast<size_t>(N) * 4;
     if (smem > 227 * 1024) return LDIT_E_SHAPE;
-    static size_t max_set = 0;
-    if (smem > max_set) {
-      cudaError_t e = cudaFuncSetAttribute(attention_mma_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem));
+    {
+      cudaError_t e = ensure_smem(attention_mma_kernel<true>, smem);
       if (e != cudaSuccess) return static_cast<int>(e);
-      max_set = smem;
     }
     launch_kernel(attention_mma_kernel<true>, dim3(grid), dim3(128), smem, st, 1, a);
   } else {
     launch_kernel(attention_mma_kernel<false>, dim3(grid), dim3(128), smem, st, 1, a);
   }
   return check_launch();
+#endif
 }
 
 int ldit_resample_taps(const void* x, void* out, int B, int Gh, int Gw, int D, float scale, void* stream) {

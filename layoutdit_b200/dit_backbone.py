@@ -85,11 +85,11 @@ class DiTBackbone(nn.Module):
         with torch.no_grad():
             return self._get_engine().forward_host(pages, result_host, result_key)
 
-    def forward_pages(self, pages, size=(224, 224), mean=(0.5, 0.5, 0.5), std=(0.5, 0.5, 0.5)):
+    def forward_pages(self, pages, size=(224, 224), mean=(0.5, 0.5, 0.5), std=(0.5, 0.5, 0.5), fixed_size=None):
         """Raw pages (list of ``[3, H_i, W_i]`` float CUDA tensors in [0, 1]) -> taps, with the detector's input
         transform (R:model.py:44-56) fused into the patch gather; see ``Engine.forward_pages``."""
         with torch.no_grad():
-            return self._get_engine().forward_pages(pages, size, mean, std, "taps")
+            return self._get_engine().forward_pages(pages, size, mean, std, "taps", fixed_size)
 
     def forward(self, x: torch.Tensor) -> "OrderedDict[str, torch.Tensor]":
         if self.training and torch.is_grad_enabled() and any(p.requires_grad for p in self.dit.parameters()):

@@ -71,11 +71,11 @@ class DiTWithFPN(nn.Module):
             eng._pack_key = None
         return eng
 
-    def forward_pages(self, pages, size=(224, 224), mean=(0.5, 0.5, 0.5), std=(0.5, 0.5, 0.5)):
+    def forward_pages(self, pages, size=(224, 224), mean=(0.5, 0.5, 0.5), std=(0.5, 0.5, 0.5), fixed_size=None):
         """Raw pages -> FPN maps: what ``FasterRCNN.forward`` computes up to its RPN (transform + backbone,
         torchvision generalized_rcnn.py), with the transform fused into the patch gather."""
         with torch.no_grad():
-            return self._engine().forward_pages(pages, size, mean, std, "fpn")
+            return self._engine().forward_pages(pages, size, mean, std, "fpn", fixed_size)
 
     def forward(self, x: torch.Tensor) -> "OrderedDict[str, torch.Tensor]":
         if self.training and torch.is_grad_enabled() and any(p.requires_grad for p in self.parameters()):

@@ -9,6 +9,7 @@ torch only casts, concatenates and transposes parameters into the kernels' layou
 """
 from __future__ import annotations
 
+import contextlib
 import dataclasses
 import math
 import os
@@ -109,11 +110,14 @@ class Engine:
         self.lib = _lib.load()
         self._pack_key = None
         self._layers: list[_LayerPack] = []
-        self._geoms: dict = {}
+        self._geoms: "OrderedDict" = OrderedDict()   # LRU over (B, H, W[, slot, head]); see _remember()
+        self._max_geoms = int(os.environ.get("LDIT_MAX_GEOMETRIES", "8"))
+        self.device = None
         self.tap_idx = tap_layer_indices(cfg.num_hidden_layers)
-        # fc1 + fc2 of a layer as one persistent kernel with a balanced tile schedule (ldit_mlp_fused)
-        self.mlp_fused = os.environ.get("LDIT_MLP_FUSED", "0") != "0"
-        # L2 access-policy window (persisting) over the fp32 residual stream on every launch (ldit_set_l2_persist)
+        # fc1 + fc2 of a layer as one persistent kernel with a balanced tile schedule (ldit_mlp_fused): experimental,
+        # measured slower; needs a library built with -DLDIT_EXPERIMENTAL
+        self.mlp_fused = os.environ.get("LDIT_MLP_FUSED", "0") != "0" and bool(self.lib.ldit_has_experimental())
+        # L2 access-policy window (persisting) over the fp32 residual stream on every launch (ldit_set_l2_window)
         # On by default (LDIT_L2_PERSIST=0 switches it off): measured -3 % step time at base224.  Process-level side
         # effect: grows the device's persisting-L2 set-aside to the window size (at most the device maximum, 79 MB).
         self.l2_persist = os.environ.get("LDIT_L2_PERSIST", "1") != "0"
@@ -122,10 +126,15 @@ class Engine:
 
     # ------------------------------------------------------------------ weight packing
     def _weights_key(self):
-        ps = list(self.params.parameters())
-        if self.fpn_params is not None:
-            ps += list(self.fpn_params.parameters())
-        return tuple((p.data_ptr(), p._version) for p in ps)
+        """Changes whenever a parameter is written in place (``_version``), replaced (``data_ptr``) or moved.  The
+        parameter list itself is cached: walking the module tree costs more than the 211 attribute reads."""
+        ps = self.__dict__.get("_param_list")
+        if ps is None or self.__dict__.get("_param_list_fpn") is not self.fpn_params:
+            ps = list(self.params.parameters())
+            if self.fpn_params is not None:
+                ps += list(self.fpn_params.parameters())
+            self._param_list, self._param_list_fpn = ps, self.fpn_params
+        return tuple(p._version for p in ps), tuple(p.data_ptr() for p in ps)
 
     def refresh_weights(self, force: bool = False):
         key = self._weights_key()
@@ -182,8 +191,9 @@ class Engine:
         src = src.contiguous()
         C = src.shape[-1]
         dst = torch.empty(oh * ow, C, device=self.device, dtype=torch.float32)
-        _lib.check(self.lib.ldit_resize_rows(src.data_ptr(), dst.data_ptr(), _ptr(add), h, w, oh, ow, C, int(bicubic),
-                                             torch.cuda.current_stream(self.device).cuda_stream), "ldit_resize_rows")
+        with self._on_device():
+            _lib.check(self.lib.ldit_resize_rows(src.data_ptr(), dst.data_ptr(), _ptr(add), h, w, oh, ow, C, int(bicubic),
+                                                 torch.cuda.current_stream(self.device).cuda_stream), "ldit_resize_rows")
         return dst
 
     def _pos_rows(self, Gh, Gw, H, W):
@@ -214,12 +224,12 @@ class Engine:
         key = (B, H, W) if (slot == 0 and head == "taps") else (B, H, W, slot, head)
         geo = self._geoms.get(key)
         if geo is not None:
+            self._geoms.move_to_end(key)
             return geo
         if slot != 0:
             base = self._geometry(B, H, W, 0, head)
             geo = dataclasses.replace(base, graph=None, graph_in=None, graph_out=None, launches=0, extra=dict(base.extra))
-            self._geoms[key] = geo
-            return geo
+            return self._remember(key, geo)
         cfg, dev = self.cfg, self.device
         D, I = cfg.hidden_size, cfg.intermediate_size
         Gh, Gw = H // 16, W // 16
@@ -240,11 +250,14 @@ class Engine:
         wide = max(3 * D, I, 768)  # 768 = im2col row (3*16*16): the patch-embed scratch lives here too
         # residual stream and LayerNorm-output / context buffer share one allocation, x first: the L2 persistence window
         # (ldit_set_l2_persist) is a single address range
-        xa = torch.empty(M * D * 6, device=dev, dtype=torch.uint8)
+        ws = torch.empty(int(self.lib.ldit_workspace_bytes(B, H, W, D, I)), device=dev, dtype=torch.uint8)
+        up = lambda v: (v + 1023) // 1024 * 1024
+        o_a = M * D * 4                      # a starts right behind x (not rounded: the window must be one range)
+        o_big = up(M * D * 4) + up(M * D * 2)
         geo = _Geometry(B=B, H=H, W=W, Gh=Gh, Gw=Gw, N=N, M=M,
-                        x=xa[: M * D * 4].view(torch.float32).view(M, D),
-                        a=xa[M * D * 4:].view(torch.bfloat16).view(M, D),
-                        big=torch.empty(M * wide, device=dev, dtype=torch.bfloat16),
+                        x=ws[: M * D * 4].view(torch.float32).view(M, D),
+                        a=ws[o_a: o_a + M * D * 2].view(torch.bfloat16).view(M, D),
+                        big=ws[o_big: o_big + M * wide * 2].view(torch.bfloat16),
                         pos_bias=pos_bias, cls_pos=cls_pos, bias_tables=tables, head=head)
         if self.mlp_fused:
             stride = int(self.lib.ldit_mlp_schedule(M, D, I, None, 0))
@@ -259,7 +272,15 @@ class Engine:
             geo.extra["tok"] = torch.empty(B * P, D, **bf)                        # tap tokens without CLS, bf16
             geo.extra["lat"] = [torch.empty(B * P, C, **bf) for _ in TAP_SCALES]   # laterals on the token grid
             geo.extra["inner"] = [torch.empty(B, *self._tap_hw(geo, s), C, **bf) for s in TAP_SCALES]
+        return self._remember(key, geo)
+
+    def _remember(self, key, geo):
+        """Bounded cache: every entry owns workspaces (M*D*6 + M*max(3D, I)*2 bytes), resized tables and possibly a
+        captured graph with static inputs / outputs, so a stream of distinct page or batch sizes must not grow GPU
+        memory without limit.  Least-recently-used geometries beyond LDIT_MAX_GEOMETRIES (default 8) are dropped."""
         self._geoms[key] = geo
+        while len(self._geoms) > max(1, self._max_geoms):
+            self._geoms.popitem(last=False)
         return geo
 
     # -------------------------------------------------------------------- launch sequence
@@ -370,18 +391,26 @@ class Engine:
 
     def _enqueue(self, geo: _Geometry, x: torch.Tensor, outs, stream: int, limit: int | None = None):
         """Enqueue the whole forward on ``stream``.  Returns the number of kernels launched."""
-        n0 = self.lib.ldit_launch_count()
-        persist = self._persist_bytes(geo)
-        if persist:   # keep the residual stream (and the LayerNorm / context buffer behind it) resident in L2
-            if self.lib.ldit_set_l2_persist_capped(geo.x.data_ptr(), persist, self._persist_cap) != 0:
-                self.l2_persist, persist = False, 0     # an optimisation the device refused (MPS, MIG slice ...): run without it
-        try:
-            for name, fn, args in self._plan(geo, x, outs, stream)[:limit]:
-                _lib.check(fn(*args), name)
-        finally:
-            if persist:
-                self.lib.ldit_set_l2_persist(None, 0)
-        return int(self.lib.ldit_launch_count() - n0)
+        with self._on_device():   # function attributes, SM count and the L2 limit are those of the CURRENT device
+            n0 = self.lib.ldit_launch_count()
+            persist = self._persist_bytes(geo)
+            if persist:   # keep the residual stream (and the LayerNorm / context buffer behind it) resident in L2
+                if self.lib.ldit_set_l2_window(stream, geo.x.data_ptr(), persist, self._persist_cap) != 0:
+                    self.l2_persist, persist = False, 0     # an optimisation the device refused (MPS, MIG slice ...): run without it
+            try:
+                for name, fn, args in self._plan(geo, x, outs, stream)[:limit]:
+                    _lib.check(fn(*args), name)
+            finally:
+                if persist:
+                    self.lib.ldit_set_l2_window(stream, None, 0, 0)
+            return int(self.lib.ldit_launch_count() - n0)
+
+    def _on_device(self):
+        """Make the engine's device current for the duration of a launch sequence (a model on cuda:1 driven from a
+        process whose current device is cuda:0 would otherwise launch into the wrong context)."""
+        if self.device is None or torch.cuda.current_device() == self.device.index:
+            return contextlib.nullcontext()
+        return torch.cuda.device(self.device)
 
     @staticmethod
     def _as_feats(outs):
@@ -416,17 +445,27 @@ class Engine:
         geo.launches = self._enqueue(geo, x, outs, torch.cuda.current_stream(self.device).cuda_stream)
         return self._as_feats(outs)
 
-    def forward_pages(self, pages, size=(224, 224), mean=(0.5, 0.5, 0.5), std=(0.5, 0.5, 0.5), head: str = "taps"):
+    def forward_pages(self, pages, size=(224, 224), mean=(0.5, 0.5, 0.5), std=(0.5, 0.5, 0.5), head: str = "taps",
+                      fixed_size=None):
         """Raw pages -> features: ``GeneralizedRCNNTransform`` as the detector configures it
         (R:model.py:44-56: normalize, bilinear resize to ``fixed_size``, batch) fused into the patch gather,
         then the backbone (and FPN for ``head="fpn"``).  ``pages``: a list of ``[3, H_i, W_i]`` CUDA tensors of
-        any sizes (one floating dtype), or one ``[B, 3, Hs, Ws]`` tensor."""
+        any sizes (one floating dtype), or one ``[B, 3, Hs, Ws]`` tensor.
+
+        ``size`` is **(height, width)**, the order ``F.interpolate(size=...)`` takes.  torchvision's ``fixed_size`` is
+        **(width, height)** (``_resize_image_and_masks`` resizes to ``[fixed_size[1], fixed_size[0]]``): pass that
+        tuple unchanged as ``fixed_size=`` instead and it is swapped here.  Both sides must be multiples of 32:
+        torchvision's ``batch_images`` zero-pads the batch to ``size_divisible=32``, which this fused path does not
+        emulate (the reference's 224 x 224 needs no padding)."""
+        if fixed_size is not None:
+            size = (int(fixed_size[1]), int(fixed_size[0]))
         if isinstance(pages, torch.Tensor):
             if pages.dim() != 4:
                 raise ValueError(f"expected [B, 3, H, W] pages or a list of [3, H, W] pages, got {tuple(pages.shape)}")
             pages = list(pages.contiguous().unbind(0))
         if not pages:
             raise ValueError("empty page list")
+        self.refresh_weights()   # also tells which device the model is on
         keep = []
         for p in pages:
             if p.dim() != 3 or p.shape[0] != self.cfg.num_channels:
@@ -435,12 +474,16 @@ class Engine:
                 raise TypeError(f"Expected input images to be of floating type (in range [0, 1]), but found type {p.dtype} instead")
             if not p.is_cuda:
                 raise _lib.LditError("DiTBackbone.forward_pages needs CUDA tensors (there is no CPU path)")
+            if self.device is not None and p.device != self.device:
+                raise _lib.LditError(f"page on {p.device}, model on {self.device}: the gather kernel reads the pages through "
+                                     "raw device pointers and cannot cross devices")
             keep.append(p if p.dtype in _DTYPE_CODE else p.float())
         dt = keep[0].dtype
         keep = [p.to(dt).contiguous() for p in keep]
         H, W = int(size[0]), int(size[1])
-        if H % 16 or W % 16 or H < 16 or W < 16:
-            raise ValueError("the fixed size must be a multiple of the 16x16 patch")
+        if H % 32 or W % 32 or H < 32 or W < 32:
+            raise ValueError("the fixed size must be a multiple of 32 in both directions (torchvision pads batches to "
+                             "size_divisible=32; that padding is not emulated)")
         self.refresh_weights()
         B = len(keep)
         host = torch.tensor([p.data_ptr() for p in keep], dtype=torch.int64)
@@ -454,9 +497,7 @@ class Engine:
 
     def _geometry_ragged(self, x, H0, W0, head="taps"):
         # the position-table rule looks at the ORIGINAL height/width (HF:135), the conv at the cropped ones
-        geo = self._geometry(x.shape[0], H0, W0, 0, head)
-        geo.H, geo.W = x.shape[2], x.shape[3]
-        return geo
+        return dataclasses.replace(self._geometry(x.shape[0], H0, W0, 0, head), H=x.shape[2], W=x.shape[3])
 
     # ----------------------------------------------------------------------- CUDA graphs
     def forward_graphed(self, x: torch.Tensor, slot: int = 0, head: str = "taps"):

@@ -143,6 +143,9 @@ def test_fused_mlp_schedule_is_a_balanced_partition():
     lib = _lib.load()
     C = lib.ldit_mlp_clusters()
     assert C >= 1
+    if not lib.ldit_has_experimental():
+        assert lib.ldit_mlp_schedule(12608, 768, 3072, None, 0) == -6      # LDIT_E_UNSUPPORTED: not in the product build
+        pytest.skip("ldit_mlp_* are only in -DLDIT_EXPERIMENTAL builds")
     for (M, D, I) in [(12608, 768, 3072), (32800, 768, 3072), (12608, 1024, 4096), (197, 768, 3072), (1, 768, 3072)]:
         stride = lib.ldit_mlp_schedule(M, D, I, None, 0)
         assert stride > 0
@@ -197,8 +200,16 @@ def test_argument_validation_of_the_widened_entry_points_without_gpu():
     assert lib.ldit_resize_rows(None, p16, None, 14, 14, 20, 20, 768, 1, None) == -1
     assert lib.ldit_resize_rows(p16, p16, None, 14, 0, 20, 20, 768, 1, None) == -2
     # fused MLP: schedule and counters are required; widths must be multiples of 192 or of 256
-    assert lib.ldit_mlp_fused(p16, p16, p16, p16, p16, p16, None, p16, 128, 768, 3072, None, 4, p16, None) == -1
-    assert lib.ldit_mlp_fused(p16, p16, p16, p16, p16, p16, None, p16, 128, 128, 320, p16, 4, p16, None) == -2
-    assert lib.ldit_mlp_fused(p16, p16, p16, p16 + 4, p16, p16, None, p16, 128, 768, 3072, p16, 4, p16, None) == -3
-    # L2 window: clearing never fails, also without a device
-    assert lib.ldit_set_l2_persist(None, 0) == 0
+    if lib.ldit_has_experimental():
+        assert lib.ldit_mlp_fused(p16, p16, p16, p16, p16, p16, None, p16, 128, 768, 3072, None, 4, p16, None) == -1
+        assert lib.ldit_mlp_fused(p16, p16, p16, p16, p16, p16, None, p16, 128, 128, 320, p16, 4, p16, None) == -2
+        assert lib.ldit_mlp_fused(p16, p16, p16, p16 + 4, p16, p16, None, p16, 128, 768, 3072, p16, 4, p16, None) == -3
+    else:
+        assert lib.ldit_mlp_fused(p16, p16, p16, p16, p16, p16, None, p16, 128, 768, 3072, p16, 4, p16, None) == -6
+    # L2 window: removing a stream's window never fails, also without a device
+    assert lib.ldit_set_l2_window(None, None, 0, 0) == 0
+    # workspace size: x f32 + a bf16 + wide bf16 buffer, each rounded up to 1 KB
+    M = 64 * 197
+    up = lambda v: (v + 1023) // 1024 * 1024
+    assert lib.ldit_workspace_bytes(64, 224, 224, 768, 3072) == up(M * 768 * 4) + up(M * 768 * 2) + up(M * 3072 * 2)
+    assert lib.ldit_workspace_bytes(0, 224, 224, 768, 3072) == 0

@@ -9,7 +9,7 @@ lib = _lib.load()
 B, heads, G = (64, 12, 14) if len(sys.argv) < 2 or sys.argv[1] == "224" else (32, 12, 32)
 N, D = G * G + 1, heads * 64
 st = torch.cuda.current_stream().cuda_stream
-lib.ldit_set_attention_impl(3)
+lib.ldit_set_attention_impl(0)
 qkv = torch.randn(B * N, 3 * D, device="cuda").to(torch.bfloat16)
 ctx = torch.empty(B * N, D, device="cuda", dtype=torch.bfloat16)
 for _ in range(3): lib.ldit_attention(qkv.data_ptr(), ctx.data_ptr(), None, B, N, heads, G, G, st)

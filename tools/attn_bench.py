@@ -10,7 +10,7 @@ for name, B, heads, G in [("base224 b64", 64, 12, 14), ("base512 b32", 32, 12, 3
     N, D = G * G + 1, heads * 64
     qkv = (torch.randn(B * N, 3 * D, device="cuda")).to(torch.bfloat16)
     ctx = torch.empty(B * N, D, device="cuda", dtype=torch.bfloat16)
-    for impl in (3, 0):
+    for impl in ((0, 4) if lib.ldit_has_experimental() else (0,)):
         lib.ldit_set_attention_impl(impl)
         for _ in range(3):
             _lib.check(lib.ldit_attention(qkv.data_ptr(), ctx.data_ptr(), None, B, N, heads, G, G, st), "attn")
