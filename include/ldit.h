@@ -134,9 +134,16 @@ int ldit_fpn_merge(const void* lat, const void* top, void* out, int B, int Gh, i
 int ldit_conv3x3_bias(const void* in, const void* w, const void* bias, void* out, int B, int H, int W, int Cin, int Cout,
                       void* stream);
 
+/* Same convolution with an fp32 output map (out f32 [B, H, W, Cout]): what the detection heads behind the FPN expect when
+ * the detector runs in fp32 (torchvision's RPN / RoI heads hold fp32 weights, R:src/layoutdit/modeling/model.py:44-56);
+ * the cast is the epilogue's store format, not an extra pass. */
+int ldit_conv3x3_bias_f32(const void* in, const void* w, const void* bias, void* out, int B, int H, int W, int Cin, int Cout,
+                          void* stream);
+
 /* LastLevelMaxPool (TV:231-249): max_pool2d(kernel 1, stride 2) = out[b, y, x, :] = in[b, 2y, 2x, :];
- * out is [B, ceil(H/2), ceil(W/2), C]. */
+ * out is [B, ceil(H/2), ceil(W/2), C].  bf16 maps; ldit_subsample2_f32 for fp32 maps. */
 int ldit_subsample2(const void* in, void* out, int B, int H, int W, int C, void* stream);
+int ldit_subsample2_f32(const void* in, void* out, int B, int H, int W, int C, void* stream);
 
 /* Weight preparation, once per (weights, H, W): resize a table of rows, src f32 [h*w, C] -> dst f32 [oh*ow, C]
  * (+ add f32 [C] if not NULL), with ATen's rules for F.interpolate(size=(oh, ow), align_corners=False):

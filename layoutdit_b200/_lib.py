@@ -28,7 +28,9 @@ SIGNATURES = {
     "ldit_resample_taps": (_i, [_vp, _vp, _i, _i, _i, _i, _f, _vp]),
     "ldit_fpn_merge": (_i, [_vp, _vp, _vp, _i, _i, _i, _i, _f, _i, _i, _vp]),
     "ldit_conv3x3_bias": (_i, [_vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _vp]),
+    "ldit_conv3x3_bias_f32": (_i, [_vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _vp]),
     "ldit_subsample2": (_i, [_vp, _vp, _i, _i, _i, _i, _vp]),
+    "ldit_subsample2_f32": (_i, [_vp, _vp, _i, _i, _i, _i, _vp]),
     "ldit_resize_rows": (_i, [_vp, _vp, _vp, _i, _i, _i, _i, _i, _i, _vp]),
     "ldit_patch_embed_scratch_bytes": (_c.c_size_t, [_i, _i, _i]),
     "ldit_set_gemm_tile_n": (None, [_i]),

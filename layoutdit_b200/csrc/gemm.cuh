@@ -34,7 +34,9 @@
 
 namespace ldit {
 
-enum : int { EPI_BIAS = 0, EPI_BIAS_GELU = 1, EPI_SCALE_RESID = 2, EPI_PATCH = 3, EPI_CONV_BIAS = 4 };
+enum : int { EPI_BIAS = 0, EPI_BIAS_GELU = 1, EPI_SCALE_RESID = 2, EPI_PATCH = 3, EPI_CONV_BIAS = 4, EPI_CONV_BIAS_F32 = 5 };
+// EPI_CONV_BIAS_F32: the same convolution with an fp32 output map (the detection heads behind the FPN hold fp32 weights)
+__host__ __device__ constexpr bool epi_is_conv(int epi) { return epi == EPI_CONV_BIAS || epi == EPI_CONV_BIAS_F32; }
 
 struct GemmArgs {
   int M, N, K;
@@ -103,7 +105,7 @@ template <int BN, int EPI, int CTAS>
 struct GemmCfg {
   static_assert(BN == 128 || BN == 192 || BN == 256, "BN");
   static_assert(CTAS == 1 || CTAS == 2, "CTAS");
-  static constexpr bool OUT_F32 = (EPI == EPI_SCALE_RESID || EPI == EPI_PATCH);
+  static constexpr bool OUT_F32 = (EPI == EPI_SCALE_RESID || EPI == EPI_PATCH || EPI == EPI_CONV_BIAS_F32);
   static constexpr int TILE_M = kBM * CTAS;
   static constexpr int A_BYTES = kBM * kBK * 2;
   static constexpr int B_ROWS = BN / CTAS;            // rows of W staged by each CTA
@@ -183,7 +185,7 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
                     const __grid_constant__ CUtensorMap tmC, const GemmArgs g) {
   using Cfg = GemmCfg<BN, EPI, CTAS>;
   constexpr int S = Cfg::STAGES;
-  static_assert(EPI != EPI_CONV_BIAS || (CTAS == 2 && LDIT_KSTEP == 1), "the convolution mode is written for CTA pairs, one ring slot per step");
+  static_assert(!epi_is_conv(EPI) || (CTAS == 2 && LDIT_KSTEP == 1), "the convolution mode is written for CTA pairs, one ring slot per step");
   pdl_launch_dependents();
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
@@ -256,7 +258,7 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
       const int m0 = mblk * Cfg::TILE_M + static_cast<int>(rank) * kBM;
       const int n0 = (tile % g.num_n_blocks) * BN + static_cast<int>(rank) * Cfg::B_ROWS;
       int cvx = 0, cvy = 0, cvb = 0, cv_c = 0, cv_kx = 0, cv_ky = 0;   // EPI_CONV_BIAS: patch origin, running (ky, kx, channel block)
-      if constexpr (EPI == EPI_CONV_BIAS) {
+      if constexpr (epi_is_conv(EPI)) {
         const int mb = tile / g.num_n_blocks, per_img = g.cv_tx * g.cv_ty;
         cvb = mb / per_img;
         const int r = mb - cvb * per_img, ty = r / g.cv_tx;
@@ -276,7 +278,7 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
             if constexpr (CTAS == 2) {
               if (rank == 0) mbar_arrive_expect_tx(&full_bar[st], Cfg::STAGE_BYTES * 2);
               const uint32_t leader_full = mapa_shared(smem_u32(&full_bar[st]), 0);
-              if constexpr (EPI == EPI_CONV_BIAS)
+              if constexpr (epi_is_conv(EPI))
                 tma_load_4d_cg2(sA + st * Cfg::A_BYTES, &tmA, leader_full, cv_c * kBK, cvx + cv_kx - 1, cvy + cv_ky - 1, cvb);
               else
                 tma_load_2d_cg2(sA + st * Cfg::A_BYTES, &tmA, leader_full, (kb + j) * kBK, m0);
@@ -289,7 +291,7 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
           }
         }
         __syncwarp();
-        if constexpr (EPI == EPI_CONV_BIAS) {   // next k-block: channel block fastest, then kx, then ky
+        if constexpr (epi_is_conv(EPI)) {   // next k-block: channel block fastest, then kx, then ky
           if (++cv_c == g.cv_cblocks) { cv_c = 0; if (++cv_kx == 3) { cv_kx = 0; ++cv_ky; } }
         }
         stage += kstep;
@@ -386,7 +388,7 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
       const int row0 = (g.m_reverse ? g.num_m_blocks - 1 - tile / g.num_n_blocks : tile / g.num_n_blocks) * Cfg::TILE_M + row_in_tile;
       const int col0 = (tile % g.num_n_blocks) * BN + cgrp * Cfg::CG_COLS;
       int cvx = 0, cvy = 0, cvb = 0;   // EPI_CONV_BIAS: first pixel of this warp's 32 rows (32 / cv_tw image rows of cv_tw pixels)
-      if constexpr (EPI == EPI_CONV_BIAS) {
+      if constexpr (epi_is_conv(EPI)) {
         const int mb = tile / g.num_n_blocks, per_img = g.cv_tx * g.cv_ty;
         cvb = mb / per_img;
         const int r = mb - cvb * per_img, ty = r / g.cv_tx;
@@ -520,8 +522,11 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
               o[j].z = s4[j].z * (o[j].z + b4[j].z);
               o[j].w = s4[j].w * (o[j].w + b4[j].w);
             }
+            if constexpr (EPI == EPI_CONV_BIAS_F32) {
+              o[j].x += b4[j].x; o[j].y += b4[j].y; o[j].z += b4[j].z; o[j].w += b4[j].w;
+            }
           }
-          if constexpr (EPI == EPI_SCALE_RESID) {
+          if constexpr (EPI == EPI_SCALE_RESID || EPI == EPI_CONV_BIAS_F32) {
             if (lane == 0 && !last_tile) tma_store_wait_read<LDIT_EPI_BUFS - 1>();
           }
           __syncwarp();  // EPI_PATCH: every lane has finished reading this buffer (chunk gc-2) long ago; keeps the warp converged
@@ -552,7 +557,7 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
           __syncwarp();
           if (lane == 0 && col_ok && !LDIT_DBG(g, 2)) {
             if constexpr (EPI == EPI_SCALE_RESID) { if (LDIT_DBG(g, 32)) tma_store_2d(&tmC, buf, col, row0); else tma_reduce_add_2d(&tmC, buf, col, row0); }
-            else if constexpr (EPI == EPI_CONV_BIAS) tma_store_4d(&tmC, buf, col, cvx, cvy, cvb);   // pixels past the image edge are clipped
+            else if constexpr (epi_is_conv(EPI)) tma_store_4d(&tmC, buf, col, cvx, cvy, cvb);   // pixels past the image edge are clipped
             else tma_store_2d(&tmC, buf, col, row0);
             tma_store_commit();
           }

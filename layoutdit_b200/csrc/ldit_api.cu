@@ -370,18 +370,25 @@ int launch_gemm(const void* A, const void* W, GemmArgs g, cudaStream_t st) {
   }
 }
 
-// 3x3 convolution as an implicit GEMM (EPI_CONV_BIAS): tensor maps over the channels-last images, patch shape
-template <int BN>
+// 3x3 convolution as an implicit GEMM (EPI_CONV_BIAS / EPI_CONV_BIAS_F32): tensor maps over the channels-last images, patch shape
+template <int BN, int EPI>
 int launch_conv_t(const void* in, const void* w, GemmArgs g, int B, int H, int W, int Cin, cudaStream_t st) {
-  using Cfg = GemmCfg<BN, EPI_CONV_BIAS, 2>;
+  using Cfg = GemmCfg<BN, EPI, 2>;
   CUtensorMap tmA, tmB, tmC;
   int rc = make_tmap_nhwc_4d(&tmA, in, B, H, W, Cin, 64, g.cv_tw, g.cv_th, CU_TENSOR_MAP_SWIZZLE_128B);
   if (rc) return rc;
   rc = make_tmap_bf16_2d(&tmB, w, g.N, g.K, Cfg::B_ROWS);
   if (rc) return rc;
-  rc = make_tmap_nhwc_4d(&tmC, g.out, B, H, W, g.N, kEpiCols, g.cv_tw, 32 / g.cv_tw, CU_TENSOR_MAP_SWIZZLE_32B);
+  if (Cfg::OUT_F32) {   // fp32 output map: boxes of 16 channels = 64-byte rows, 64-byte swizzle (as the residual epilogue stages them)
+    cuuint64_t dims[4] = {static_cast<cuuint64_t>(g.N), static_cast<cuuint64_t>(W), static_cast<cuuint64_t>(H), static_cast<cuuint64_t>(B)};
+    cuuint64_t strides[3] = {static_cast<cuuint64_t>(g.N) * 4, static_cast<cuuint64_t>(W) * g.N * 4, static_cast<cuuint64_t>(H) * W * g.N * 4};
+    cuuint32_t box[4] = {kEpiCols, static_cast<cuuint32_t>(g.cv_tw), static_cast<cuuint32_t>(32 / g.cv_tw), 1};
+    rc = encode_cached(&tmC, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, g.out, dims, strides, box, CU_TENSOR_MAP_SWIZZLE_64B);
+  } else {
+    rc = make_tmap_nhwc_4d(&tmC, g.out, B, H, W, g.N, kEpiCols, g.cv_tw, 32 / g.cv_tw, CU_TENSOR_MAP_SWIZZLE_32B);
+  }
   if (rc) return rc;
-  return launch_gemm_maps<BN, EPI_CONV_BIAS, 2>(tmA, tmB, tmC, g, st);
+  return launch_gemm_maps<BN, EPI, 2>(tmA, tmB, tmC, g, st);
 }
 
 template <typename T>
@@ -962,8 +969,8 @@ int ldit_fpn_merge(const void* lat, const void* top, void* out, int B, int Gh, i
   return check_launch();
 }
 
-int ldit_conv3x3_bias(const void* in, const void* w, const void* bias, void* out, int B, int H, int W, int Cin, int Cout,
-                      void* stream) {
+static int conv3x3_impl(const void* in, const void* w, const void* bias, void* out, int B, int H, int W, int Cin, int Cout,
+                        bool out_f32, void* stream) {
   if (!in || !w || !out) return LDIT_E_NULL;
   if (B <= 0 || H <= 0 || W <= 0 || Cin <= 0 || (Cin % 64) || Cout <= 0 || (Cout % 128)) return LDIT_E_SHAPE;
   if (!aligned16(in) || !aligned16(w) || !aligned16(bias) || !aligned16(out)) return LDIT_E_ALIGN;
@@ -986,8 +993,22 @@ int ldit_conv3x3_bias(const void* in, const void* w, const void* bias, void* out
   g.M = g.num_m_blocks * 256;   // rows of the implicit GEMM including the pixels past the image edge
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   const int bn = (Cout % 256 == 0) ? pick_bn(g.M, Cout, 2) : 128;
-  if (bn == 256) return launch_conv_t<256>(in, w, g, B, H, W, Cin, st);
-  return launch_conv_t<128>(in, w, g, B, H, W, Cin, st);
+  if (out_f32) {
+    if (bn == 256) return launch_conv_t<256, EPI_CONV_BIAS_F32>(in, w, g, B, H, W, Cin, st);
+    return launch_conv_t<128, EPI_CONV_BIAS_F32>(in, w, g, B, H, W, Cin, st);
+  }
+  if (bn == 256) return launch_conv_t<256, EPI_CONV_BIAS>(in, w, g, B, H, W, Cin, st);
+  return launch_conv_t<128, EPI_CONV_BIAS>(in, w, g, B, H, W, Cin, st);
+}
+
+int ldit_conv3x3_bias(const void* in, const void* w, const void* bias, void* out, int B, int H, int W, int Cin, int Cout,
+                      void* stream) {
+  return conv3x3_impl(in, w, bias, out, B, H, W, Cin, Cout, false, stream);
+}
+
+int ldit_conv3x3_bias_f32(const void* in, const void* w, const void* bias, void* out, int B, int H, int W, int Cin, int Cout,
+                          void* stream) {
+  return conv3x3_impl(in, w, bias, out, B, H, W, Cin, Cout, true, stream);
 }
 
 int ldit_resize_rows(const void* src, void* dst, const void* add, int h, int w, int oh, int ow, int C, int bicubic, void* stream) {
@@ -1005,14 +1026,23 @@ int ldit_resize_rows(const void* src, void* dst, const void* add, int h, int w, 
   return check_launch();
 }
 
-int ldit_subsample2(const void* in, void* out, int B, int H, int W, int C, void* stream) {
+static int subsample2_impl(const void* in, void* out, int B, int H, int W, int C, int esize, void* stream) {
   if (!in || !out) return LDIT_E_NULL;
-  if (B <= 0 || H <= 0 || W <= 0 || C <= 0 || (C % 8)) return LDIT_E_SHAPE;
+  if (B <= 0 || H <= 0 || W <= 0 || C <= 0 || ((C * esize) % 16)) return LDIT_E_SHAPE;
   if (!aligned16(in) || !aligned16(out)) return LDIT_E_ALIGN;
-  const size_t n = static_cast<size_t>(B) * ((H + 1) / 2) * ((W + 1) / 2) * (C / 8);
+  const int c16 = C * esize / 16;
+  const size_t n = static_cast<size_t>(B) * ((H + 1) / 2) * ((W + 1) / 2) * c16;
   launch_kernel(subsample2_kernel, dim3(static_cast<unsigned>((n + 255) / 256)), dim3(256), 0, static_cast<cudaStream_t>(stream), 1,
-                static_cast<const __nv_bfloat16*>(in), static_cast<__nv_bfloat16*>(out), B, H, W, C);
+                static_cast<const uint4*>(in), static_cast<uint4*>(out), B, H, W, c16);
   return check_launch();
+}
+
+int ldit_subsample2(const void* in, void* out, int B, int H, int W, int C, void* stream) {
+  return subsample2_impl(in, out, B, H, W, C, 2, stream);
+}
+
+int ldit_subsample2_f32(const void* in, void* out, int B, int H, int W, int C, void* stream) {
+  return subsample2_impl(in, out, B, H, W, C, 4, stream);
 }
 
 }  // extern "C"

@@ -559,21 +559,21 @@ cast_tokens_kernel(const float* __restrict__ xres, __nv_bfloat16* __restrict__ o
 }
 
 // LastLevelMaxPool (TV:ops/feature_pyramid_network.py:231-249): max_pool2d(kernel 1, stride 2) == every second
-// pixel of every second row.  in [B, H, W, C] -> out [B, ceil(H/2), ceil(W/2), C], bf16, 16 bytes per thread.
+// pixel of every second row.  in [B, H, W, C] -> out [B, ceil(H/2), ceil(W/2), C], any element type: a pixel is
+// c16 16-byte pieces (C * sizeof(element) / 16), one piece per thread.
 __global__ void __launch_bounds__(256)
-subsample2_kernel(const __nv_bfloat16* __restrict__ in, __nv_bfloat16* __restrict__ out, int B, int H, int W, int C) {
+subsample2_kernel(const uint4* __restrict__ in, uint4* __restrict__ out, int B, int H, int W, int c16) {
   pdl_launch_dependents();
   pdl_wait();
-  const int oh = (H + 1) / 2, ow = (W + 1) / 2, c8 = C / 8;
+  const int oh = (H + 1) / 2, ow = (W + 1) / 2;
   const size_t idx = static_cast<size_t>(blockIdx.x) * blockDim.x + threadIdx.x;
-  if (idx >= static_cast<size_t>(B) * oh * ow * c8) return;
-  const int c = static_cast<int>(idx % c8);
-  size_t t = idx / c8;
+  if (idx >= static_cast<size_t>(B) * oh * ow * c16) return;
+  const int c = static_cast<int>(idx % c16);
+  size_t t = idx / c16;
   const int x = static_cast<int>(t % ow); t /= ow;
   const int y = static_cast<int>(t % oh);
   const int b = static_cast<int>(t / oh);
-  reinterpret_cast<uint4*>(out)[idx] =
-      __ldg(reinterpret_cast<const uint4*>(in + ((static_cast<size_t>(b) * H + 2 * y) * W + 2 * x) * C) + c);
+  out[idx] = __ldg(in + ((static_cast<size_t>(b) * H + 2 * y) * W + 2 * x) * c16 + c);
 }
 
 }  // namespace ldit

@@ -54,8 +54,15 @@ class DiTWithFPN(nn.Module):
     """DiT backbone + FPN (p2..p5 + pool), the module ``FasterRCNN`` is given at R:model.py:44-56."""
 
     def __init__(self, pretrained: bool = True, config: DiTConfig | None = None, state_dict: dict | None = None,
-                 fpn_state_dict: dict | None = None, use_cuda_graph: bool = False):
+                 fpn_state_dict: dict | None = None, use_cuda_graph: bool = False, out_dtype: torch.dtype = torch.bfloat16):
+        """``out_dtype``: dtype of the returned maps.  bf16 (default) is what the kernels compute in; ``torch.float32``
+        makes the 3x3 output convolutions store fp32 (same arithmetic, the cast is the epilogue's store format), which is
+        what torchvision's fp32 RPN / RoI heads need when this module is the ``backbone`` of ``FasterRCNN``
+        (R:model.py:44-56) outside autocast -- no user-side cast."""
         super().__init__()
+        if out_dtype not in (torch.bfloat16, torch.float32):
+            raise ValueError("out_dtype must be torch.bfloat16 or torch.float32")
+        self.out_dtype = out_dtype
         self.backbone = DiTBackbone(pretrained=pretrained, config=config, state_dict=state_dict)
         in_channels = [self.backbone.hidden_size] * 4          # R:dit_backbone.py:79
         self.fpn = FPNParameters(in_channels, out_channels=256)  # R:dit_backbone.py:80-84
@@ -63,6 +70,9 @@ class DiTWithFPN(nn.Module):
             self.fpn.load_state_dict(fpn_state_dict, strict=True)
         self.out_channels = 256
         self.use_cuda_graph = use_cuda_graph
+
+    def _head(self) -> str:
+        return "fpn32" if self.out_dtype == torch.float32 else "fpn"
 
     def _engine(self):
         eng = self.backbone._get_engine()
@@ -75,7 +85,7 @@ class DiTWithFPN(nn.Module):
         """Raw pages -> FPN maps: what ``FasterRCNN.forward`` computes up to its RPN (transform + backbone,
         torchvision generalized_rcnn.py), with the transform fused into the patch gather."""
         with torch.no_grad():
-            return self._engine().forward_pages(pages, size, mean, std, "fpn", fixed_size)
+            return self._engine().forward_pages(pages, size, mean, std, self._head(), fixed_size)
 
     def forward(self, x: torch.Tensor) -> "OrderedDict[str, torch.Tensor]":
         if self.training and torch.is_grad_enabled() and any(p.requires_grad for p in self.parameters()):
@@ -84,4 +94,4 @@ class DiTWithFPN(nn.Module):
                 "the call in torch.no_grad()")
         eng = self._engine()
         with torch.no_grad():
-            return eng.forward_graphed(x, 0, "fpn") if self.use_cuda_graph else eng.forward(x, "fpn")
+            return eng.forward_graphed(x, 0, self._head()) if self.use_cuda_graph else eng.forward(x, self._head())

@@ -266,7 +266,7 @@ class Engine:
                 _lib.check(min(0, int(self.lib.ldit_mlp_schedule(M, D, I, host.data_ptr(), host.numel()))), "ldit_mlp_schedule")
                 geo.extra["mlp_sched"] = (host.to(dev), stride)
                 geo.extra["mlp_ready"] = torch.zeros(2 * ((M + 255) // 256), device=dev, dtype=torch.int32)
-        if head == "fpn":
+        if head in ("fpn", "fpn32"):
             C = self._fpn.C
             bf = dict(device=dev, dtype=torch.bfloat16)
             geo.extra["tok"] = torch.empty(B * P, D, **bf)                        # tap tokens without CLS, bf16
@@ -290,11 +290,12 @@ class Engine:
 
     def _alloc_outputs(self, geo: _Geometry):
         bf = dict(device=self.device, dtype=torch.bfloat16)
-        if geo.head == "fpn":   # p2..p5 of the FPN + "pool" (TV:231-249), C channels each
+        if geo.head in ("fpn", "fpn32"):   # p2..p5 of the FPN + "pool" (TV:231-249), C channels each; "fpn32": fp32 maps
             C = self._fpn.C
-            outs = [torch.empty(geo.B, *self._tap_hw(geo, s), C, **bf) for s in TAP_SCALES]
+            od = dict(device=self.device, dtype=torch.float32 if geo.head == "fpn32" else torch.bfloat16)
+            outs = [torch.empty(geo.B, *self._tap_hw(geo, s), C, **od) for s in TAP_SCALES]
             h5, w5 = self._tap_hw(geo, TAP_SCALES[-1])
-            return outs + [torch.empty(geo.B, (h5 + 1) // 2, (w5 + 1) // 2, C, **bf)]
+            return outs + [torch.empty(geo.B, (h5 + 1) // 2, (w5 + 1) // 2, C, **od)]
         return [torch.empty(geo.B, *self._tap_hw(geo, s), self.cfg.hidden_size, **bf) for s in TAP_SCALES]
 
     def _plan(self, geo: _Geometry, x, outs, stream: int):
@@ -315,7 +316,11 @@ class Engine:
                      (x.data_ptr(), _DTYPE_CODE[x.dtype], self.w_patch.data_ptr(), geo.pos_bias.data_ptr(),
                       geo.cls_pos.data_ptr(), big, xr, B, geo.H, geo.W, D, stream))]
 
-        fpn = self._fpn if geo.head == "fpn" else None
+        fpn = self._fpn if geo.head in ("fpn", "fpn32") else None
+        conv_fn, conv_name = ((lib.ldit_conv3x3_bias_f32, "ldit_conv3x3_bias_f32") if geo.head == "fpn32"
+                              else (lib.ldit_conv3x3_bias, "ldit_conv3x3_bias"))
+        sub_fn, sub_name = ((lib.ldit_subsample2_f32, "ldit_subsample2_f32") if geo.head == "fpn32"
+                            else (lib.ldit_subsample2, "ldit_subsample2"))
 
         def emit_tap(layer_no):
             # hidden_states[layer_no] is the residual stream right now (HF:628-630, 654-655)
@@ -367,11 +372,11 @@ class Engine:
                               TAP_SCALES[slot], th, tw, stream)))
             for slot in range(len(TAP_SCALES)):
                 h, w = inner[slot].shape[1], inner[slot].shape[2]
-                plan.append(("ldit_conv3x3_bias", lib.ldit_conv3x3_bias,
+                plan.append((conv_name, conv_fn,
                              (inner[slot].data_ptr(), fpn.w_out[slot].data_ptr(), fpn.b_out[slot].data_ptr(),
                               outs[slot].data_ptr(), B, h, w, C, C, stream)))
             h5, w5 = outs[3].shape[1], outs[3].shape[2]
-            plan.append(("ldit_subsample2", lib.ldit_subsample2, (outs[3].data_ptr(), outs[4].data_ptr(), B, h5, w5, C, stream)))
+            plan.append((sub_name, sub_fn, (outs[3].data_ptr(), outs[4].data_ptr(), B, h5, w5, C, stream)))
         return plan
 
     def _persist_bytes(self, geo: _Geometry) -> int:

@@ -45,6 +45,13 @@ CASES = {
     "base_224_w1":       (dit_base(), 1, True, 1, 224, 224, 1234, False),
     "base_320x224_w1":   (dit_base(), 1, True, 1, 320, 224, 1235, False),
     "large_224_w1":      (dit_large(), 2, True, 1, 224, 224, 1236, False),
+    # relative-position bias at the real size (N = 197, 12 heads, window 27 x 27 + 3): per-layer and shared tables
+    "base_224_relpos_w1": (dit_base(use_absolute_position_embeddings=False, use_relative_position_bias=True),
+                           3, True, 1, 224, 224, 1237, False),
+    "base_224_shared_relpos_w1": (dit_base(use_absolute_position_embeddings=False, use_shared_relative_position_bias=True),
+                                  4, True, 1, 224, 224, 1238, False),
+    # BASELINE config 3 geometry (N = 1025, position table interpolated 14 x 14 -> 32 x 32)
+    "base_512_w1":       (dit_base(), 1, True, 1, 512, 512, 1239, False),
 }
 
 SAMPLE_STRIDE = 97  # prime; flattened outputs are sampled every SAMPLE_STRIDE elements
@@ -70,7 +77,13 @@ def main():
     os.makedirs(out_dir, exist_ok=True)
     torch.manual_seed(0)
     index = {}
+    only = set(sys.argv[1:])          # optional: regenerate just these cases (the others keep their index entries)
+    index_path = os.path.join(out_dir, "index.json")
+    if only and os.path.exists(index_path):
+        index = json.load(open(index_path))["cases"]
     for name, (cfg, wseed, stress, B, H, W, xseed, full) in CASES.items():
+        if only and name not in only:
+            continue
         sd = make_state_dict(cfg, wseed, stress)
         x = synthetic_pages(B, H, W, xseed)
         ref = reference_backbone(cfg)
