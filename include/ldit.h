@@ -61,6 +61,16 @@ int ldit_gemm_bias_gelu(const void* A, const void* W, const void* bias, void* ou
 int ldit_gemm_bias_scale_residual(const void* A, const void* W, const void* bias, const void* scale, void* x, int M, int N,
                                   int K, void* stream);
 
+/* The same residual block in two steps, for a residual stream that is about to be normalised anyway:
+ *   ldit_gemm_bias_scale:  out bf16 [M, N] = scale (.) (A x W^T + bias)          (the layer-scaled branch; scale may be NULL)
+ *   ldit_add_layernorm:    x f32 [rows, D] += branch bf16 [rows, D];  y bf16 = LayerNorm(x)   (HF:488-495 / 500-504 + HF:478)
+ * The GEMM then ends in a plain bf16 tile store and the residual add rides on the LayerNorm that streams x anyway.
+ * y may alias branch.  D multiple of 128, D <= 2048. */
+int ldit_gemm_bias_scale(const void* A, const void* W, const void* bias, const void* scale, void* out, int M, int N, int K,
+                         void* stream);
+int ldit_add_layernorm(void* x, const void* branch, const void* gamma, const void* beta, void* y, int rows, int D, float eps,
+                       void* stream);
+
 /* BeitIntermediate + BeitOutput + layer scale + residual (HF:428-432, 441-445, 500-504) as ONE persistent kernel:
  *   h bf16 [M, I] = gelu_erf(a bf16 [M, D] x W1 bf16 [I, D]^T + b1);   x f32 [M, D] += lam2 (.) (h x W2 bf16 [D, I]^T + b2)
  * Same arithmetic as ldit_gemm_bias_gelu followed by ldit_gemm_bias_scale_residual, bit for bit; the two GEMMs

@@ -19,6 +19,8 @@ SIGNATURES = {
     "ldit_gemm_bias": (_i, [_vp, _vp, _vp, _vp, _i, _i, _i, _vp]),
     "ldit_gemm_bias_gelu": (_i, [_vp, _vp, _vp, _vp, _i, _i, _i, _vp]),
     "ldit_gemm_bias_scale_residual": (_i, [_vp, _vp, _vp, _vp, _vp, _i, _i, _i, _vp]),
+    "ldit_gemm_bias_scale": (_i, [_vp, _vp, _vp, _vp, _vp, _i, _i, _i, _vp]),
+    "ldit_add_layernorm": (_i, [_vp, _vp, _vp, _vp, _vp, _i, _i, _f, _vp]),
     "ldit_mlp_clusters": (_i, []),
     "ldit_mlp_schedule": (_i, [_i, _i, _i, _vp, _i]),
     "ldit_mlp_fused": (_i, [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _i, _i, _i, _vp, _i, _vp, _vp]),

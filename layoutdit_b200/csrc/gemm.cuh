@@ -34,7 +34,10 @@
 
 namespace ldit {
 
-enum : int { EPI_BIAS = 0, EPI_BIAS_GELU = 1, EPI_SCALE_RESID = 2, EPI_PATCH = 3, EPI_CONV_BIAS = 4, EPI_CONV_BIAS_F32 = 5 };
+enum : int { EPI_BIAS = 0, EPI_BIAS_GELU = 1, EPI_SCALE_RESID = 2, EPI_PATCH = 3, EPI_CONV_BIAS = 4, EPI_CONV_BIAS_F32 = 5, EPI_BIAS_SCALE = 6 };
+// EPI_BIAS_SCALE: bf16 out = scale (.) (acc + bias) -- the layer-scaled branch of a residual block, stored for a fused
+// residual-add + LayerNorm kernel to pick up (rowwise.cuh) instead of being reduce-added into the fp32 stream here
+__host__ __device__ constexpr bool epi_has_scale(int epi) { return epi == EPI_SCALE_RESID || epi == EPI_BIAS_SCALE; }
 // EPI_CONV_BIAS_F32: the same convolution with an fp32 output map (the detection heads behind the FPN hold fp32 weights)
 __host__ __device__ constexpr bool epi_is_conv(int epi) { return epi == EPI_CONV_BIAS || epi == EPI_CONV_BIAS_F32; }
 
@@ -419,11 +422,11 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
         const bool ok = 2 * lane < Cfg::CG_COLS && cc < g.N;
         float2 bb = make_float2(0.f, 0.f), ss = make_float2(1.f, 1.f);
         if (ok && g.bias != nullptr) bb = __ldg(reinterpret_cast<const float2*>(g.bias + cc));
-        if constexpr (EPI == EPI_SCALE_RESID) {
+        if constexpr (epi_has_scale(EPI)) {
           if (ok && g.scale != nullptr) ss = __ldg(reinterpret_cast<const float2*>(g.scale + cc));
         }
         *reinterpret_cast<float2*>(my_colop + 2 * lane) = bb;
-        if constexpr (EPI == EPI_SCALE_RESID) *reinterpret_cast<float2*>(my_colop + 64 + 2 * lane) = ss;
+        if constexpr (epi_has_scale(EPI)) *reinterpret_cast<float2*>(my_colop + 64 + 2 * lane) = ss;
         __syncwarp();
       }
       if (tl) tl[4] = clock64();
@@ -459,7 +462,7 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
 #pragma unroll
           for (int j = 0; j < 4; ++j) {
             b4[j] = *reinterpret_cast<const float4*>(my_colop + c * kEpiCols + 4 * j);
-            if constexpr (EPI == EPI_SCALE_RESID) s4[j] = *reinterpret_cast<const float4*>(my_colop + 64 + c * kEpiCols + 4 * j);
+            if constexpr (epi_has_scale(EPI)) s4[j] = *reinterpret_cast<const float4*>(my_colop + 64 + c * kEpiCols + 4 * j);
           }
         }
         tmem_wait_ld16(rc);
@@ -480,6 +483,12 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
                       v[4 * j + 0], v[4 * j + 1]);
             f2_unpack(f2_add(f2_pack(__uint_as_float(rc[4 * j + 2]), __uint_as_float(rc[4 * j + 3])), f2_pack(b4[j].z, b4[j].w)),
                       v[4 * j + 2], v[4 * j + 3]);
+          }
+          if constexpr (EPI == EPI_BIAS_SCALE) {
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+              v[4 * j + 0] *= s4[j].x; v[4 * j + 1] *= s4[j].y; v[4 * j + 2] *= s4[j].z; v[4 * j + 3] *= s4[j].w;
+            }
           }
           if constexpr (EPI == EPI_BIAS_GELU) {
             if (!LDIT_DBG(g, 8)) {

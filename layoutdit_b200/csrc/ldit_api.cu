@@ -629,6 +629,42 @@ int ldit_layernorm(const void* x, const void* gamma, const void* beta, void* y, 
   return check_launch();
 }
 
+int ldit_add_layernorm(void* x, const void* branch, const void* gamma, const void* beta, void* y, int rows, int D, float eps,
+                       void* stream) {
+  if (!x || !branch || !gamma || !beta || !y) return LDIT_E_NULL;
+  if (rows <= 0 || D <= 0 || (D % 128) || D > 2048) return LDIT_E_SHAPE;
+  if (!aligned16(x) || !aligned16(branch) || !aligned16(gamma) || !aligned16(beta) || !aligned16(y)) return LDIT_E_ALIGN;
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  const int lnw = aln_warps(D / 128);
+  const int want = (rows + lnw - 1) / lnw;
+  const int blocks = want < 2 * num_sms() ? want : 2 * num_sms();
+  float* xf = static_cast<float*>(x);
+  const __nv_bfloat16* bb = static_cast<const __nv_bfloat16*>(branch);
+  const float* gf = static_cast<const float*>(gamma);
+  const float* bf = static_cast<const float*>(beta);
+  __nv_bfloat16* yb = static_cast<__nv_bfloat16*>(y);
+#define LDIT_ALN_CASE(V) \
+  case V: launch_kernel(add_layernorm_kernel<V>, dim3(blocks), dim3(lnw * 32), 0, st, 1, xf, bb, gf, bf, yb, rows, eps); break;
+  switch (D / 128) {
+    LDIT_ALN_CASE(1) LDIT_ALN_CASE(2) LDIT_ALN_CASE(3) LDIT_ALN_CASE(4) LDIT_ALN_CASE(5) LDIT_ALN_CASE(6) LDIT_ALN_CASE(7)
+    LDIT_ALN_CASE(8) LDIT_ALN_CASE(9) LDIT_ALN_CASE(10) LDIT_ALN_CASE(11) LDIT_ALN_CASE(12) LDIT_ALN_CASE(13)
+    LDIT_ALN_CASE(14) LDIT_ALN_CASE(15) LDIT_ALN_CASE(16)
+    default: return LDIT_E_SHAPE;
+  }
+#undef LDIT_ALN_CASE
+  return check_launch();
+}
+
+int ldit_gemm_bias_scale(const void* A, const void* W, const void* bias, const void* scale, void* out, int M, int N, int K,
+                         void* stream) {
+  GemmArgs g{};
+  g.M = M; g.N = N; g.K = K;
+  g.bias = static_cast<const float*>(bias);
+  g.scale = static_cast<const float*>(scale);
+  g.out = out; g.ldo = N;
+  return launch_gemm<EPI_BIAS_SCALE>(A, W, g, static_cast<cudaStream_t>(stream));
+}
+
 int ldit_gemm_bias(const void* A, const void* W, const void* bias, void* out, int M, int N, int K, void* stream) {
   GemmArgs g{};
   g.M = M; g.N = N; g.K = K;

@@ -78,6 +78,83 @@ layernorm_kernel(const float* __restrict__ x, const float* __restrict__ gamma, c
   }
 }
 
+// Residual add fused into the LayerNorm that follows it (HF:488-495, 500-504 then the next layer's HF:478):
+//     x <- x + branch;   y = LayerNorm(x)
+// `branch` is the bf16, already layer-scaled output of the out-projection / fc2 GEMM (EPI_BIAS_SCALE).  The GEMM then
+// ends in a plain bf16 tile store instead of an fp32 reduce-add through the L2 atomic units, and the residual stream
+// is updated by the kernel that has to stream it anyway.  y may alias branch (same thread reads then writes the same
+// elements).  Same persistent structure as layernorm_kernel.
+__host__ __device__ constexpr int aln_warps(int vpl) { return vpl <= 4 ? 12 : (vpl <= 6 ? 8 : (vpl <= 8 ? 6 : 3)); }
+template <int VPL>
+__global__ void __launch_bounds__(aln_warps(VPL) * 32, 2)
+add_layernorm_kernel(float* __restrict__ x, const __nv_bfloat16* branch, const float* __restrict__ gamma,
+                     const float* __restrict__ beta, __nv_bfloat16* y, int rows, float eps) {
+  pdl_launch_dependents();
+  pdl_wait();
+  constexpr int D = 128 * VPL;
+  constexpr int kLnWarps = aln_warps(VPL);
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  const int stride = gridDim.x * kLnWarps;
+  int row = blockIdx.x + gridDim.x * warp;
+  if (row >= rows) return;
+  const float4* g4 = reinterpret_cast<const float4*>(gamma);
+  const float4* b4 = reinterpret_cast<const float4*>(beta);
+  float4 v[VPL], nx[VPL];
+  uint2 br[VPL], nb[VPL];
+  {
+    const float4* xr = reinterpret_cast<const float4*>(x + static_cast<size_t>(row) * D);
+    const uint2* rr = reinterpret_cast<const uint2*>(branch + static_cast<size_t>(row) * D);
+#pragma unroll
+    for (int i = 0; i < VPL; ++i) { v[i] = xr[lane + 32 * i]; br[i] = rr[lane + 32 * i]; }
+  }
+  for (; row < rows; row += stride) {
+    const int nrow = row + stride;
+    if (nrow < rows) {
+      const float4* xr = reinterpret_cast<const float4*>(x + static_cast<size_t>(nrow) * D);
+      const uint2* rr = reinterpret_cast<const uint2*>(branch + static_cast<size_t>(nrow) * D);
+#pragma unroll
+      for (int i = 0; i < VPL; ++i) { nx[i] = xr[lane + 32 * i]; nb[i] = rr[lane + 32 * i]; }
+    }
+    float4* xw = reinterpret_cast<float4*>(x + static_cast<size_t>(row) * D);
+    float sum = 0.f;
+#pragma unroll
+    for (int i = 0; i < VPL; ++i) {
+      const float2 lo = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&br[i].x));
+      const float2 hi = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&br[i].y));
+      v[i].x += lo.x; v[i].y += lo.y; v[i].z += hi.x; v[i].w += hi.y;
+      xw[lane + 32 * i] = v[i];
+      sum += (v[i].x + v[i].y) + (v[i].z + v[i].w);
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, o);
+    const float mean = sum * (1.0f / D);
+    float sq = 0.f;
+#pragma unroll
+    for (int i = 0; i < VPL; ++i) {
+      v[i].x -= mean; v[i].y -= mean; v[i].z -= mean; v[i].w -= mean;
+      sq += (v[i].x * v[i].x + v[i].y * v[i].y) + (v[i].z * v[i].z + v[i].w * v[i].w);
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) sq += __shfl_xor_sync(0xffffffffu, sq, o);
+    const float rstd = rsqrtf(sq * (1.0f / D) + eps);
+    uint2* yr = reinterpret_cast<uint2*>(y + static_cast<size_t>(row) * D);
+#pragma unroll
+    for (int i = 0; i < VPL; ++i) {
+      const float4 g = __ldg(g4 + lane + 32 * i);
+      const float4 b = __ldg(b4 + lane + 32 * i);
+      uint2 o;
+      o.x = pack_bf16x2(fmaf(v[i].x * rstd, g.x, b.x), fmaf(v[i].y * rstd, g.y, b.y));
+      o.y = pack_bf16x2(fmaf(v[i].z * rstd, g.z, b.z), fmaf(v[i].w * rstd, g.w, b.w));
+      yr[lane + 32 * i] = o;
+    }
+    if (nrow < rows) {
+#pragma unroll
+      for (int i = 0; i < VPL; ++i) { v[i] = nx[i]; br[i] = nb[i]; }
+    }
+  }
+}
+
 // ------------------------------------------------------------------------- im2col (+cast)
 // Conv2d(3, D, k=16, s=16) at HF:209,218 is a GEMM over 16x16 patches.  This pass rewrites
 // the NCHW page batch as the GEMM's A operand [B*P, 768] bf16 with column order (c, py, px)

@@ -123,6 +123,14 @@ class Engine:
         self.l2_persist = os.environ.get("LDIT_L2_PERSIST", "1") != "0"
         self._persist_cap = int(os.environ.get("LDIT_L2_PERSIST_CAP_MB", "64")) << 20
         self._persist_partial = os.environ.get("LDIT_L2_PERSIST_PARTIAL", "0") != "0"   # experiment: partial window for x > cap
+        # Residual adds deferred into the LayerNorm that follows them: out-projection / fc2 end in a bf16 store of the
+        # layer-scaled branch (ldit_gemm_bias_scale) and ldit_add_layernorm does x += branch; a = LN(x).  Only the last
+        # layer's fc2 (no LayerNorm behind it) keeps the fp32 reduce-add epilogue.
+        # Measured (same-box A/B, bench.py): base224 -1.6 % step time (out-projection 24.7 -> 17.5 us, fc2 52.9 -> 45.7,
+        # each LayerNorm +4.6 us); base512 +2.4 % and large224 +3.3 %, where x and the branch no longer sit in the L2 window
+        # and the add streams the residual through HBM twice.  Hence "auto": only when x and a are both inside the window.
+        # LDIT_DEFER_RESID = 0 never, 1 auto (default), 2 always.
+        self.defer_residual = int(os.environ.get("LDIT_DEFER_RESID", "1"))
 
     # ------------------------------------------------------------------ weight packing
     def _weights_key(self):
@@ -339,7 +347,35 @@ class Engine:
                                  (tok, fpn.w_lat[slot].data_ptr(), fpn.b_lat[slot].data_ptr(), lat, B * geo.Gh * geo.Gw, fpn.C, D, stream)))
 
         emit_tap(0)
+        defer = "mlp_sched" not in geo.extra and (
+            self.defer_residual == 2 or (self.defer_residual == 1 and self._persist_bytes(geo) >= geo.x.numel() * 6))
+        nl = len(self._layers)
         for i, L in enumerate(self._layers):
+            if defer:
+                # x <- x + branch of the previous layer's fc2 (waiting in `a`) fused into LayerNorm 1, which overwrites `a`
+                # in place; hidden_states[i] is complete only now, so its tap is emitted here
+                if i == 0:
+                    plan.append(("ldit_layernorm", lib.ldit_layernorm, (xr, L.ln1_w.data_ptr(), L.ln1_b.data_ptr(), a, M, D, eps, stream)))
+                else:
+                    plan.append(("ldit_add_layernorm", lib.ldit_add_layernorm, (xr, a, L.ln1_w.data_ptr(), L.ln1_b.data_ptr(), a, M, D, eps, stream)))
+                    emit_tap(i)
+                plan += [
+                    ("ldit_gemm_bias", lib.ldit_gemm_bias, (a, L.wqkv.data_ptr(), L.bqkv.data_ptr(), big, M, 3 * D, D, stream)),
+                    ("ldit_attention", lib.ldit_attention, (big, a, _ptr(geo.bias_tables[i]), B, N, heads, geo.Gh, geo.Gw, stream)),
+                    # out-projection branch -> the (now dead) QKV buffer
+                    ("ldit_gemm_bias_scale", lib.ldit_gemm_bias_scale, (a, L.wo.data_ptr(), L.bo.data_ptr(), _ptr(L.lam1), big, M, D, D, stream)),
+                    ("ldit_add_layernorm", lib.ldit_add_layernorm, (xr, big, L.ln2_w.data_ptr(), L.ln2_b.data_ptr(), a, M, D, eps, stream)),
+                ]
+                # fc1 writes the MLP hidden over the branch it no longer needs; big is [M, max(3D, I)]: hidden at offset 0 would
+                # overlap nothing live (the branch was consumed by the add above)
+                plan.append(("ldit_gemm_bias_gelu", lib.ldit_gemm_bias_gelu, (a, L.w1.data_ptr(), L.b1.data_ptr(), big, M, I, D, stream)))
+                if i + 1 < nl:   # fc2 branch -> `a` (LayerNorm 2's output is dead once fc1 has run)
+                    plan.append(("ldit_gemm_bias_scale", lib.ldit_gemm_bias_scale, (big, L.w2.data_ptr(), L.b2.data_ptr(), _ptr(L.lam2), a, M, D, I, stream)))
+                else:
+                    plan.append(("ldit_gemm_bias_scale_residual", lib.ldit_gemm_bias_scale_residual,
+                                 (big, L.w2.data_ptr(), L.b2.data_ptr(), _ptr(L.lam2), xr, M, D, I, stream)))
+                    emit_tap(i + 1)
+                continue
             plan += [
                 ("ldit_layernorm", lib.ldit_layernorm, (xr, L.ln1_w.data_ptr(), L.ln1_b.data_ptr(), a, M, D, eps, stream)),
                 ("ldit_gemm_bias", lib.ldit_gemm_bias, (a, L.wqkv.data_ptr(), L.bqkv.data_ptr(), big, M, 3 * D, D, stream)),

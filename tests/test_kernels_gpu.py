@@ -260,3 +260,39 @@ def test_mlp_fused_matches_the_two_gemms_bit_for_bit(lib, M, D, I):
         assert torch.equal(h, h_ref), f"h differs (rep {rep})"
         assert torch.equal(x, x_ref), f"x differs (rep {rep})"
         assert int(ready.abs().sum()) == 0, "counters not re-armed"
+
+
+# ------------------------------------------------------- residual add deferred into the LayerNorm
+@pytest.mark.parametrize("rows,D", [(5, 128), (1001, 768), (1576, 1024), (12608, 768)])
+def test_add_layernorm(lib, rows, D):
+    g = torch.Generator(device="cuda").manual_seed(rows * 3 + D)
+    x = torch.randn(rows, D, device="cuda", generator=g) * 2 + 0.3
+    br = (torch.randn(rows, D, device="cuda", generator=g) * 0.7).to(torch.bfloat16)
+    w, b = torch.randn(D, device="cuda", generator=g), torch.randn(D, device="cuda", generator=g)
+    x_ref = x + br.float()
+    y_ref = F.layer_norm(x_ref, (D,), w, b, 1e-12)
+    xs, ys = x.clone(), br.clone()                       # y aliases the branch buffer, as in the forward
+    _lib.check(lib.ldit_add_layernorm(xs.data_ptr(), ys.data_ptr(), w.data_ptr(), b.data_ptr(), ys.data_ptr(), rows, D, 1e-12, _stream()), "add_ln")
+    torch.cuda.synchronize()
+    assert torch.equal(xs, x_ref)                        # one fp32 add per element: exact
+    torch.testing.assert_close(ys.float(), y_ref, rtol=2 ** -7, atol=2e-2)
+    ya = torch.empty(rows, D, device="cuda", dtype=torch.bfloat16)
+    xs2 = x.clone()
+    _lib.check(lib.ldit_add_layernorm(xs2.data_ptr(), br.data_ptr(), w.data_ptr(), b.data_ptr(), ya.data_ptr(), rows, D, 1e-12, _stream()), "add_ln")
+    assert torch.equal(ya, ys)
+
+
+@pytest.mark.parametrize("M,N,K", [(12608, 768, 768), (12608, 768, 3072), (300, 1024, 4096), (64, 128, 256)])
+def test_gemm_bias_scale(lib, M, N, K):
+    g = torch.Generator(device="cuda").manual_seed(M + N + K)
+    a = torch.randn(M, K, device="cuda", generator=g).to(torch.bfloat16)
+    w = (torch.randn(N, K, device="cuda", generator=g) * 0.05).to(torch.bfloat16)
+    bias, lam = torch.randn(N, device="cuda", generator=g), torch.rand(N, device="cuda", generator=g) + 0.1
+    out = torch.full((M, N), float("nan"), device="cuda", dtype=torch.bfloat16)
+    _lib.check(lib.ldit_gemm_bias_scale(a.data_ptr(), w.data_ptr(), bias.data_ptr(), lam.data_ptr(), out.data_ptr(), M, N, K, _stream()), "gemm")
+    ref = lam * (a.float() @ w.float().t() + bias)
+    assert torch.isfinite(out.float()).all()
+    assert _rel_fro(out.float(), ref) < 4e-3
+    out2 = torch.empty_like(out)
+    _lib.check(lib.ldit_gemm_bias_scale(a.data_ptr(), w.data_ptr(), bias.data_ptr(), None, out2.data_ptr(), M, N, K, _stream()), "gemm")
+    assert _rel_fro(out2.float(), a.float() @ w.float().t() + bias) < 4e-3

@@ -9,7 +9,7 @@ from conftest import (build_case, build_fpn_case, build_transform_case, compare_
 from oracle import dit_oracle, fpn_oracle, hf_reference, transform_oracle
 
 ALL = sorted(golden_index().keys())
-FAST = [n for n in ALL if n.startswith("tiny")] + ["base_224_w1"]
+FAST = [n for n in ALL if n.startswith("tiny")] + ["base_224_w1", "base_224_relpos_w1", "base_224_shared_relpos_w1"]
 
 
 @pytest.mark.parametrize("name", FAST)
