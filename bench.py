@@ -252,6 +252,12 @@ def _alg(name, args, cfg, geo):
     D, I, h = cfg.hidden_size, cfg.intermediate_size, cfg.num_attention_heads
     M, N, B = geo.M, geo.N, geo.B
     P = geo.Gh * geo.Gw
+    if name == "ldit_gemm_bias_scale":
+        m, n, k = args[-4], args[-3], args[-2]
+        return f"{name} M={m} N={n} K={k}", 2.0 * m * n * k, 2.0 * (m * k + n * k + m * n), "tensor"
+    if name == "ldit_add_layernorm":
+        # residual add (fp32 x read + written, bf16 branch read) fused with the LayerNorm (bf16 out): 12 bytes per element
+        return f"{name} rows={M} D={D} (x += branch; LN)", 0.0, 12.0 * M * D, "hbm"
     if name in ("ldit_gemm_bias", "ldit_gemm_bias_gelu"):
         m, n, k = args[-4], args[-3], args[-2]
         return f"{name} M={m} N={n} K={k}", 2.0 * m * n * k, 2.0 * (m * k + n * k + m * n), "tensor"

@@ -162,6 +162,32 @@ int ldit_subsample2_f32(const void* in, void* out, int B, int H, int W, int C, v
  * Equal sizes copy exactly.  Not part of the per-forward launch sequence. */
 int ldit_resize_rows(const void* src, void* dst, const void* add, int h, int w, int oh, int ow, int C, int bicubic, void* stream);
 
+/* ---- Backward of one BeitLayer (first vertical slice; host side: layoutdit_b200/train.py).
+ * The reference trains through torch.autograd over HF BeitLayer (R:src/layoutdit/training/trainer.py:164-183, HF:469-508).
+ * The eight GEMMs of a layer's backward run on the forward entry points: dgrad dA = dY W is ldit_gemm_bias(dY, W^T),
+ * wgrad dW += dY^T A is ldit_gemm_bias_scale_residual(dY^T, A^T) accumulating into an fp32 dW; the rest is below.
+ * bf16 activations / gradients, fp32 residual-stream gradients and parameter gradients (ACCUMULATED into, like .grad). */
+/* out bf16 [C, ld_out] (ld_out >= R) = in bf16 [R, C]^T  (operands of the wgrad GEMMs; pad ld_out to a multiple of 8
+ * and zero the padding: a TMA operand's row pitch must be a multiple of 16 bytes) */
+int ldit_transpose_bf16(const void* in, void* out, int R, int C, int ld_out, void* stream);
+/* out f32 [C] += column sums of in bf16 [R, ld] over columns [0, C)  (bias gradients; C, ld even) */
+int ldit_colsum_bf16(const void* in, void* out, int R, int C, int ld, void* stream);
+/* erf-GELU (HF:430) on a stored pre-activation, and its backward dpre = dh * gelu'(pre); n elements, n % 8 == 0 */
+int ldit_gelu(const void* pre, void* h, size_t n, void* stream);
+int ldit_gelu_bwd(const void* dh, const void* pre, void* dpre, size_t n, void* stream);
+/* y f32 [rows, D] = x f32 + lam (.) branch bf16   (HF:488-492 / 500-504; lam may be NULL); y may alias x */
+int ldit_scale_residual(const void* x, const void* branch, const void* lam, void* y, int rows, int D, void* stream);
+/* dbranch bf16 = lam (.) dy f32;  dlam f32 [D] += column sums of dy (.) branch  (dlam may be NULL) */
+int ldit_scale_residual_bwd(const void* dy, const void* branch, const void* lam, void* dbranch, void* dlam, int rows, int D,
+                            void* stream);
+/* nn.LayerNorm backward: dx_out f32 = (dx_in or 0) + d/dx of LN(x) gamma + beta under dy bf16; dgamma, dbeta f32 [D] +=.
+ * dx_in may be NULL and may alias dx_out.  Row statistics are recomputed from x. */
+int ldit_layernorm_bwd(const void* x, const void* gamma, const void* dy, const void* dx_in, void* dx_out, void* dgamma, void* dbeta,
+                       int rows, int D, float eps, void* stream);
+/* Backward of ldit_attention without relative-position bias: dqkv bf16 [B*N, 3D] from qkv and dctx bf16 [B*N, D].
+ * Correctness-first stand-in (CUDA cores, one block per (image, head), N <= 256; LDIT_E_UNSUPPORTED beyond). */
+int ldit_attention_bwd(const void* qkv, const void* dctx, void* dqkv, int B, int N, int heads, void* stream);
+
 /* Bytes of the im2col scratch ldit_patch_embed needs. */
 size_t ldit_patch_embed_scratch_bytes(int B, int H, int W);
 

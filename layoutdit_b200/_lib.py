@@ -21,6 +21,14 @@ SIGNATURES = {
     "ldit_gemm_bias_scale_residual": (_i, [_vp, _vp, _vp, _vp, _vp, _i, _i, _i, _vp]),
     "ldit_gemm_bias_scale": (_i, [_vp, _vp, _vp, _vp, _vp, _i, _i, _i, _vp]),
     "ldit_add_layernorm": (_i, [_vp, _vp, _vp, _vp, _vp, _i, _i, _f, _vp]),
+    "ldit_transpose_bf16": (_i, [_vp, _vp, _i, _i, _i, _vp]),
+    "ldit_colsum_bf16": (_i, [_vp, _vp, _i, _i, _i, _vp]),
+    "ldit_gelu": (_i, [_vp, _vp, _c.c_size_t, _vp]),
+    "ldit_gelu_bwd": (_i, [_vp, _vp, _vp, _c.c_size_t, _vp]),
+    "ldit_scale_residual": (_i, [_vp, _vp, _vp, _vp, _i, _i, _vp]),
+    "ldit_scale_residual_bwd": (_i, [_vp, _vp, _vp, _vp, _vp, _i, _i, _vp]),
+    "ldit_layernorm_bwd": (_i, [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _i, _i, _f, _vp]),
+    "ldit_attention_bwd": (_i, [_vp, _vp, _vp, _i, _i, _i, _vp]),
     "ldit_mlp_clusters": (_i, []),
     "ldit_mlp_schedule": (_i, [_i, _i, _i, _vp, _i]),
     "ldit_mlp_fused": (_i, [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _i, _i, _i, _vp, _i, _vp, _vp]),

@@ -14,6 +14,7 @@
 
 #include "../../include/ldit.h"
 #include "attention_v3.cuh"
+#include "backward.cuh"
 #include "gemm.cuh"
 #include "rowwise.cuh"
 // Superseded / experimental kernels (round-1 attention variants, the fused fc1+fc2 kernel): measured slower than the
@@ -1045,6 +1046,100 @@ int ldit_conv3x3_bias(const void* in, const void* w, const void* bias, void* out
 int ldit_conv3x3_bias_f32(const void* in, const void* w, const void* bias, void* out, int B, int H, int W, int Cin, int Cout,
                           void* stream) {
   return conv3x3_impl(in, w, bias, out, B, H, W, Cin, Cout, true, stream);
+}
+
+// ------------------------------------------------------------------ backward of one BeitLayer (first slice)
+// Plain stream-ordered launches (no programmatic dependent launch: these kernels do not carry griddepcontrol).
+int ldit_transpose_bf16(const void* in, void* out, int R, int C, int ld_out, void* stream) {
+  if (!in || !out) return LDIT_E_NULL;
+  if (R <= 0 || C <= 0 || ld_out < R) return LDIT_E_SHAPE;
+  transpose_bf16_kernel<<<dim3((C + 31) / 32, (R + 31) / 32), dim3(32, 8), 0, static_cast<cudaStream_t>(stream)>>>(
+      static_cast<const __nv_bfloat16*>(in), static_cast<__nv_bfloat16*>(out), R, C, ld_out);
+  return check_launch();
+}
+
+int ldit_colsum_bf16(const void* in, void* out, int R, int C, int ld, void* stream) {
+  if (!in || !out) return LDIT_E_NULL;
+  if (R <= 0 || C <= 0 || (C % 2) || ld < C || (ld % 2)) return LDIT_E_SHAPE;
+  const int rpb = 256;
+  colsum_bf16_kernel<<<dim3((C + 63) / 64, (R + rpb - 1) / rpb), dim3(32, 8), 0, static_cast<cudaStream_t>(stream)>>>(
+      static_cast<const __nv_bfloat16*>(in), static_cast<float*>(out), R, C, ld, rpb);
+  return check_launch();
+}
+
+int ldit_gelu(const void* pre, void* h, size_t n, void* stream) {
+  if (!pre || !h) return LDIT_E_NULL;
+  if (n == 0 || (n % 8)) return LDIT_E_SHAPE;
+  if (!aligned16(pre) || !aligned16(h)) return LDIT_E_ALIGN;
+  gelu_fwd_kernel<<<static_cast<unsigned>((n / 8 + 255) / 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(
+      static_cast<const __nv_bfloat16*>(pre), static_cast<__nv_bfloat16*>(h), n / 8);
+  return check_launch();
+}
+
+int ldit_gelu_bwd(const void* dh, const void* pre, void* dpre, size_t n, void* stream) {
+  if (!dh || !pre || !dpre) return LDIT_E_NULL;
+  if (n == 0 || (n % 8)) return LDIT_E_SHAPE;
+  if (!aligned16(dh) || !aligned16(pre) || !aligned16(dpre)) return LDIT_E_ALIGN;
+  gelu_bwd_kernel<<<static_cast<unsigned>((n / 8 + 255) / 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(
+      static_cast<const __nv_bfloat16*>(dh), static_cast<const __nv_bfloat16*>(pre), static_cast<__nv_bfloat16*>(dpre), n / 8);
+  return check_launch();
+}
+
+int ldit_scale_residual(const void* x, const void* branch, const void* lam, void* y, int rows, int D, void* stream) {
+  if (!x || !branch || !y) return LDIT_E_NULL;
+  if (rows <= 0 || D <= 0 || (D % 8)) return LDIT_E_SHAPE;
+  if (!aligned16(x) || !aligned16(branch) || !aligned16(lam) || !aligned16(y)) return LDIT_E_ALIGN;
+  const size_t n8 = static_cast<size_t>(rows) * (D / 8);
+  scale_residual_fwd_kernel<<<static_cast<unsigned>((n8 + 255) / 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(
+      static_cast<const float*>(x), static_cast<const __nv_bfloat16*>(branch), static_cast<const float*>(lam), static_cast<float*>(y), rows, D);
+  return check_launch();
+}
+
+int ldit_scale_residual_bwd(const void* dy, const void* branch, const void* lam, void* dbranch, void* dlam, int rows, int D,
+                            void* stream) {
+  if (!dy || !branch || !dbranch) return LDIT_E_NULL;
+  if (rows <= 0 || D <= 0 || (D % 8)) return LDIT_E_SHAPE;
+  if (!aligned16(dy) || !aligned16(branch) || !aligned16(lam) || !aligned16(dbranch) || !aligned16(dlam)) return LDIT_E_ALIGN;
+  const int rpb = 64, threads = 128;
+  scale_residual_bwd_kernel<<<dim3((D / 8 + threads - 1) / threads, (rows + rpb - 1) / rpb), threads, 0, static_cast<cudaStream_t>(stream)>>>(
+      static_cast<const float*>(dy), static_cast<const __nv_bfloat16*>(branch), static_cast<const float*>(lam),
+      static_cast<__nv_bfloat16*>(dbranch), static_cast<float*>(dlam), rows, D, rpb);
+  return check_launch();
+}
+
+int ldit_layernorm_bwd(const void* x, const void* gamma, const void* dy, const void* dx_in, void* dx_out, void* dgamma, void* dbeta,
+                       int rows, int D, float eps, void* stream) {
+  if (!x || !gamma || !dy || !dx_out || !dgamma || !dbeta) return LDIT_E_NULL;
+  if (rows <= 0 || D <= 0 || (D % 128) || D > 2048) return LDIT_E_SHAPE;
+  if (!aligned16(x) || !aligned16(gamma) || !aligned16(dy) || !aligned16(dx_in) || !aligned16(dx_out)) return LDIT_E_ALIGN;
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  const int want = (rows + 7) / 8;
+  const int blocks = want < 4 * num_sms() ? want : 4 * num_sms();
+#define LDIT_LNB_CASE(V)                                                                                                        \
+  case V:                                                                                                                       \
+    layernorm_bwd_kernel<V><<<blocks, 256, 0, st>>>(static_cast<const float*>(x), static_cast<const float*>(gamma),            \
+                                                    static_cast<const __nv_bfloat16*>(dy), static_cast<const float*>(dx_in),    \
+                                                    static_cast<float*>(dx_out), static_cast<float*>(dgamma),                  \
+                                                    static_cast<float*>(dbeta), rows, eps);                                    \
+    break;
+  switch (D / 128) {
+    LDIT_LNB_CASE(1) LDIT_LNB_CASE(2) LDIT_LNB_CASE(3) LDIT_LNB_CASE(4) LDIT_LNB_CASE(5) LDIT_LNB_CASE(6) LDIT_LNB_CASE(7)
+    LDIT_LNB_CASE(8) LDIT_LNB_CASE(9) LDIT_LNB_CASE(10) LDIT_LNB_CASE(11) LDIT_LNB_CASE(12) LDIT_LNB_CASE(13)
+    LDIT_LNB_CASE(14) LDIT_LNB_CASE(15) LDIT_LNB_CASE(16)
+    default: return LDIT_E_SHAPE;
+  }
+#undef LDIT_LNB_CASE
+  return check_launch();
+}
+
+int ldit_attention_bwd(const void* qkv, const void* dctx, void* dqkv, int B, int N, int heads, void* stream) {
+  if (!qkv || !dctx || !dqkv) return LDIT_E_NULL;
+  if (B <= 0 || heads <= 0 || N <= 0) return LDIT_E_SHAPE;
+  if (N > kAbThreads) return LDIT_E_UNSUPPORTED;   // the stand-in kernel maps one thread to one key
+  if (!aligned16(qkv) || !aligned16(dctx) || !aligned16(dqkv)) return LDIT_E_ALIGN;
+  attention_bwd_kernel<<<B * heads, kAbThreads, 0, static_cast<cudaStream_t>(stream)>>>(
+      static_cast<const __nv_bfloat16*>(qkv), static_cast<const __nv_bfloat16*>(dctx), static_cast<__nv_bfloat16*>(dqkv), N, heads);
+  return check_launch();
 }
 
 int ldit_resize_rows(const void* src, void* dst, const void* add, int h, int w, int oh, int ow, int C, int bicubic, void* stream) {

@@ -1,0 +1,184 @@
+"""GPU: first vertical slice of the training path -- the backward of BeitLayer through the C ABI
+against torch.autograd over the oracle's restatement of the same layer (oracle/dit_oracle.py: beit_layer, written in
+differentiable torch ops and pinned to the reference's fixtures in tests/test_oracle.py), fp64 on the CPU.
+
+Stated tolerance: bf16 activations / activation gradients with fp32 accumulation against an fp64 reference: relative
+Frobenius error <= 2e-2 per gradient tensor (the forward's bound is 1e-2; a backward chains twice as many bf16 roundings).
+"""
+import pytest
+import torch
+import torch.nn.functional as F
+
+from layoutdit_b200 import _lib
+from layoutdit_b200.config import DiTConfig
+from layoutdit_b200.dit_params import DiTParameters
+from layoutdit_b200.synth import make_state_dict
+from layoutdit_b200.train import TrainableEncoder
+from oracle import dit_oracle
+
+pytestmark = pytest.mark.gpu
+GRAD_TOL = 2e-2
+
+
+def _st():
+    return torch.cuda.current_stream().cuda_stream
+
+
+def _rel(got, ref):
+    return float((got.double().cpu() - ref.double().cpu()).norm() / ref.double().cpu().norm().clamp_min(1e-30))
+
+
+@pytest.fixture(scope="module")
+def lib(cuda_device):
+    return _lib.load()
+
+
+# ------------------------------------------------------------------------------ kernels
+@pytest.mark.parametrize("R,C", [(34, 128), (197, 768), (1000, 96), (5, 8)])
+def test_transpose(lib, R, C):
+    x = torch.randn(R, C, device="cuda").to(torch.bfloat16)
+    ld = (R + 7) // 8 * 8
+    out = torch.zeros(C, ld, device="cuda", dtype=torch.bfloat16)
+    _lib.check(lib.ldit_transpose_bf16(x.data_ptr(), out.data_ptr(), R, C, ld, _st()), "transpose")
+    assert torch.equal(out[:, :R], x.t())
+    assert float(out[:, R:].float().abs().sum()) == 0.0
+
+
+def test_colsum_and_gelu(lib):
+    g = torch.Generator(device="cuda").manual_seed(3)
+    x = torch.randn(777, 256, device="cuda", generator=g).to(torch.bfloat16)
+    acc = torch.ones(256, device="cuda")
+    _lib.check(lib.ldit_colsum_bf16(x.data_ptr(), acc.data_ptr(), 777, 256, 256, _st()), "colsum")
+    torch.testing.assert_close(acc, 1.0 + x.float().sum(0), rtol=1e-4, atol=1e-3)
+    pre = (torch.randn(512, 256, device="cuda", generator=g) * 2).to(torch.bfloat16)
+    dh = torch.randn(512, 256, device="cuda", generator=g).to(torch.bfloat16)
+    h, dpre = torch.empty_like(pre), torch.empty_like(pre)
+    _lib.check(lib.ldit_gelu(pre.data_ptr(), h.data_ptr(), pre.numel(), _st()), "gelu")
+    _lib.check(lib.ldit_gelu_bwd(dh.data_ptr(), pre.data_ptr(), dpre.data_ptr(), pre.numel(), _st()), "gelu_bwd")
+    p32 = pre.float().requires_grad_(True)
+    ref = F.gelu(p32)
+    ref.backward(dh.float())
+    torch.testing.assert_close(h.float(), ref.detach(), rtol=2 ** -7, atol=1e-3)
+    torch.testing.assert_close(dpre.float(), p32.grad, rtol=2 ** -7, atol=2e-3)
+
+
+@pytest.mark.parametrize("rows,D,with_lam", [(34, 128, True), (1001, 768, True), (197, 1024, False)])
+def test_scale_residual_and_layernorm_backward(lib, rows, D, with_lam):
+    g = torch.Generator(device="cuda").manual_seed(rows + D)
+    x = torch.randn(rows, D, device="cuda", generator=g)
+    br = torch.randn(rows, D, device="cuda", generator=g).to(torch.bfloat16)
+    lam = (torch.rand(D, device="cuda", generator=g) + 0.2) if with_lam else None
+    y = torch.empty_like(x)
+    _lib.check(lib.ldit_scale_residual(x.data_ptr(), br.data_ptr(), None if lam is None else lam.data_ptr(), y.data_ptr(), rows, D, _st()), "sr")
+    torch.testing.assert_close(y, x + (lam if with_lam else 1.0) * br.float(), rtol=1e-6, atol=1e-6)
+    dy = torch.randn(rows, D, device="cuda", generator=g)
+    dbr = torch.empty_like(br)
+    dlam = torch.zeros(D, device="cuda") if with_lam else None
+    _lib.check(lib.ldit_scale_residual_bwd(dy.data_ptr(), br.data_ptr(), None if lam is None else lam.data_ptr(), dbr.data_ptr(),
+                                           None if dlam is None else dlam.data_ptr(), rows, D, _st()), "srb")
+    torch.testing.assert_close(dbr.float(), ((lam if with_lam else 1.0) * dy), rtol=2 ** -7, atol=1e-3)
+    if with_lam:
+        torch.testing.assert_close(dlam, (dy * br.float()).sum(0), rtol=1e-3, atol=1e-2)
+    # LayerNorm backward vs autograd
+    w, b = torch.randn(D, device="cuda", generator=g), torch.randn(D, device="cuda", generator=g)
+    dyb = torch.randn(rows, D, device="cuda", generator=g).to(torch.bfloat16)
+    dx_in = torch.randn(rows, D, device="cuda", generator=g)
+    xr, wr, brr = x.clone().requires_grad_(True), w.clone().requires_grad_(True), b.clone().requires_grad_(True)
+    F.layer_norm(xr, (D,), wr, brr, 1e-12).backward(dyb.float())
+    dx, dw, db = torch.empty_like(x), torch.zeros(D, device="cuda"), torch.zeros(D, device="cuda")
+    _lib.check(lib.ldit_layernorm_bwd(x.data_ptr(), w.data_ptr(), dyb.data_ptr(), dx_in.data_ptr(), dx.data_ptr(), dw.data_ptr(), db.data_ptr(),
+                                      rows, D, 1e-12, _st()), "lnb")
+    torch.testing.assert_close(dx, dx_in + xr.grad, rtol=1e-3, atol=1e-3)
+    torch.testing.assert_close(dw, wr.grad, rtol=1e-3, atol=2e-2)
+    torch.testing.assert_close(db, brr.grad, rtol=1e-3, atol=2e-2)
+
+
+@pytest.mark.parametrize("B,heads,N", [(2, 2, 17), (1, 12, 197), (3, 3, 256), (1, 1, 1)])
+def test_attention_backward(lib, B, heads, N):
+    D = heads * 64
+    g = torch.Generator(device="cuda").manual_seed(N + heads)
+    qkv = torch.randn(B * N, 3 * D, device="cuda", generator=g).to(torch.bfloat16)
+    dctx = torch.randn(B * N, D, device="cuda", generator=g).to(torch.bfloat16)
+    dqkv = torch.full_like(qkv, float("nan"))
+    _lib.check(lib.ldit_attention_bwd(qkv.data_ptr(), dctx.data_ptr(), dqkv.data_ptr(), B, N, heads, _st()), "attn_bwd")
+    x = qkv.double().requires_grad_(True)
+    q, k, v = x.reshape(B, N, 3, heads, 64).permute(2, 0, 3, 1, 4)
+    ctx = (torch.softmax(q @ k.transpose(-1, -2) / 8.0, dim=-1) @ v).transpose(1, 2).reshape(B * N, D)
+    ctx.backward(dctx.double())
+    assert torch.isfinite(dqkv.float()).all()
+    assert _rel(dqkv.float(), x.grad) < 6e-3
+    assert lib.ldit_attention_bwd(qkv.data_ptr(), dctx.data_ptr(), dqkv.data_ptr(), 1, 257, 1, _st()) == -6   # beyond the stand-in kernel
+
+
+# --------------------------------------------------------------------- the layer, end to end
+@pytest.mark.parametrize("layer_scale,B,G", [(0.1, 2, 4), (0.0, 1, 5), (0.1, 2, 14)])
+def test_two_layer_encoder_gradients_match_oracle_autograd(cuda_device, layer_scale, B, G):
+    cfg = DiTConfig(hidden_size=128, num_hidden_layers=2, num_attention_heads=2, intermediate_size=256, image_size=G * 16,
+                    layer_scale_init_value=layer_scale)
+    sd = make_state_dict(cfg, 77, True)
+    N, D = G * G + 1, cfg.hidden_size
+    gen = torch.Generator().manual_seed(5)
+    h0 = torch.randn(B, N, D, generator=gen)
+    wgt = torch.randn(B, N, D, generator=gen)           # loss = <output, wgt>: a dense upstream gradient
+
+    # ours
+    tree = DiTParameters(cfg)
+    tree.load_state_dict(sd)
+    tree = tree.cuda()
+    enc = TrainableEncoder(tree, cfg)
+    hin = h0.cuda().requires_grad_(True)
+    out = enc(hin, G, G)
+    (out * wgt.cuda()).sum().backward()
+
+    # oracle: the same two layers in fp64 under torch.autograd
+    sd64 = {k: v.double().requires_grad_(v.is_floating_point()) for k, v in sd.items()}
+    x = h0.double().requires_grad_(True)
+    y = x
+    for i in range(cfg.num_hidden_layers):
+        y = dit_oracle.beit_layer(sd64, cfg.to_dict(), i, y, None, G, G)
+    (y * wgt.double()).sum().backward()
+
+    assert _rel(out.detach(), y.detach()) < 1e-2
+    e = _rel(hin.grad, x.grad)
+    print(f"dx rel-Fro {e:.2e}")
+    assert e < GRAD_TOL
+    worst = 0.0
+    for name, p in tree.named_parameters():
+        if not name.startswith("encoder.layer."):
+            continue
+        ref = sd64[name].grad
+        assert p.grad is not None, name
+        e = _rel(p.grad, ref)
+        worst = max(worst, e)
+        assert e < GRAD_TOL, f"{name}: rel-Frobenius {e:.3e}"
+    print(f"worst parameter-gradient rel-Fro {worst:.2e}")
+    # a second backward accumulates into .grad like torch.autograd does
+    before = tree.encoder.layer[0].output.dense.weight.grad.clone()
+    (enc(hin, G, G) * wgt.cuda()).sum().backward()
+    torch.testing.assert_close(tree.encoder.layer[0].output.dense.weight.grad, 2 * before, rtol=1e-3, atol=1e-5)
+
+
+def test_base_size_layer_gradients(cuda_device):
+    """One DiT-base layer (D = 768, 12 heads, I = 3072) on 8 pages of 224 x 224 (M = 1576 rows, 197 tokens): the wgrad
+    GEMMs contract over a token dimension that is not a multiple of 64, the dgrad GEMMs run at the forward's widths."""
+    cfg = DiTConfig(num_hidden_layers=1)
+    sd = make_state_dict(cfg, 78, True)
+    B, G = 8, 14
+    N, D = G * G + 1, cfg.hidden_size
+    gen = torch.Generator().manual_seed(6)
+    h0, wgt = torch.randn(B, N, D, generator=gen), torch.randn(B, N, D, generator=gen)
+    tree = DiTParameters(cfg)
+    tree.load_state_dict(sd)
+    tree = tree.cuda()
+    hin = h0.cuda().requires_grad_(True)
+    out = TrainableEncoder(tree, cfg)(hin, G, G)
+    (out * wgt.cuda()).sum().backward()
+    sdg = {k: v.cuda().float().requires_grad_(v.is_floating_point()) for k, v in sd.items()}   # fp32 oracle on the GPU (size)
+    x = h0.cuda().requires_grad_(True)
+    y = dit_oracle.beit_layer(sdg, cfg.to_dict(), 0, x, None, G, G)
+    (y * wgt.cuda()).sum().backward()
+    assert _rel(hin.grad, x.grad) < GRAD_TOL
+    for name, p in tree.named_parameters():
+        if name.startswith("encoder.layer.0."):
+            e = _rel(p.grad, sdg[name].grad)
+            assert e < GRAD_TOL, f"{name}: {e:.3e}"
