@@ -98,6 +98,19 @@ int ldit_mlp_fused(const void* a, const void* W1, const void* b1, void* h, const
 int ldit_patch_embed(const void* pixels, int pixel_dtype, const void* w, const void* pos_bias, const void* cls_pos,
                      void* scratch, void* x, int B, int H, int W, int D, void* stream);
 
+/* BeitEmbeddings.forward for 16-bit pixels as ONE TMA-fed im2col GEMM (no scratch, no separate gather / CLS kernels): the A
+ * operand tiles are gathered by 5-D TMA boxes (px, py, patch column, patch row, image x channel) straight out of the NCHW
+ * batch, patches outside the grid are zero-filled by the TMA unit, token row 0 of every image is written by the same kernel.
+ *  pixels  [B, 3, H, W] fp16 or bf16 (pixel_dtype LDIT_DTYPE_F16 / LDIT_DTYPE_BF16; the reference feeds fp16 under autocast,
+ *          R:src/layoutdit/training/trainer.py:155,168)
+ *  w       [D, 768] flattened conv weight IN THE SAME 16-BIT TYPE AS THE PIXELS (tcgen05 kind::f16 traps on mixed f16 / bf16)
+ * everything else as ldit_patch_embed, which takes this path by itself for bf16 pixels. */
+int ldit_patch_embed_tma(const void* pixels, int pixel_dtype, const void* w, const void* pos_bias, const void* cls_pos, void* x,
+                         int B, int H, int W, int D, void* stream);
+/* 1 if the one-launch TMA path is expected to beat gather pass + plain GEMM for this geometry (it tiles every image on its
+ * own, so narrow grids and wide D can lose), else 0; ldit_patch_embed applies the same rule to bf16 pixels. */
+int ldit_patch_embed_tma_preferred(int B, int H, int W, int D);
+
 /* ldit_patch_embed with the detector's input transform fused into the patch gather (SURVEY.md section 8 row
  * f3): GeneralizedRCNNTransform as configured at R:src/layoutdit/modeling/model.py:44-56 -- per page
  * normalize (image - mean) / std, then F.interpolate(size=(H, W), mode="bilinear", align_corners=False)

@@ -33,6 +33,8 @@ SIGNATURES = {
     "ldit_mlp_schedule": (_i, [_i, _i, _i, _vp, _i]),
     "ldit_mlp_fused": (_i, [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _i, _i, _i, _vp, _i, _vp, _vp]),
     "ldit_patch_embed": (_i, [_vp, _i, _vp, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _vp]),
+    "ldit_patch_embed_tma": (_i, [_vp, _i, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _vp]),
+    "ldit_patch_embed_tma_preferred": (_i, [_i, _i, _i, _i]),
     "ldit_patch_embed_pages": (_i, [_vp, _vp, _i, _i, _f, _f, _f, _f, _f, _f, _vp, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _vp]),
     "ldit_attention": (_i, [_vp, _vp, _vp, _i, _i, _i, _i, _i, _vp]),
     "ldit_resample_taps": (_i, [_vp, _vp, _i, _i, _i, _i, _f, _vp]),

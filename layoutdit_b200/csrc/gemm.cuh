@@ -34,7 +34,10 @@
 
 namespace ldit {
 
-enum : int { EPI_BIAS = 0, EPI_BIAS_GELU = 1, EPI_SCALE_RESID = 2, EPI_PATCH = 3, EPI_CONV_BIAS = 4, EPI_CONV_BIAS_F32 = 5, EPI_BIAS_SCALE = 6 };
+enum : int { EPI_BIAS = 0, EPI_BIAS_GELU = 1, EPI_SCALE_RESID = 2, EPI_PATCH = 3, EPI_CONV_BIAS = 4, EPI_CONV_BIAS_F32 = 5, EPI_BIAS_SCALE = 6, EPI_PATCH_TMA = 7 };
+// EPI_PATCH_TMA: the patch embedding with its A operand gathered by TMA straight out of the NCHW page batch (16-bit pixels):
+// no im2col matrix, CLS rows written by the same kernel
+__host__ __device__ constexpr bool epi_is_patch(int epi) { return epi == EPI_PATCH || epi == EPI_PATCH_TMA; }
 // EPI_BIAS_SCALE: bf16 out = scale (.) (acc + bias) -- the layer-scaled branch of a residual block, stored for a fused
 // residual-add + LayerNorm kernel to pick up (rowwise.cuh) instead of being reduce-added into the fp32 stream here
 __host__ __device__ constexpr bool epi_has_scale(int epi) { return epi == EPI_SCALE_RESID || epi == EPI_BIAS_SCALE; }
@@ -50,6 +53,15 @@ struct GemmArgs {
   int ldo;             // output row pitch in elements
   int P;               // EPI_PATCH: patches per image; GEMM row b*P+p -> token row b*(P+1)+1+p
   const float* posb;   // EPI_PATCH: [P, N] fp32 = position rows 1..P + conv bias
+  // EPI_PATCH_TMA (HF:176-180, 218 without an im2col pass): pixels [B, 3, H, W] of a 16-bit float type are a 5-D tensor
+  // (px 16, patch column pe_gw, py 16, patch row pe_gh, image x channel) -- dimensions in order of increasing stride, which
+  // the TMA unit needs.  One UMMA_K step (16 K elements = pixel row py of channel c) of a CTA's 128 patches (cv_tw columns
+  // x cv_th rows of the patch grid; the pair's second CTA takes the cv_th rows below) is ONE box [16, cv_tw, 1, cv_th, 1]
+  // = 128 rows of 32 B, a K-major operand tile with 32-byte swizzle; a 64-wide k-block is four of them.  Patches outside
+  // the grid are zero filled by the TMA unit and skipped by the epilogue.  cv_tx x cv_ty pair tiles per image.
+  int pe_gw, pe_gh;
+  int a_f16;           // both operands fp16 (pixels as the reference feeds them under autocast + an fp16 copy of the weights)
+  const float* cls;    // [N] fp32 = cls_token + position row 0, written to token row 0 of every image
   int num_m_blocks, num_n_blocks;
   int m_reverse;       // 1: row blocks are visited last-to-first (consume a just-written A operand freshest-first, see ldit_api.cu)
   // EPI_CONV_BIAS (3x3 convolution, stride 1, zero padding 1, over a channels-last image [B, H, W, Cin] as an
@@ -108,7 +120,7 @@ template <int BN, int EPI, int CTAS>
 struct GemmCfg {
   static_assert(BN == 128 || BN == 192 || BN == 256, "BN");
   static_assert(CTAS == 1 || CTAS == 2, "CTAS");
-  static constexpr bool OUT_F32 = (EPI == EPI_SCALE_RESID || EPI == EPI_PATCH || EPI == EPI_CONV_BIAS_F32);
+  static constexpr bool OUT_F32 = (EPI == EPI_SCALE_RESID || epi_is_patch(EPI) || EPI == EPI_CONV_BIAS_F32);
   static constexpr int TILE_M = kBM * CTAS;
   static constexpr int A_BYTES = kBM * kBK * 2;
   static constexpr int B_ROWS = BN / CTAS;            // rows of W staged by each CTA
@@ -126,7 +138,7 @@ struct GemmCfg {
   static constexpr int CHUNK_BYTES = 32 * kEpiCols * (OUT_F32 ? 4 : 2);
   static constexpr int STAGING_BYTES = kGemmEpiWarps * LDIT_EPI_BUFS * CHUNK_BYTES;
   // per epilogue warp: bias and layer-scale of the warp's CG_COLS columns, staged once per tile
-  static constexpr int COLOP_BYTES = (EPI == EPI_PATCH) ? 0 : kGemmEpiWarps * 2 * 64 * 4;
+  static constexpr int COLOP_BYTES = epi_is_patch(EPI) ? 0 : kGemmEpiWarps * 2 * 64 * 4;
   static constexpr int BAR_BYTES = 256;
   static constexpr int STAGES_FIT = (kMaxSmem - 1024 - BAR_BYTES - STAGING_BYTES - COLOP_BYTES) / STAGE_BYTES;
   static constexpr int STAGES = (STAGES_FIT > 8 ? 8 : STAGES_FIT) & ~(LDIT_KSTEP - 1);  // even when the loops take slots in pairs
@@ -188,7 +200,7 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
                     const __grid_constant__ CUtensorMap tmC, const GemmArgs g) {
   using Cfg = GemmCfg<BN, EPI, CTAS>;
   constexpr int S = Cfg::STAGES;
-  static_assert(!epi_is_conv(EPI) || (CTAS == 2 && LDIT_KSTEP == 1), "the convolution mode is written for CTA pairs, one ring slot per step");
+  static_assert(!(epi_is_conv(EPI) || EPI == EPI_PATCH_TMA) || (CTAS == 2 && LDIT_KSTEP == 1), "the convolution mode is written for CTA pairs, one ring slot per step");
   pdl_launch_dependents();
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
@@ -211,7 +223,7 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
   if (warp == kWarpProducer && lane == 0) {
     tma_prefetch_desc(&tmA);
     tma_prefetch_desc(&tmB);
-    if constexpr (EPI != EPI_PATCH) tma_prefetch_desc(&tmC);
+    if constexpr (!epi_is_patch(EPI)) tma_prefetch_desc(&tmC);
   }
   if (warp == kWarpMma && lane == 0) {
     for (int i = 0; i < S; ++i) {
@@ -268,6 +280,13 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
         cvx = ((r - ty * g.cv_tx) * 2 + static_cast<int>(rank)) * g.cv_tw;
         cvy = ty * g.cv_th;
       }
+      if constexpr (EPI == EPI_PATCH_TMA) {   // patch rectangle of this CTA: columns cvx.., rows cvy.. of image cvb's patch grid
+        const int mb = tile / g.num_n_blocks, per_img = g.cv_tx * g.cv_ty;
+        cvb = mb / per_img;
+        const int r = mb - cvb * per_img, ty = r / g.cv_tx;
+        cvx = (r - ty * g.cv_tx) * g.cv_tw;
+        cvy = (ty * 2 + static_cast<int>(rank)) * g.cv_th;
+      }
       long long* ptl = (LDIT_TL(g) != nullptr && rank == 0 && lane == 0 && pti < 16) ? LDIT_TL(g) + (static_cast<size_t>(cluster_id) * 16 + pti) * 16 : nullptr;
       long long wempty = 0;
       for (int kb = 0; kb < nkb; kb += kstep) {
@@ -283,7 +302,12 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
               const uint32_t leader_full = mapa_shared(smem_u32(&full_bar[st]), 0);
               if constexpr (epi_is_conv(EPI))
                 tma_load_4d_cg2(sA + st * Cfg::A_BYTES, &tmA, leader_full, cv_c * kBK, cvx + cv_kx - 1, cvy + cv_ky - 1, cvb);
-              else
+              else if constexpr (EPI == EPI_PATCH_TMA) {   // k-block kb = (channel kb / 4, pixel rows 4 (kb % 4) ..): one box per pixel row
+#pragma unroll
+                for (int q = 0; q < 4; ++q)
+                  tma_load_5d_cg2(sA + st * Cfg::A_BYTES + q * (Cfg::A_BYTES / 4), &tmA, leader_full, 0, cvx, ((kb + j) & 3) * 4 + q, cvy,
+                                  cvb * 3 + ((kb + j) >> 2));
+              } else
                 tma_load_2d_cg2(sA + st * Cfg::A_BYTES, &tmA, leader_full, (kb + j) * kBK, m0);
               tma_load_2d_cg2(sB + st * Cfg::B_BYTES, &tmB, leader_full, (kb + j) * kBK, n0);
             } else {
@@ -303,8 +327,11 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
     }
   } else if (warp == kWarpMma) {
     if (rank == 0) {
-      constexpr uint32_t idesc = umma_idesc_bf16(Cfg::TILE_M, BN, 0, 0);
-      const uint64_t adesc0 = umma_desc_kmajor_sw128(smem_u32(sA));
+      constexpr uint32_t idesc_bf16 = umma_idesc_bf16(Cfg::TILE_M, BN, 0, 0);
+      // EPI_PATCH_TMA with fp16 pixels: both operand format fields ([7,10) A, [10,13) B) = 0 (f16); the weights are then an
+      // fp16 copy (mixing an f16 A with a bf16 B traps with "illegal instruction" on sm_100a, measured)
+      const uint32_t idesc = (EPI == EPI_PATCH_TMA && g.a_f16) ? (idesc_bf16 & ~((7u << 7) | (7u << 10))) : idesc_bf16;
+      const uint64_t adesc0 = (EPI == EPI_PATCH_TMA) ? umma_desc_kmajor_sw32(smem_u32(sA)) : umma_desc_kmajor_sw128(smem_u32(sA));
       const uint64_t bdesc0 = umma_desc_kmajor_sw128(smem_u32(sB));
       int stage = 0;
       uint32_t phase = 0;
@@ -330,10 +357,13 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
               const int st = stage + j;
               const uint64_t adesc = adesc0 + static_cast<uint32_t>(st * (Cfg::A_BYTES >> 4));
               const uint64_t bdesc = bdesc0 + static_cast<uint32_t>(st * (Cfg::B_BYTES >> 4));
+              // A advances by 32 B inside the 128-byte swizzle atom per UMMA_K step; the TMA-gathered patch operand instead
+              // holds one 32-byte-swizzled [128 x 16] sub-tile per step (A_BYTES / 4 apart)
+              constexpr uint32_t a_step = (EPI == EPI_PATCH_TMA) ? (Cfg::A_BYTES / 4) >> 4 : 2;
 #pragma unroll
               for (int k = 0; k < kBK / kUmmaK; ++k) {
-                if constexpr (CTAS == 2) umma_bf16_ss_cg2(d_tmem, adesc + 2 * k, bdesc + 2 * k, idesc, (kb | j | k) != 0);
-                else umma_bf16_ss(d_tmem, adesc + 2 * k, bdesc + 2 * k, idesc, (kb | j | k) != 0);
+                if constexpr (CTAS == 2) umma_bf16_ss_cg2(d_tmem, adesc + a_step * k, bdesc + 2 * k, idesc, (kb | j | k) != 0);
+                else umma_bf16_ss(d_tmem, adesc + a_step * k, bdesc + 2 * k, idesc, (kb | j | k) != 0);
               }
               // smem slot reusable (in both CTAs) once these MMAs have read it
               if constexpr (CTAS == 2) tcgen05_commit_cg2(&empty_bar[st], 3); else tcgen05_commit(&empty_bar[st]);
@@ -413,11 +443,31 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
           p_orow[i] = static_cast<size_t>(b) * (g.P + 1) + 1 + p;
         }
       }
+      if constexpr (EPI == EPI_PATCH_TMA) {
+        const int mb = tile / g.num_n_blocks, per_img = g.cv_tx * g.cv_ty;
+        const int b = mb / per_img, r = mb - b * per_img, ty = r / g.cv_tx, tx = r - ty * g.cv_tx;
+        const int gx0 = tx * g.cv_tw, gy0 = (ty * 2 + static_cast<int>(rank)) * g.cv_th;
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+          const int rl = quarter * 32 + (lane >> 2) + 8 * i;        // accumulator row = patch (rl / tw, rl % tw) of the rectangle
+          const int gy = gy0 + rl / g.cv_tw, gx = gx0 + rl % g.cv_tw;
+          const int p = gy * g.pe_gw + gx;
+          p_prow[i] = (gy < g.pe_gh && gx < g.pe_gw) ? p : -1;
+          p_orow[i] = static_cast<size_t>(b) * (g.P + 1) + 1 + p;
+        }
+        // token row 0 of the image (cls_token + position row 0, HF:176-180): written once per image and column block,
+        // by the CTA that owns patch (0, 0)
+        if (tx == 0 && ty == 0 && rank == 0 && quarter == 0) {
+          float* dst = reinterpret_cast<float*>(g.out) + static_cast<size_t>(b) * (g.P + 1) * g.ldo;
+          for (int jj = lane; jj < Cfg::CG_COLS; jj += 32)
+            if (col0 + jj < g.N) dst[col0 + jj] = __ldg(g.cls + col0 + jj);
+        }
+      }
 
       // bias / layer-scale of this warp's columns -> smem, requested before the accumulator wait so the
       // global-load latency never sits in the per-chunk chain (CG_COLS <= 64 = 2 floats per lane)
       float* my_colop = sColOp + warp * 128;
-      if constexpr (EPI != EPI_PATCH) {
+      if constexpr (!epi_is_patch(EPI)) {
         const int cc = col0 + 2 * lane;
         const bool ok = 2 * lane < Cfg::CG_COLS && cc < g.N;
         float2 bb = make_float2(0.f, 0.f), ss = make_float2(1.f, 1.f);
@@ -458,7 +508,7 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
 #endif
         // per-column operands of this chunk (smem broadcast reads)
         float4 b4[4], s4[4];
-        if constexpr (EPI != EPI_PATCH) {
+        if constexpr (!epi_is_patch(EPI)) {
 #pragma unroll
           for (int j = 0; j < 4; ++j) {
             b4[j] = *reinterpret_cast<const float4*>(my_colop + c * kEpiCols + 4 * j);
@@ -545,7 +595,7 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
             *reinterpret_cast<float4*>(buf + lane * 64 + ((j ^ ((lane >> 1) & 3)) << 4)) = o[j];
         }
 
-        if constexpr (EPI == EPI_PATCH) {
+        if constexpr (epi_is_patch(EPI)) {
           // GEMM row b*P+p lands on token row b*(P+1)+1+p, plus position/conv-bias row p (HF:176-180)
           __syncwarp();
           if (col_ok) {
@@ -576,7 +626,7 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
       acc ^= 1;
       if (acc == 0) acc_phase ^= 1;
     }
-    if constexpr (EPI != EPI_PATCH) {
+    if constexpr (!epi_is_patch(EPI)) {
       if (lane == 0) tma_store_wait<0>();  // smem must stay valid until the last stores have read it
     }
   }

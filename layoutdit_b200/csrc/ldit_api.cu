@@ -499,6 +499,82 @@ int launch_mlp_t(const void* a, const void* W1, void* h, const void* W2, void* x
 
 #endif  // LDIT_EXPERIMENTAL
 
+// Patch embedding of 16-bit pixels with the A operand gathered by TMA (EPI_PATCH_TMA): ONE launch, no im2col scratch.
+template <int BN>
+int launch_patch_tma(const void* pixels, bool f16, const void* w, GemmArgs g, int B, int H, int W, cudaStream_t st) {
+  using Cfg = GemmCfg<BN, EPI_PATCH_TMA, 2>;
+  CUtensorMap tmA, tmB;
+  // pixels [B, 3, H, W] as (px 16 | patch column | py 16 | patch row | image x channel), strides (bytes, dims 1..4) increasing;
+  // one box = one pixel row of cv_tw x cv_th patches = 128 operand rows of 32 B
+  cuuint64_t dims[5] = {16, static_cast<cuuint64_t>(g.pe_gw), 16, static_cast<cuuint64_t>(g.pe_gh), static_cast<cuuint64_t>(B) * 3};
+  cuuint64_t strides[4] = {32, static_cast<cuuint64_t>(W) * 2, static_cast<cuuint64_t>(W) * 32, static_cast<cuuint64_t>(H) * W * 2};
+  cuuint32_t box[5] = {16, static_cast<cuuint32_t>(g.cv_tw), 1, static_cast<cuuint32_t>(g.cv_th), 1};
+  int rc = encode_cached(&tmA, f16 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT16 : CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 5, pixels, dims, strides, box,
+                         CU_TENSOR_MAP_SWIZZLE_32B);
+  if (rc) return rc;
+  rc = make_tmap_2d(&tmB, w, f16 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT16 : CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, g.N, g.K, g.K, Cfg::B_ROWS, 64,
+                    CU_TENSOR_MAP_SWIZZLE_128B);
+  if (rc) return rc;
+  return launch_gemm_maps<BN, EPI_PATCH_TMA, 2>(tmA, tmB, tmA, g, st);
+}
+
+// One launch with a TMA-gathered operand, or gather pass + CLS kernel + plain GEMM?  The TMA path tiles every image on
+// its own (a pair tile is a 16 x 16 rectangle of the patch grid: 196 of 256 rows are real at 224 x 224), the plain GEMM runs
+// over the dense [B P, 768] matrix but pays ~11 us for the gather pass.  Compare busiest-pair times in "columns"
+// (rounds x tile width, as pick_bn) with the gather pass worth ~224 of them (calibrated: base224 29 vs 33 us,
+// base512 57 vs 77 us for the TMA path, large224 45 vs 41 us against it).
+bool patch_tma_preferred(int B, int H, int W, int D) {
+  static const int force = [] { const char* e = getenv("LDIT_PATCH_TMA"); return e ? atoi(e) : -1; }();
+  if (force == 0) return false;
+  if (force == 2) return true;
+  const int Gh = H / 16, Gw = W / 16, units = num_sms() / 2;
+  auto cost = [&](long mblocks) {
+    const int bn = pick_bn(static_cast<int>(mblocks * 256), D, 2);
+    const long tiles = mblocks * ((D + bn - 1) / bn);
+    return ((tiles + units - 1) / units) * static_cast<long>(bn);
+  };
+  long best = -1;
+  const int tws[3] = {16, 8, 32};
+  for (int tw : tws) {
+    const int th = 128 / tw;
+    const long tiles = static_cast<long>((Gw + tw - 1) / tw) * ((Gh + 2 * th - 1) / (2 * th));
+    if (best < 0 || tiles < best) best = tiles;
+  }
+  const long dense = (static_cast<long>(B) * Gh * Gw + 255) / 256;
+  return cost(static_cast<long>(B) * best) <= cost(dense) + 224;
+}
+
+int patch_embed_tma(const void* pixels, bool f16, const void* w, const void* pos_bias, const void* cls_pos, void* x, int B, int H, int W,
+                    int D, cudaStream_t st) {
+  const int Gh = H / 16, Gw = W / 16;
+  GemmArgs g{};
+  g.N = D; g.K = 768;
+  g.out = x; g.ldo = D;
+  g.P = Gh * Gw;
+  g.posb = static_cast<const float*>(pos_bias);
+  g.cls = static_cast<const float*>(cls_pos);
+  g.pe_gw = Gw; g.pe_gh = Gh;
+  g.a_f16 = f16 ? 1 : 0;
+  // 128 patches per CTA as th rows x tw columns of the patch grid, the pair's second CTA below the first; fewest pair tiles wins
+  long best = -1;
+  const int tws[3] = {16, 8, 32};
+  for (int tw : tws) {
+    const int th = 128 / tw;
+    const long tiles = static_cast<long>((Gw + tw - 1) / tw) * ((Gh + 2 * th - 1) / (2 * th));
+    if (best < 0 || tiles < best) { best = tiles; g.cv_tw = tw; g.cv_th = th; }
+  }
+  g.cv_tx = (Gw + g.cv_tw - 1) / g.cv_tw;
+  g.cv_ty = (Gh + 2 * g.cv_th - 1) / (2 * g.cv_th);
+  g.num_m_blocks = B * g.cv_tx * g.cv_ty;
+  g.M = g.num_m_blocks * 256;   // rows of the tiled index space (patches outside the grid included)
+  const int bn = pick_bn(g.M, D, 2);
+  switch (bn) {
+    case 128: return launch_patch_tma<128>(pixels, f16, w, g, B, H, W, st);
+    case 192: return launch_patch_tma<192>(pixels, f16, w, g, B, H, W, st);
+    default: return launch_patch_tma<256>(pixels, f16, w, g, B, H, W, st);
+  }
+}
+
 }  // namespace
 
 extern "C" {
@@ -758,6 +834,10 @@ int ldit_patch_embed(const void* pixels, int pixel_dtype, const void* w, const v
   if (!aligned16(pixels) || !aligned16(scratch) || !aligned16(x) || !aligned16(cls_pos)) return LDIT_E_ALIGN;
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   const int Gh = H / 16, Gw = W / 16, P = Gh * Gw;
+  // 16-bit pixels (what the reference feeds on CUDA, R:trainer.py:155,168): TMA-fed im2col GEMM, one launch, scratch unused.
+  // fp32 pixels keep the cast / gather pass below (TMA cannot convert, and a tf32 MMA would halve the tensor rate).
+  if (gemm_ctas() == 2 && pixel_dtype == LDIT_DTYPE_BF16 && patch_tma_preferred(B, H, W, D))   // fp16 pixels: ldit_patch_embed_tma + fp16 weights
+    return patch_embed_tma(pixels, false, w, pos_bias, cls_pos, x, B, H, W, D, st);
   const size_t threads = static_cast<size_t>(B) * 3 * H * (W / 8);
   const unsigned blocks = static_cast<unsigned>((threads + 255) / 256);
   __nv_bfloat16* a = static_cast<__nv_bfloat16*>(scratch);
@@ -780,6 +860,21 @@ int ldit_patch_embed(const void* pixels, int pixel_dtype, const void* w, const v
   g.P = P;
   g.posb = static_cast<const float*>(pos_bias);
   return launch_gemm<EPI_PATCH>(scratch, w, g, st);
+}
+
+int ldit_patch_embed_tma_preferred(int B, int H, int W, int D) {
+  if (B <= 0 || H < 16 || W < 16 || D <= 0 || gemm_ctas() != 2) return 0;
+  return patch_tma_preferred(B, H, W, D) ? 1 : 0;
+}
+
+int ldit_patch_embed_tma(const void* pixels, int pixel_dtype, const void* w, const void* pos_bias, const void* cls_pos, void* x,
+                         int B, int H, int W, int D, void* stream) {
+  if (!pixels || !w || !pos_bias || !cls_pos || !x) return LDIT_E_NULL;
+  if (B <= 0 || H < 16 || W < 16 || (H % 16) || (W % 16) || D <= 0 || (D % 32)) return LDIT_E_SHAPE;
+  if (pixel_dtype != LDIT_DTYPE_F16 && pixel_dtype != LDIT_DTYPE_BF16) return LDIT_E_DTYPE;
+  if (!aligned16(pixels) || !aligned16(w) || !aligned16(x) || !aligned16(cls_pos) || !aligned16(pos_bias)) return LDIT_E_ALIGN;
+  if (gemm_ctas() != 2) return LDIT_E_UNSUPPORTED;
+  return patch_embed_tma(pixels, pixel_dtype == LDIT_DTYPE_F16, w, pos_bias, cls_pos, x, B, H, W, D, static_cast<cudaStream_t>(stream));
 }
 
 int ldit_patch_embed_pages(const void* const* pages, const int* page_hw, int max_page_w, int pixel_dtype, float mean0, float mean1,

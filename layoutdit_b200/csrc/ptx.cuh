@@ -202,6 +202,14 @@ __device__ __forceinline__ void tma_load_4d_cg2(void* smem_dst, const CUtensorMa
       ::"r"(smem_u32(smem_dst)), "l"(reinterpret_cast<uint64_t>(tm)), "r"(mbar_cluster_addr), "r"(c0), "r"(c1), "r"(c2), "r"(c3)
       : "memory");
 }
+// 5-D box: the patch-embedding gather (px, py, patch column, patch row, image x channel) straight out of an NCHW batch
+__device__ __forceinline__ void tma_load_5d_cg2(void* smem_dst, const CUtensorMap* tm, uint32_t mbar_cluster_addr, int c0, int c1,
+                                                int c2, int c3, int c4) {
+  asm volatile(
+      "cp.async.bulk.tensor.5d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6, %7}], [%2];"
+      ::"r"(smem_u32(smem_dst)), "l"(reinterpret_cast<uint64_t>(tm)), "r"(mbar_cluster_addr), "r"(c0), "r"(c1), "r"(c2), "r"(c3), "r"(c4)
+      : "memory");
+}
 __device__ __forceinline__ void tmem_alloc_cg2(uint32_t* smem_result, uint32_t ncols) {
   asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(smem_result)), "r"(ncols)
                : "memory");
@@ -329,6 +337,17 @@ __device__ __forceinline__ uint64_t umma_desc_kmajor_sw128(uint32_t smem_addr) {
   d |= static_cast<uint64_t>(1024 >> 4) << 32;              // [32,46) SBO
   d |= static_cast<uint64_t>(1) << 46;                      // [46,48) descriptor version (Blackwell)
   d |= static_cast<uint64_t>(2) << 61;                      // [61,64) SWIZZLE_128B
+  return d;
+}
+// K-major operand whose rows are only 32 B (16 bf16 = ONE UMMA_K step) with 32-byte swizzle: groups of 8 rows are
+// SBO = 256 B apart.  Used for the TMA-gathered patch-embedding operand, whose natural box row is one 16-pixel run.
+__device__ __forceinline__ uint64_t umma_desc_kmajor_sw32(uint32_t smem_addr) {
+  uint64_t d = 0;
+  d |= static_cast<uint64_t>((smem_addr & 0x3FFFFu) >> 4);
+  d |= static_cast<uint64_t>(1) << 16;
+  d |= static_cast<uint64_t>(256 >> 4) << 32;
+  d |= static_cast<uint64_t>(1) << 46;
+  d |= static_cast<uint64_t>(6) << 61;                      // SWIZZLE_32B
   return d;
 }
 // MN-major operand with 128-byte swizzle whose MN extent is exactly one 64-element atom

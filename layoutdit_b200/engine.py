@@ -131,6 +131,7 @@ class Engine:
         # and the add streams the residual through HBM twice.  Hence "auto": only when x and a are both inside the window.
         # LDIT_DEFER_RESID = 0 never, 1 auto (default), 2 always.
         self.defer_residual = int(os.environ.get("LDIT_DEFER_RESID", "1"))
+        self.patch_tma = os.environ.get("LDIT_PATCH_TMA", "1") != "0"   # fp16 pages: TMA-fed patch GEMM (bf16 pages: inside the library)
 
     # ------------------------------------------------------------------ weight packing
     def _weights_key(self):
@@ -158,6 +159,8 @@ class Engine:
             e = P.embeddings
             D = cfg.hidden_size
             self.w_patch = bf16(e.patch_embeddings.projection.weight.reshape(D, -1))
+            # fp16 copy for fp16 pages (what the reference feeds on CUDA): the TMA-fed patch GEMM needs both operands in one type
+            self.w_patch_f16 = e.patch_embeddings.projection.weight.detach().reshape(D, -1).to(dev, torch.float16).contiguous()
             self.b_patch = f32(e.patch_embeddings.projection.bias)
             self.cls = f32(e.cls_token.reshape(D))
             self.pos = None if e.position_embeddings is None else f32(e.position_embeddings)
@@ -319,6 +322,10 @@ class Engine:
             plan = [("ldit_patch_embed_pages", lib.ldit_patch_embed_pages,
                      (x.ptrs.data_ptr(), x.hw.data_ptr(), x.max_w, _DTYPE_CODE[x.dtype], *x.mean, *x.std, self.w_patch.data_ptr(),
                       geo.pos_bias.data_ptr(), geo.cls_pos.data_ptr(), big, xr, B, geo.H, geo.W, D, stream))]
+        elif x.dtype == torch.float16 and self.patch_tma and lib.ldit_patch_embed_tma_preferred(B, geo.H, geo.W, D):
+            plan = [("ldit_patch_embed_tma", lib.ldit_patch_embed_tma,
+                     (x.data_ptr(), _DTYPE_CODE[x.dtype], self.w_patch_f16.data_ptr(), geo.pos_bias.data_ptr(),
+                      geo.cls_pos.data_ptr(), xr, B, geo.H, geo.W, D, stream))]
         else:
             plan = [("ldit_patch_embed", lib.ldit_patch_embed,
                      (x.data_ptr(), _DTYPE_CODE[x.dtype], self.w_patch.data_ptr(), geo.pos_bias.data_ptr(),

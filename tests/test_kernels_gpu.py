@@ -112,8 +112,11 @@ def test_gemm_rejects_bad_arguments(lib):
 
 # ---------------------------------------------------------------------------- patch embed
 @pytest.mark.parametrize("dtype", [torch.float32, torch.float16, torch.bfloat16])
-@pytest.mark.parametrize("B,H,W,D", [(2, 64, 96, 128), (3, 224, 224, 768)])
+@pytest.mark.parametrize("B,H,W,D", [(2, 64, 96, 128), (3, 224, 224, 768), (1, 80, 112, 128), (2, 512, 512, 768), (1, 16, 16, 128),
+                                     (5, 320, 224, 1024)])
 def test_patch_embed(lib, B, H, W, D, dtype):
+    """fp32 pixels: cast / gather pass + GEMM; fp16 / bf16 pixels: ONE kernel whose A operand is gathered by 5-D TMA boxes
+    straight out of the NCHW batch (fp16 pixels stay fp16 in the MMA, the weights bf16), CLS rows included."""
     lib.ldit_set_gemm_cta_pair(2)
     lib.ldit_set_gemm_tile_n(0)
     g = torch.Generator(device="cuda").manual_seed(B * H + W)
@@ -127,11 +130,18 @@ def test_patch_embed(lib, B, H, W, D, dtype):
     cls_pos = (cls + pos[0]).contiguous()
     scratch = torch.empty(lib.ldit_patch_embed_scratch_bytes(B, H, W) // 2, device="cuda", dtype=torch.bfloat16)
     x = torch.full((B, P + 1, D), float("nan"), device="cuda")
-    _lib.check(lib.ldit_patch_embed(px.data_ptr(), {torch.float32: 0, torch.float16: 1, torch.bfloat16: 2}[dtype],
-                                    w.reshape(D, -1).data_ptr(), pos_bias.data_ptr(), cls_pos.data_ptr(),
-                                    scratch.data_ptr(), x.data_ptr(), B, H, W, D, _stream()), "patch_embed")
-    pxr = px.to(torch.bfloat16).float()                      # the kernel's A operand is bf16
-    tok = F.conv2d(pxr, w.float(), cb, stride=16).flatten(2).transpose(1, 2)
+    code = {torch.float32: 0, torch.float16: 1, torch.bfloat16: 2}[dtype]
+    wf = w.float()
+    if dtype == torch.float16:     # the TMA-fed GEMM wants both operands in one 16-bit type: an fp16 copy of the weights
+        w16 = w.float().to(torch.float16)
+        wf = w16.float()
+        _lib.check(lib.ldit_patch_embed_tma(px.data_ptr(), code, w16.reshape(D, -1).data_ptr(), pos_bias.data_ptr(), cls_pos.data_ptr(),
+                                            x.data_ptr(), B, H, W, D, _stream()), "patch_embed_tma")
+    else:
+        _lib.check(lib.ldit_patch_embed(px.data_ptr(), code, w.reshape(D, -1).data_ptr(), pos_bias.data_ptr(), cls_pos.data_ptr(),
+                                        scratch.data_ptr(), x.data_ptr(), B, H, W, D, _stream()), "patch_embed")
+    pxr = px.float() if dtype == torch.float16 else px.to(torch.bfloat16).float()   # A operand: fp16 as given, else bf16
+    tok = F.conv2d(pxr, wf, cb, stride=16).flatten(2).transpose(1, 2)
     ref = torch.cat([cls.expand(B, 1, D), tok], dim=1) + pos
     torch.testing.assert_close(x, ref, rtol=1e-4, atol=2e-3)
 
