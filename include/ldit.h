@@ -60,6 +60,10 @@ int ldit_gemm_bias_gelu(const void* A, const void* W, const void* bias, void* ou
  * scale may be NULL (layer_scale_init_value <= 0, HF:462-467). */
 int ldit_gemm_bias_scale_residual(const void* A, const void* W, const void* bias, const void* scale, void* x, int M, int N,
                                   int K, void* stream);
+/* (The branch scale (.) (A x W^T + bias) is rounded to bf16 before it is added: x then receives bit for bit what the two-step
+ * form below adds, so the forward's numbers do not depend on which form a geometry uses.)
+ * Plain accumulation without bias, scale or rounding, acc f32 [M, N] += A x W^T: the wgrad GEMMs of the backward. */
+int ldit_gemm_accumulate(const void* A, const void* W, void* acc, int M, int N, int K, void* stream);
 
 /* The same residual block in two steps, for a residual stream that is about to be normalised anyway:
  *   ldit_gemm_bias_scale:  out bf16 [M, N] = scale (.) (A x W^T + bias)          (the layer-scaled branch; scale may be NULL)

@@ -19,6 +19,7 @@ SIGNATURES = {
     "ldit_gemm_bias": (_i, [_vp, _vp, _vp, _vp, _i, _i, _i, _vp]),
     "ldit_gemm_bias_gelu": (_i, [_vp, _vp, _vp, _vp, _i, _i, _i, _vp]),
     "ldit_gemm_bias_scale_residual": (_i, [_vp, _vp, _vp, _vp, _vp, _i, _i, _i, _vp]),
+    "ldit_gemm_accumulate": (_i, [_vp, _vp, _vp, _i, _i, _i, _vp]),
     "ldit_gemm_bias_scale": (_i, [_vp, _vp, _vp, _vp, _vp, _i, _i, _i, _vp]),
     "ldit_add_layernorm": (_i, [_vp, _vp, _vp, _vp, _vp, _i, _i, _f, _vp]),
     "ldit_transpose_bf16": (_i, [_vp, _vp, _i, _i, _i, _vp]),

@@ -63,6 +63,9 @@ struct GemmArgs {
   int a_f16;           // both operands fp16 (pixels as the reference feeds them under autocast + an fp16 copy of the weights)
   const float* cls;    // [N] fp32 = cls_token + position row 0, written to token row 0 of every image
   int num_m_blocks, num_n_blocks;
+  int round_bf16;      // EPI_SCALE_RESID: round scale * (acc + bias) to bf16 before the fp32 reduce-add, so that the residual stream
+                       // gets bit for bit what the deferred form (EPI_BIAS_SCALE + add_layernorm_kernel) adds -- the forward's
+                       // numbers then do not depend on which of the two forms a geometry uses.  0 for the wgrad accumulation.
   int m_reverse;       // 1: row blocks are visited last-to-first (consume a just-written A operand freshest-first, see ldit_api.cu)
   // EPI_CONV_BIAS (3x3 convolution, stride 1, zero padding 1, over a channels-last image [B, H, W, Cin] as an
   // implicit GEMM): a CTA's 128 rows are a cv_th x cv_tw patch of output pixels, a CTA pair covers two patches
@@ -580,6 +583,11 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
               o[j].y = s4[j].y * (o[j].y + b4[j].y);
               o[j].z = s4[j].z * (o[j].z + b4[j].z);
               o[j].w = s4[j].w * (o[j].w + b4[j].w);
+              if (g.round_bf16) {
+                const uint32_t lo = pack_bf16x2(o[j].x, o[j].y), hi = pack_bf16x2(o[j].z, o[j].w);
+                o[j] = make_float4(__uint_as_float(lo << 16), __uint_as_float(lo & 0xffff0000u), __uint_as_float(hi << 16),
+                                   __uint_as_float(hi & 0xffff0000u));
+              }
             }
             if constexpr (EPI == EPI_CONV_BIAS_F32) {
               o[j].x += b4[j].x; o[j].y += b4[j].y; o[j].z += b4[j].z; o[j].w += b4[j].w;

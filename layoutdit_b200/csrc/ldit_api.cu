@@ -770,7 +770,15 @@ int ldit_gemm_bias_scale_residual(const void* A, const void* W, const void* bias
   // base224), the rows still resident are consumed first.  Measured neutral (2.62 vs 2.64 ms/step): off.
   static const int rev = [] { const char* e = getenv("LDIT_FC2_REVERSE"); return e ? atoi(e) : 0; }();
   g.m_reverse = (rev && K > N) ? 1 : 0;
+  g.round_bf16 = 1;   // same contribution, bit for bit, as ldit_gemm_bias_scale + ldit_add_layernorm
   return launch_gemm<EPI_SCALE_RESID>(A, W, g, static_cast<cudaStream_t>(stream));
+}
+
+int ldit_gemm_accumulate(const void* A, const void* W, void* acc, int M, int N, int K, void* stream) {
+  GemmArgs g{};
+  g.M = M; g.N = N; g.K = K;
+  g.out = acc; g.ldo = N;
+  return launch_gemm<EPI_SCALE_RESID>(A, W, g, static_cast<cudaStream_t>(stream));   // unrounded fp32 reduce-add
 }
 
 #ifdef LDIT_EXPERIMENTAL

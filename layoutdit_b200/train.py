@@ -61,8 +61,7 @@ class _K:
         """acc f32 [M, N] += a [M, K] x w [N, K]^T  (the wgrad form: fp32 reduce-add epilogue)."""
         M, K = a.shape
         N = w.shape[0]
-        _lib.check(self.lib.ldit_gemm_bias_scale_residual(a.data_ptr(), w.data_ptr(), None, None, acc.data_ptr(), M, N, K, _st(self.dev)),
-                   "ldit_gemm_bias_scale_residual")
+        _lib.check(self.lib.ldit_gemm_accumulate(a.data_ptr(), w.data_ptr(), acc.data_ptr(), M, N, K, _st(self.dev)), "ldit_gemm_accumulate")
 
     def attention(self, qkv, B, N, heads, Gh, Gw):
         D = heads * 64

@@ -94,13 +94,31 @@ def test_gemm_bias_scale_residual(lib, M, N, K, with_scale, ctas):
     A, W, bias = _gemm_inputs(M, N, K, 11)
     g = torch.Generator(device="cuda").manual_seed(5)
     x = torch.randn(M, N, device="cuda", generator=g)
+    x0 = x.clone()
     scale = torch.rand(N, device="cuda", generator=g) + 0.05 if with_scale else None
     ref = x + (scale if with_scale else 1.0) * (A.float() @ W.float().t() + bias)
     _lib.check(lib.ldit_gemm_bias_scale_residual(A.data_ptr(), W.data_ptr(), bias.data_ptr(),
                                                  scale.data_ptr() if with_scale else None, x.data_ptr(), M, N, K, _stream()),
                "gemm")
-    # fp32 output: only accumulation-order noise over K bf16 products
-    torch.testing.assert_close(x, ref, rtol=1e-4, atol=2e-3)
+    # the branch is rounded to bf16 before it is added (so that this call and ldit_gemm_bias_scale + ldit_add_layernorm agree
+    # bit for bit): half a bf16 ulp of the branch on top of the accumulation-order noise over K bf16 products
+    branch = ref - x0
+    torch.testing.assert_close(x, x0 + branch.to(torch.bfloat16).float(), rtol=1e-4, atol=2e-3 + 2 ** -7 * float(branch.abs().max()))   # a rounding boundary may flip: one bf16 ulp
+    assert _rel_fro(x - x0, branch) < 4e-3
+    # ... and it is the same contribution, bit for bit, as the two-step form
+    x2 = x0.clone()
+    br = torch.empty(M, N, device="cuda", dtype=torch.bfloat16)
+    _lib.check(lib.ldit_gemm_bias_scale(A.data_ptr(), W.data_ptr(), bias.data_ptr(), scale.data_ptr() if with_scale else None,
+                                        br.data_ptr(), M, N, K, _stream()), "gemm")
+    if N % 128 == 0:
+        ones, zeros = torch.ones(N, device="cuda"), torch.zeros(N, device="cuda")
+        y = torch.empty(M, N, device="cuda", dtype=torch.bfloat16)
+        _lib.check(lib.ldit_add_layernorm(x2.data_ptr(), br.data_ptr(), ones.data_ptr(), zeros.data_ptr(), y.data_ptr(), M, N, 1e-12, _stream()), "add_ln")
+        assert torch.equal(x2, x)
+    # the unrounded accumulate used by the wgrad GEMMs
+    acc = x0.clone()
+    _lib.check(lib.ldit_gemm_accumulate(A.data_ptr(), W.data_ptr(), acc.data_ptr(), M, N, K, _stream()), "gemm")
+    torch.testing.assert_close(acc, x0 + A.float() @ W.float().t(), rtol=1e-4, atol=2e-3)
 
 
 def test_gemm_rejects_bad_arguments(lib):
