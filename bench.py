@@ -466,10 +466,27 @@ def extra_config(name, fac, global_batch, H, W, dev, rank, world, peaks, flush, 
            "model_tflops": round(fl * value / 1e12, 1),
            "model_frac_of_peak": round(fl * value / 1e12 / (world * peaks["bf16_tflops"]), 4), "steps": steps,
            "launches_per_step": run.launches}
-    if rank == 0 and world == 1:
+    if world > 1:
+        # what the shard costs with no exchange at all (every rank runs it, rank 0's figure is reported): the gap to
+        # ms_per_step is the p5 gather + rank skew, the gap to (N=1 time / world) is the small-batch kernel efficiency
+        for _ in range(warmup):
+            run.model(run.x_dev)
+        torch.cuda.synchronize(dev); dist.barrier()
+        ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(steps)]
+        for s_, e_ in ev:
+            flush.zero_()
+            s_.record(); run.model(run.x_dev); e_.record()
+        torch.cuda.synchronize(dev); dist.barrier()
+        out["shard_ms_per_step_no_gather"] = round(sum(a.elapsed_time(b) for a, b in ev) / steps, 4)
+    if rank == 0:
         rows, _ = kernel_table(run.eng, run.eng._geometry(b_local, H, W), run.x_dev, dev, peaks, reps=2)
         dom = max(rows, key=lambda r: r["us_per_step"])
         out["dominant_kernel"] = {k: dom[k] for k in dom}
+        if world > 1:
+            out["shard_kernels"] = [{k: r[k] for k in r if k in ("kernel", "launches_per_step", "us", "us_per_step",
+                                                                   "frac_of_burst_peak", "frac_of_hbm_peak")} for r in rows]
+    if world > 1:
+        dist.barrier()
     del run
     torch.cuda.empty_cache()
     return out
