@@ -352,6 +352,34 @@ def library_ops(cfg, B, H, W, dev, ours):
     out["layer_norm_f32_in_bf16_out_us"] = round(t(lambda: F.layer_norm(x32, (D,), g_.float(), b_.float(), 1e-12).to(torch.bfloat16)), 2)
     out["gelu_bf16_us"] = round(t(lambda: F.gelu(hbuf)), 2)
     out["ours_us"] = ours
+    # our entry points timed the SAME way (20 back-to-back calls, warm L2, no per-launch events): the like-for-like column
+    from layoutdit_b200 import _lib
+    lib = _lib.load()
+    st = torch.cuda.current_stream(dev).cuda_stream
+    f32 = dict(device=dev, dtype=torch.float32)
+    b2b = {}
+    for key, (n, k, src) in {"qkv": (3 * D, D, a), "proj": (D, D, a), "fc1": (I, D, a), "fc2": (D, I, hbuf)}.items():
+        w = torch.randn(n, k, **bf) * 0.02; b = torch.randn(n, **f32); lam = torch.full((n,), 0.1, **f32)
+        o = torch.empty(M, n, **bf)
+        if key == "qkv":
+            fn = lambda: lib.ldit_gemm_bias(src.data_ptr(), w.data_ptr(), b.data_ptr(), o.data_ptr(), M, n, k, st)
+        elif key == "fc1":
+            fn = lambda: lib.ldit_gemm_bias_gelu(src.data_ptr(), w.data_ptr(), b.data_ptr(), o.data_ptr(), M, n, k, st)
+        else:
+            fn = lambda: lib.ldit_gemm_bias_scale(src.data_ptr(), w.data_ptr(), b.data_ptr(), lam.data_ptr(), o.data_ptr(), M, n, k, st)
+        _lib.check(fn(), key)
+        b2b[f"gemm_{key}_us"] = round(t(fn), 2)
+    Gh, Gw = H // 16, W // 16
+    qkv2 = torch.randn(M, 3 * D, **bf); ctx = torch.empty(M, D, **bf)
+    fn = lambda: lib.ldit_attention(qkv2.data_ptr(), ctx.data_ptr(), None, B, N, h, Gh, Gw, st)
+    _lib.check(fn(), "attention"); b2b["attention_us"] = round(t(fn), 2)
+    table = torch.randn(h, (2 * Gh - 1) * (2 * Gw - 1) + 3, **f32)
+    fn = lambda: lib.ldit_attention(qkv2.data_ptr(), ctx.data_ptr(), table.data_ptr(), B, N, h, Gh, Gw, st)
+    _lib.check(fn(), "attention+bias"); b2b["attention_relpos_bias_us"] = round(t(fn), 2)
+    gam, bet, y = torch.ones(D, **f32), torch.zeros(D, **f32), torch.empty(M, D, **bf)
+    fn = lambda: lib.ldit_layernorm(x32.data_ptr(), gam.data_ptr(), bet.data_ptr(), y.data_ptr(), M, D, 1e-12, st)
+    _lib.check(fn(), "layernorm"); b2b["layernorm_f32_in_bf16_out_us"] = round(t(fn), 2)
+    out["ours_back_to_back_us"] = b2b
     return out
 
 
@@ -374,6 +402,17 @@ def hf_gpu_baseline(cfg, B, H, W, dev, seed_pages, steps=8):
     return {"value": round(B / (ms / 1e3), 1), "unit": "images/s", "ms_per_step": round(ms, 3), "steps": steps,
             "what": "transformers BeitModel wrapped as R:dit_backbone.py:38-62, torch %s bf16 eager (cuBLASLt / SDPA / ATen), "
                     "same batch, weights and pages, device-resident, 4 taps computed" % torch.__version__}
+
+
+GATHER_TEXT = {
+    "none": "none",
+    "peer": "p5 taps gathered on every rank each step by copy-engine pulls out of symmetric memory over NVLink "
+            "(layoutdit_b200.sharding.PeerGather: no SM taken) on a side stream, under the next step's kernels "
+            "(the last one inside the timed region)",
+    "nccl": "p5 taps all-gathered over NCCL every step on the compute stream, behind the forward",
+    "nccl-side": "p5 taps all-gathered over NCCL every step on a side stream, under the next step's kernels "
+                 "(the last one inside the timed region)",
+}
 
 
 class DeviceRun:
@@ -400,18 +439,55 @@ class DeviceRun:
         self.stage = [torch.empty_like(p5.contiguous()) for _ in range(2)] if world > 1 else None
         self.gath_ev = [None, None]
         self.i = 0
+        # how the p5 taps are exchanged (LDIT_BENCH_GATHER): "peer" = copy-engine pulls out of symmetric memory on a side
+        # stream (sharding.PeerGather; the default when the node offers it), "nccl" = NCCL all-gather on the compute
+        # stream behind the forward, "nccl-side" = NCCL all-gather on a side stream under the next step's kernels
+        self.gather_mode, self.peer = "none", None
+        if world > 1:
+            import torch.distributed as dist
+            from layoutdit_b200.sharding import PeerGather
+            want = os.environ.get("LDIT_BENCH_GATHER", "peer")
+            ok = 0
+            if want == "peer":
+                try:
+                    self.peer = PeerGather(tuple(p5.shape), p5.dtype, dev)
+                    ok = 1
+                except Exception as e:   # symmetric memory unavailable on this node / in this container
+                    print(f"[bench] rank {rank}: peer-copy gather unavailable ({type(e).__name__}: {e}); NCCL instead", file=sys.stderr)
+            flag = torch.tensor([ok], device=dev)
+            dist.all_reduce(flag, op=dist.ReduceOp.MIN)
+            if want == "peer" and int(flag.item()) == 1:
+                self.gather_mode = "peer"
+            else:
+                self.peer = None
+                self.gather_mode = "nccl-side" if want == "nccl-side" else "nccl"
 
     def step(self, model=None, x=None):
-        """forward; for N > 1 the p5 taps are all-gathered (layoutdit_b200.sharding.gather_tap) on a side stream, under
-        the next step's kernels (the taps are copied out of the graph's static output first, 4.8 MB device to device)."""
+        """forward; for N > 1 the p5 taps are gathered on every rank (see ``gather_mode``); the side-stream modes run the
+        exchange under the next step's kernels (the taps are copied out of the graph's static output first, 4.8 MB)."""
         feats = (model or self.model)(self.x_dev if x is None else x)
         if self.world > 1:
             from layoutdit_b200.sharding import gather_tap
             cur = torch.cuda.current_stream(self.dev)
+            p5 = feats["p5"].permute(0, 2, 3, 1)
+            if self.gather_mode == "nccl":
+                self.gathered = gather_tap(feats["p5"])
+                return feats
             k = self.i & 1
+            if self.gather_mode == "peer":
+                ready, staged = torch.cuda.Event(), torch.cuda.Event()
+                ready.record(cur)
+                with torch.cuda.stream(self.side):
+                    self.side.wait_event(ready)
+                    self.peer.stage_in(p5)
+                    staged.record(self.side)
+                    self.gathered = self.peer.exchange()
+                cur.wait_event(staged)      # the next forward rewrites the static p5 output: only after it has been staged
+                self.i += 1
+                return feats
             if self.gath_ev[k] is not None:
                 cur.wait_event(self.gath_ev[k])             # the gather two steps back has read this staging buffer
-            self.stage[k].copy_(feats["p5"].permute(0, 2, 3, 1), non_blocking=True)
+            self.stage[k].copy_(p5, non_blocking=True)
             ready = torch.cuda.Event(); ready.record(cur)
             with torch.cuda.stream(self.side):
                 self.side.wait_event(ready)
@@ -570,12 +646,26 @@ def main():
     e2e_model.dit.load_state_dict(model.dit.state_dict())
     e2e_model.pretrained = False
     gathered = torch.empty(world * p5_flat(feats0).numel(), dtype=torch.bfloat16, device=dev) if world > 1 else None
+    peer_e2e = None
+    if run.gather_mode == "peer":
+        from layoutdit_b200.sharding import PeerGather
+        peer_e2e = PeerGather(tuple(feats0["p5"].permute(0, 2, 3, 1).shape), torch.bfloat16, dev)
 
     def step_e2e(i):
         # the call a user makes for host-resident pages: H2D of this step's pages, forward, D2H of its result
         # (forward_host keeps the PCIe copies on their own streams, under the neighbouring steps' kernels)
         f, done = e2e_model.forward_host(host_in[i & 1], host_out[i & 1], "p5")
-        if world > 1:
+        if peer_e2e is not None:
+            cur = torch.cuda.current_stream(dev)
+            ready, staged = torch.cuda.Event(), torch.cuda.Event()
+            ready.record(cur)
+            with torch.cuda.stream(run.side):
+                run.side.wait_event(ready)
+                peer_e2e.stage_in(f["p5"].permute(0, 2, 3, 1))
+                staged.record(run.side)
+                peer_e2e.exchange()
+            cur.wait_event(staged)                  # the slot's outputs are rewritten two steps on: not before p5 is staged
+        elif world > 1:
             dist.all_gather_into_tensor(gathered, p5_flat(f))
         return done
 
@@ -588,6 +678,7 @@ def main():
     for i in range(args.steps):
         done = step_e2e(i)
     torch.cuda.current_stream(dev).wait_event(done)      # the last step's result has reached the host buffer
+    run.join()                                           # ... and the last gathers have landed
     e1.record()
     barrier()
     e2e_ms = torch.tensor([e0.elapsed_time(e1)], dtype=torch.float64, device=dev)
@@ -693,8 +784,7 @@ def main():
                                    f"random-init (HF init, seed 0) weights, 4 taps written",
                        "global_batch": world * B, "l2": "256 MiB buffer written between timed steps (outside the events)",
                        "parallelism": f"dp{world}",
-                       "gather": "p5 taps all-gathered over NCCL every step on a side stream, under the next step's kernels "
-                                 "(the last one inside the timed region)" if world > 1 else "none",
+                       "gather": GATHER_TEXT[run.gather_mode],
                        "timing": ("CUDA-graph replay" if args.graph else "stream launches with programmatic dependent launch (PDL)")
                                  + "; per-step CUDA events summed; max over ranks"},
             "model_tflops": round(model_tflops, 1),

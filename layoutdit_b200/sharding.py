@@ -57,3 +57,48 @@ def gather_tap(tap: torch.Tensor, group=None) -> torch.Tensor:
         dist.all_gather_into_tensor(buf, padded, group=group)
         out = torch.cat([buf[r * m: r * m + n] for r, n in enumerate(sizes)], dim=0)
     return out.permute(0, 3, 1, 2)
+
+
+class PeerGather:
+    """All-gather of one fixed-shape tap by PEER COPIES over NVLink instead of a NCCL kernel.
+
+    Every rank stages its shard in a symmetric-memory buffer (``torch.distributed._symmetric_memory``: the same
+    allocation mapped into every rank of the node), the ranks meet in a signal-pad barrier (one tiny kernel), each rank
+    PULLS the other shards with plain device-to-device copies -- executed by the copy engines, no SM is taken -- and a
+    second barrier releases the staging buffers.  This matters because the forward is a sequence of persistent
+    kernels that own all 148 SMs: a NCCL kernel running beside them on a side stream displaces some of their CTAs and a
+    persistent kernel that loses an SM runs its static tile schedule in two waves (measured: the overlapped NCCL gather
+    cost +14 % per step on 8 GPUs where the same gather on the compute stream cost +2.5 %).
+
+    One node only (NVLink / NVSwitch peers), equal shard shapes on every rank.  Construction is collective; it raises if
+    symmetric memory is unavailable and the caller falls back to :func:`gather_tap`."""
+
+    def __init__(self, shard_shape, dtype, device, group=None):
+        import torch.distributed._symmetric_memory as symm_mem
+        group = group or dist.group.WORLD
+        self.world = dist.get_world_size(group)
+        self.rank = dist.get_rank(group)
+        self.shape, self.dtype = tuple(shard_shape), dtype
+        self.stage = symm_mem.empty(self.shape, dtype=dtype, device=device)
+        self.handle = symm_mem.rendezvous(self.stage, group.group_name)
+        self.out = torch.empty((self.world * self.shape[0],) + self.shape[1:], dtype=dtype, device=device)
+        self.peers = [self.handle.get_buffer(r, self.shape, dtype) for r in range(self.world)]
+
+    def stage_in(self, shard: torch.Tensor) -> None:
+        """Copy this rank's [b, ...] block into its symmetric staging buffer (current stream)."""
+        self.stage.copy_(shard)
+
+    def exchange(self) -> torch.Tensor:
+        """Barrier, pull every rank's staged block, barrier (current stream); returns [world*b, ...], valid until the
+        next call."""
+        self.handle.barrier()                        # every rank's shard is staged
+        chunks = self.out.chunk(self.world)
+        for step in range(self.world):
+            r = (self.rank - step) % self.world      # start with the local shard, spread the pulls over the peers
+            chunks[r].copy_(self.peers[r])
+        self.handle.barrier()                        # every rank has read every staging buffer: they may be rewritten
+        return self.out
+
+    def __call__(self, shard: torch.Tensor) -> torch.Tensor:
+        self.stage_in(shard)
+        return self.exchange()

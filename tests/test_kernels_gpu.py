@@ -191,7 +191,9 @@ def _dense_bias(table_t, Gh, Gw):
 @pytest.mark.parametrize("qk_scale", [1.5, 6.0])
 @pytest.mark.parametrize("with_bias", [False, True])
 @pytest.mark.parametrize("B,heads,Gh,Gw", [(2, 2, 4, 4), (3, 12, 14, 14), (2, 4, 14, 20), (1, 3, 32, 32), (2, 2, 5, 7),
-                                           (1, 2, 13, 16), (2, 1, 1, 1)])
+                                           (1, 2, 13, 16), (2, 1, 1, 1),
+                                           # N % 128 in 1..4: the rows past the last full tile take the CUDA-core tail path
+                                           (2, 2, 16, 16), (1, 2, 16, 8), (2, 1, 43, 3), (1, 2, 131, 1), (3, 5, 32, 16)])
 def test_attention(lib, B, heads, Gh, Gw, with_bias, qk_scale, impl):
     """impl 0 = the product kernel (attention_v3); 1 / 2 / 4 = the superseded variants of -DLDIT_EXPERIMENTAL builds.
     qk_scale 6 gives logits of +-100 and rows whose maximum jumps by far more than 2^8 between key tiles: the lazy
