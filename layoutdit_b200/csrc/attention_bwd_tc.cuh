@@ -1,0 +1,284 @@
+// Attention backward on the tensor cores (tcgen05 / TMEM), head_dim 64, up to 256 tokens per image:
+//     dQ, dK, dV  from  Q, K, V (the forward's fused QKV buffer [B, N, 3D]) and dO = d ctx [B, N, D]
+// for ctx = softmax(q k^T / 8) v, HF:249-306.  One CTA per (image, head); P is recomputed, nothing but QKV is
+// needed from the forward:
+//     S = Q K^T            P = softmax(S / 8)          delta_i = sum_j P_ij dP_ij
+//     dP = dO V^T          dS = P (.) (dP - delta) / 8
+//     dV = P^T dO          dK = dS^T Q                  dQ = dS K
+// All five products are tcgen05.mma with fp32 accumulators in TMEM; the element-wise part runs with thread <-> query
+// row, exactly as in the forward kernel.  Work is cut into (query tile t, key half kh) blocks of 128 x 128:
+//   TMEM columns   [0,128) S(t,kh)   [128,256) dP(t,kh)   [256,320) dV(kh)   [320,384) dK(kh)   [384,448) dQ(0)   [448,512) dQ(1)
+//   shared memory  Q, K, V, dO as two 128 x 64 K-major tiles each (TMA, 128-byte swizzle; the same tiles serve as
+//                  MN-major B operands where the contraction runs over their rows), P^T and dS^T as [128 keys x 128
+//                  rows] K-major (written transposed by the row threads), dS as [128 rows x 128 keys] K-major
+// A statistics pre-pass computes S and dP for the whole row (all 512 columns are free then) and leaves the row max,
+// 1 / row sum and delta in registers; the main pass loops kh (outer: dV / dK of one key half stay in TMEM) over t.
+// 8 warps: warp w owns TMEM lanes 32 (w & 3) .. +32 and the 16-column chunks c with (c & 1) == (w >> 2).
+// Correctness-first scheduling (no overlap of MMA and element-wise phases): this kernel replaces a CUDA-core
+// version that took 10.7 ms per layer at B = 64, N = 197; it is not tuned beyond that.
+#pragma once
+
+#include "ptx.cuh"
+
+namespace ldit {
+
+struct AttnBwdArgs {
+  const __nv_bfloat16* qkv;
+  __nv_bfloat16* dqkv;
+  int B, N, heads, D;
+  float scale_log2e, scale;
+};
+
+constexpr int kAbtThreads = 256;
+constexpr int kAbtTile = 16384;                         // one 128 x 64 bf16 tile
+constexpr int kAbtSmemTiles = 14 * kAbtTile;            // Q, K, V, dO (2 each) + P^T, dS^T, dS (2 atoms each)
+constexpr int kAbtTmemCols = 512;
+
+// element (row r, column c) of a [128 x 64] bf16 tile with rows of 128 B and the 128-byte swizzle: byte offset
+__device__ __forceinline__ uint32_t abt_sw128(int r, int c) {
+  return static_cast<uint32_t>(r * 128 + ((((c >> 3) ^ (r & 7)) << 4) | ((c & 7) << 1)));
+}
+
+__global__ void __launch_bounds__(kAbtThreads, 1)
+attention_bwd_tc_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_constant__ CUtensorMap tmDO, const AttnBwdArgs a) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint8_t* sQ = smem;                       // [t]
+  uint8_t* sK = smem + 2 * kAbtTile;        // [kh]
+  uint8_t* sV = smem + 4 * kAbtTile;        // [kh]
+  uint8_t* sDO = smem + 6 * kAbtTile;       // [t]
+  uint8_t* sPT = smem + 8 * kAbtTile;       // [row atom]: 128 keys x 64 rows
+  uint8_t* sDST = smem + 10 * kAbtTile;     // [row atom]
+  uint8_t* sDS = smem + 12 * kAbtTile;      // [key atom]: 128 rows x 64 keys
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + kAbtSmemTiles);
+  uint64_t* bar_load = bars;
+  uint64_t* bar_mma = bars + 1;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int quarter = warp & 3, half = warp >> 2;
+  const int row = quarter * 32 + lane;                   // row of a 128-row tile = TMEM lane
+  const int b = blockIdx.x / a.heads, h = blockIdx.x % a.heads;
+  const int NT = (a.N + 127) / 128;                      // query tiles = key halves (1 or 2)
+
+  if (threadIdx.x == 0) {
+    mbar_init(bar_load, 1);
+    mbar_init(bar_mma, 1);
+    fence_barrier_init();
+    fence_proxy_async_smem();
+    tma_prefetch_desc(&tmQKV);
+    tma_prefetch_desc(&tmDO);
+  }
+  if (warp == 1) {
+    tmem_alloc(tmem_slot, kAbtTmemCols);
+    tmem_relinquish();
+  }
+  tcgen05_fence_before();
+  __syncthreads();
+  tcgen05_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+  const uint32_t lane_addr = tmem_base + (static_cast<uint32_t>(quarter * 32) << 16);
+
+  if (threadIdx.x == 0) {
+    mbar_arrive_expect_tx(bar_load, static_cast<uint32_t>(NT) * 4u * kAbtTile);
+    for (int t = 0; t < NT; ++t) {
+      tma_load_3d(sQ + t * kAbtTile, &tmQKV, bar_load, h * 64, t * 128, b);
+      tma_load_3d(sK + t * kAbtTile, &tmQKV, bar_load, a.D + h * 64, t * 128, b);
+      tma_load_3d(sV + t * kAbtTile, &tmQKV, bar_load, 2 * a.D + h * 64, t * 128, b);
+      tma_load_3d(sDO + t * kAbtTile, &tmDO, bar_load, h * 64, t * 128, b);
+    }
+  }
+  mbar_wait(bar_load, 0);
+  tcgen05_fence_after();
+
+  constexpr uint32_t idesc_s = umma_idesc_bf16(128, 128, 0, 0);    // S, dP: both operands K-major
+  constexpr uint32_t idesc_g = umma_idesc_bf16(128, 64, 0, 1);     // dV, dK, dQ: B (dO, Q, K tiles) is MN-major
+  uint32_t mma_phase = 0;
+  // S(t, kh) -> columns col_s, dP(t, kh) -> columns col_p  (one thread issues; the commit covers everything before it)
+  auto issue_s_dp = [&](int t, int kh, uint32_t col_s, uint32_t col_p) {
+    const uint64_t qd = umma_desc_kmajor_sw128(smem_u32(sQ + t * kAbtTile));
+    const uint64_t kd = umma_desc_kmajor_sw128(smem_u32(sK + kh * kAbtTile));
+    const uint64_t dod = umma_desc_kmajor_sw128(smem_u32(sDO + t * kAbtTile));
+    const uint64_t vd = umma_desc_kmajor_sw128(smem_u32(sV + kh * kAbtTile));
+#pragma unroll
+    for (int k = 0; k < 4; ++k) umma_bf16_ss(tmem_base + col_s, qd + 2 * k, kd + 2 * k, idesc_s, k != 0);
+#pragma unroll
+    for (int k = 0; k < 4; ++k) umma_bf16_ss(tmem_base + col_p, dod + 2 * k, vd + 2 * k, idesc_s, k != 0);
+  };
+  auto wait_mma = [&]() {
+    mbar_wait(bar_mma, mma_phase);
+    mma_phase ^= 1;
+    tcgen05_fence_after();
+  };
+
+  // ------------------------------------------------------------------ statistics pre-pass
+  float m_row[2], linv_row[2], delta_row[2];
+  float* xch = reinterpret_cast<float*>(sPT);            // [2 halves][128 rows][2]: partials of the other warp of a row
+  for (int t = 0; t < NT; ++t) {
+    if (threadIdx.x == 0) {
+      for (int kh = 0; kh < NT; ++kh) issue_s_dp(t, kh, kh * 128, 256 + kh * 128);
+      tcgen05_commit(bar_mma);
+    }
+    wait_mma();
+    const int ncols = NT * 128;
+    // pass A: row max and sum over this warp's chunks, merged with the partner warp's through shared memory
+    float m = -INFINITY, l = 0.f;
+    for (int c = half; c < ncols / 16; c += 2) {
+      uint32_t r[16];
+      tmem_ld_32x32b_x16(lane_addr + c * 16, r);
+      tmem_wait_ld16(r);
+      float cm = -INFINITY;
+#pragma unroll
+      for (int i = 0; i < 16; ++i) {
+        const float s = (c * 16 + i < a.N) ? __uint_as_float(r[i]) * a.scale_log2e : -INFINITY;
+        r[i] = __float_as_uint(s);
+        cm = fmaxf(cm, s);
+      }
+      if (cm != -INFINITY) {                             // a chunk entirely past the last key contributes nothing
+        if (cm > m) { l *= exp2f(m - cm); m = cm; }    // first chunk: 0 * exp2(-inf) = 0
+#pragma unroll
+        for (int i = 0; i < 16; ++i) l += exp2f(__uint_as_float(r[i]) - m);
+      }
+    }
+    xch[(half * 128 + row) * 2] = m;
+    xch[(half * 128 + row) * 2 + 1] = l;
+    __syncthreads();
+    {
+      const float m2 = xch[((half ^ 1) * 128 + row) * 2], l2 = xch[((half ^ 1) * 128 + row) * 2 + 1];
+      const float mm = fmaxf(m, m2);                     // key 0 always exists: at least one of the two is finite
+      l = ((m == -INFINITY) ? 0.f : l * exp2f(m - mm)) + ((m2 == -INFINITY) ? 0.f : l2 * exp2f(m2 - mm));
+      m = mm;
+    }
+    __syncthreads();
+    const float linv = 1.0f / l;
+    // pass B: delta = sum_j P_ij dP_ij
+    float dl = 0.f;
+    for (int c = half; c < ncols / 16; c += 2) {
+      uint32_t r[16], q[16];
+      tmem_ld_32x32b_x16(lane_addr + c * 16, r);
+      tmem_ld_32x32b_x16(lane_addr + 256 + c * 16, q);
+      tmem_wait_ld16(r);
+      tmem_wait_ld16(q);
+#pragma unroll
+      for (int i = 0; i < 16; ++i)
+        if (c * 16 + i < a.N) dl = fmaf(exp2f(__uint_as_float(r[i]) * a.scale_log2e - m) * linv, __uint_as_float(q[i]), dl);
+    }
+    xch[half * 128 + row] = dl;
+    __syncthreads();
+    dl += xch[(half ^ 1) * 128 + row];
+    m_row[t] = m; linv_row[t] = linv; delta_row[t] = dl;
+    tcgen05_fence_before();
+    __syncthreads();                                     // xch and the TMEM columns are rewritten by the next tile
+  }
+
+  // ------------------------------------------------------------------ main pass
+  for (int kh = 0; kh < NT; ++kh) {
+    for (int t = 0; t < NT; ++t) {
+      if (threadIdx.x == 0) {
+        tcgen05_fence_after();
+        issue_s_dp(t, kh, 0, 128);
+        tcgen05_commit(bar_mma);
+      }
+      wait_mma();      // ... and with it every earlier MMA: P^T / dS^T / dS of the previous block are free to rewrite
+      const float m = m_row[t], linv = linv_row[t], dl = delta_row[t];
+      for (int c = half; c < 8; c += 2) {
+        uint32_t r[16], q[16];
+        tmem_ld_32x32b_x16(lane_addr + c * 16, r);
+        tmem_ld_32x32b_x16(lane_addr + 128 + c * 16, q);
+        tmem_wait_ld16(r);
+        tmem_wait_ld16(q);
+        uint32_t dsp[8];
+#pragma unroll
+        for (int i = 0; i < 16; i += 2) {
+          float p[2], ds[2];
+#pragma unroll
+          for (int e = 0; e < 2; ++e) {
+            const int key = kh * 128 + c * 16 + i + e;
+            p[e] = (key < a.N) ? exp2f(__uint_as_float(r[i + e]) * a.scale_log2e - m) * linv : 0.f;
+            ds[e] = p[e] * (__uint_as_float(q[i + e]) - dl) * a.scale;
+            const int kl = c * 16 + i + e;                // key inside the half = row of the transposed tiles
+            const uint32_t off = static_cast<uint32_t>(row >> 6) * kAbtTile + abt_sw128(kl, row & 63);
+            *reinterpret_cast<__nv_bfloat16*>(sPT + off) = __float2bfloat16_rn(p[e]);
+            *reinterpret_cast<__nv_bfloat16*>(sDST + off) = __float2bfloat16_rn(ds[e]);
+          }
+          dsp[i >> 1] = pack_bf16x2(ds[0], ds[1]);
+        }
+        // dS, K-major: this thread's row, keys c*16 .. +16 = two 16-byte pieces of the row's 128-byte line in key atom c / 4
+        {
+          uint8_t* line = sDS + (c >> 2) * kAbtTile + row * 128;
+          const int piece = (c & 3) * 2;
+          *reinterpret_cast<uint4*>(line + (((piece) ^ (row & 7)) << 4)) = make_uint4(dsp[0], dsp[1], dsp[2], dsp[3]);
+          *reinterpret_cast<uint4*>(line + (((piece + 1) ^ (row & 7)) << 4)) = make_uint4(dsp[4], dsp[5], dsp[6], dsp[7]);
+        }
+      }
+      fence_proxy_async_smem();     // the generic-proxy writes above are operands of the MMAs below
+      tcgen05_fence_before();
+      __syncthreads();
+      if (threadIdx.x == 0) {
+        tcgen05_fence_after();
+        const uint64_t ptd = umma_desc_kmajor_sw128(smem_u32(sPT));
+        const uint64_t dstd = umma_desc_kmajor_sw128(smem_u32(sDST));
+        const uint64_t dsd = umma_desc_kmajor_sw128(smem_u32(sDS));
+        const uint64_t dod = umma_desc_mnmajor_sw128(smem_u32(sDO + t * kAbtTile));
+        const uint64_t qd = umma_desc_mnmajor_sw128(smem_u32(sQ + t * kAbtTile));
+        const uint64_t kd = umma_desc_mnmajor_sw128(smem_u32(sK + kh * kAbtTile));
+#pragma unroll
+        for (int k = 0; k < 8; ++k) {   // contraction over the 128 rows of the tile, 16 per MMA; atom k / 4, 32 B per step inside it
+          const uint32_t aoff = static_cast<uint32_t>((k >> 2) * (kAbtTile >> 4) + (k & 3) * 2);
+          umma_bf16_ss(tmem_base + 256, ptd + aoff, dod + 128 * k, idesc_g, (t | k) != 0);    // dV(kh) += P^T dO_t
+          umma_bf16_ss(tmem_base + 320, dstd + aoff, qd + 128 * k, idesc_g, (t | k) != 0);    // dK(kh) += dS^T Q_t
+          umma_bf16_ss(tmem_base + 384 + 64 * t, dsd + aoff, kd + 128 * k, idesc_g, (kh | k) != 0);   // dQ(t) += dS K_kh
+        }
+        // no commit here: the next block's commit (or the one below) covers these
+      }
+    }
+    // dV(kh), dK(kh): thread <-> key row
+    if (threadIdx.x == 0) tcgen05_commit(bar_mma);
+    wait_mma();
+    {
+      const int key = kh * 128 + row;
+      for (int c = half; c < 8; c += 2) {                 // chunks 0-3: dV, 4-7: dK (64 columns each)
+        uint32_t r[16];
+        tmem_ld_32x32b_x16(lane_addr + 256 + c * 16, r);
+        tmem_wait_ld16(r);
+        if (key < a.N) {
+          const int which = c >> 2;                       // 0 = dV -> third third of the row, 1 = dK -> second third
+          __nv_bfloat16* dst = a.dqkv + (static_cast<size_t>(b) * a.N + key) * 3 * a.D + (which ? a.D : 2 * a.D) + h * 64 + (c & 3) * 16;
+          uint4 v0, v1;
+          v0.x = pack_bf16x2(__uint_as_float(r[0]), __uint_as_float(r[1]));   v0.y = pack_bf16x2(__uint_as_float(r[2]), __uint_as_float(r[3]));
+          v0.z = pack_bf16x2(__uint_as_float(r[4]), __uint_as_float(r[5]));   v0.w = pack_bf16x2(__uint_as_float(r[6]), __uint_as_float(r[7]));
+          v1.x = pack_bf16x2(__uint_as_float(r[8]), __uint_as_float(r[9]));   v1.y = pack_bf16x2(__uint_as_float(r[10]), __uint_as_float(r[11]));
+          v1.z = pack_bf16x2(__uint_as_float(r[12]), __uint_as_float(r[13])); v1.w = pack_bf16x2(__uint_as_float(r[14]), __uint_as_float(r[15]));
+          reinterpret_cast<uint4*>(dst)[0] = v0;
+          reinterpret_cast<uint4*>(dst)[1] = v1;
+        }
+      }
+    }
+    tcgen05_fence_before();
+    __syncthreads();     // dV / dK columns are read out before the next key half overwrites them
+  }
+  // dQ(t): thread <-> query row (every MMA has completed: the last commit above covered them)
+  for (int t = 0; t < NT; ++t) {
+    const int qrow = t * 128 + row;
+    for (int c = half; c < 4; c += 2) {
+      uint32_t r[16];
+      tmem_ld_32x32b_x16(lane_addr + 384 + 64 * t + c * 16, r);
+      tmem_wait_ld16(r);
+      if (qrow < a.N) {
+        __nv_bfloat16* dst = a.dqkv + (static_cast<size_t>(b) * a.N + qrow) * 3 * a.D + h * 64 + c * 16;
+        uint4 v0, v1;
+        v0.x = pack_bf16x2(__uint_as_float(r[0]), __uint_as_float(r[1]));   v0.y = pack_bf16x2(__uint_as_float(r[2]), __uint_as_float(r[3]));
+        v0.z = pack_bf16x2(__uint_as_float(r[4]), __uint_as_float(r[5]));   v0.w = pack_bf16x2(__uint_as_float(r[6]), __uint_as_float(r[7]));
+        v1.x = pack_bf16x2(__uint_as_float(r[8]), __uint_as_float(r[9]));   v1.y = pack_bf16x2(__uint_as_float(r[10]), __uint_as_float(r[11]));
+        v1.z = pack_bf16x2(__uint_as_float(r[12]), __uint_as_float(r[13])); v1.w = pack_bf16x2(__uint_as_float(r[14]), __uint_as_float(r[15]));
+        reinterpret_cast<uint4*>(dst)[0] = v0;
+        reinterpret_cast<uint4*>(dst)[1] = v1;
+      }
+    }
+  }
+  tcgen05_fence_before();
+  __syncthreads();
+  if (warp == 1) tmem_dealloc(tmem_base, kAbtTmemCols);
+}
+
+}  // namespace ldit

@@ -63,13 +63,20 @@ constexpr int kA3BarQFull = 0, kA3BarQEmpty = 2, kA3BarKFull = 4, kA3BarKEmpty =
               kA3BarPvDone = kA3BarPFull + 4,    // [warpgroup][S buffer]
               kA3NumBars = kA3BarPvDone + 4;
 
+// length of a warpgroup's bias table in shared memory: T entries + (largest column term + 1) copies of entry T - 3,
+// rounded up to 4 floats (the column terms behind it are read as int4)
+__host__ __device__ inline int a3_ext_len(int Gh, int Gw, int T) {
+  return (T + (Gh - 1) * (2 * Gw - 1) + Gw - 1 + 1 + 3) & ~3;
+}
 __device__ __forceinline__ float a3_fmax3(float a, float b, float c) {
   float d;
   asm("max.f32 %0, %1, %2, %3;" : "=f"(d) : "f"(a), "f"(b), "f"(c));
   return d;
 }
-__device__ __forceinline__ void a3_bar_sync(int id, int nthreads) {
-  asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory");
+// barrier of one softmax warpgroup (128 threads); immediate ids, so ptxas reserves 3 named barriers and not all 16
+__device__ __forceinline__ void a3_wg_sync(int g) {
+  if (g == 0) asm volatile("bar.sync 1, 128;" ::: "memory");
+  else asm volatile("bar.sync 2, 128;" ::: "memory");
 }
 __device__ __forceinline__ float a3_exp2(float x) {
   float y;
@@ -113,8 +120,11 @@ attention_v3_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
                                               // buffer: warps of a warpgroup may be a step apart, their arrivals for steps t and t+1 must not mix
   uint64_t* pv_done = bars + kA3BarPvDone;    // [warpgroup][S buffer]: P V of a step on that buffer (and everything issued before it) complete
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + kA3NumBars);
-  float* sTab = reinterpret_cast<float*>(bars + kA3NumBars + 2);  // [2][T] (one copy per warpgroup)
-  int* sCol = reinterpret_cast<int*>(sTab + (HAS_BIAS ? 2 * a.T : 0));
+  // relative-position bias: per warpgroup the head's table (x log2 e) followed by a flat run of the "CLS row" entry, so
+  // that bias(q, k) = sTab[rowterm(q) - sCol[k]] holds for EVERY row without a per-element special case (a3_ext_len)
+  float* sTab = reinterpret_cast<float*>(bars + kA3NumBars + 2);  // [2][ext] (one copy per warpgroup)
+  const int ext = HAS_BIAS ? a3_ext_len(a.Gh, a.Gw, a.T) : 0;
+  int* sCol = reinterpret_cast<int*>(sTab + 2 * ext);             // [n_ktiles * 32]: column term of key k (0 past the last key)
 
   const int warp = __shfl_sync(0xffffffffu, static_cast<int>(threadIdx.x >> 5), 0);
   const int lane = threadIdx.x & 31;
@@ -138,9 +148,9 @@ attention_v3_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
     tmem_relinquish();
   }
   if constexpr (HAS_BIAS) {
-    for (int k = threadIdx.x; k < a.N; k += kA3Threads) {
+    for (int k = threadIdx.x; k < a.n_ktiles * kA3KT; k += kA3Threads) {
       const int p = k - 1;
-      sCol[k] = (k == 0) ? 0 : (p / a.Gw) * (2 * a.Gw - 1) + (p % a.Gw);
+      sCol[k] = (k == 0 || k >= a.N) ? 0 : (p / a.Gw) * (2 * a.Gw - 1) + (p % a.Gw);
     }
   }
   tcgen05_fence_before();
@@ -264,7 +274,8 @@ attention_v3_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
     const int g = warp >> 2;
     const int quarter = warp & 3;
     const uint32_t lane_addr = tmem_base + g * 128 + (static_cast<uint32_t>(quarter * 32) << 16);
-    float* myTab = sTab + (HAS_BIAS ? g * a.T : 0);
+    float* myTab = sTab + g * ext;
+    const int cmax = (a.Gh - 1) * (2 * a.Gw - 1) + a.Gw - 1;   // largest column term
     const float sc = a.scale_log2e;
     uint32_t sbits = 0;          // parity of the next phase of s_full[g][S buffer], one bit each
     // pv_done[g][b] completes once per step on buffer b.  A warp waits on it only when it needs O (a rescale, the
@@ -300,13 +311,16 @@ attention_v3_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
       int rowterm = 0;
       if constexpr (HAS_BIAS) {
         if (h != cur_h) {  // (re)load this head's table; 128 threads of the warpgroup
-          a3_bar_sync(1 + g, 128);
+          a3_wg_sync(g);
           const float* tab = a.bias_table + static_cast<size_t>(h) * a.T;
-          for (int i = quarter * 32 + lane; i < a.T; i += 128) myTab[i] = tab[i] * 1.4426950408889634f;
-          a3_bar_sync(1 + g, 128);
+          for (int i = quarter * 32 + lane; i < ext; i += 128) myTab[i] = tab[i < a.T ? i : a.T - 3] * 1.4426950408889634f;
+          a3_wg_sync(g);
           cur_h = h;
         }
-        if (q >= 1) { const int pp = q - 1; rowterm = (pp / a.Gw + a.Gh - 1) * (2 * a.Gw - 1) + (pp % a.Gw) + a.Gw - 1; }
+        // patch rows: (row term) - (column term) is the index rule of HF:522-544; the CLS row (q = 0) and the padding rows
+        // past N point at the flat run behind the table, which holds the "CLS to token" entry T - 3 for every column
+        rowterm = a.T + cmax;
+        if (q >= 1 && q < a.N) { const int pp = q - 1; rowterm = (pp / a.Gw + a.Gh - 1) * (2 * a.Gw - 1) + (pp % a.Gw) + a.Gw - 1; }
       }
       float m_run = -INFINITY, l_run = 0.f;
 
@@ -334,25 +348,27 @@ attention_v3_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
               tmem_wait_ld16(rc);
               if (c + 1 < nch) tmem_ld_32x32b_x16(s_addr + (c + 1) * 16, r[(c + 1) & 1]);
               const bool partial = (c + 1) * 16 > valid;
-              if (HAS_BIAS || partial) {
+              if constexpr (HAS_BIAS) {
+                // logits = s * scale * log2 e + bias: one table load and one FMA per element; the column terms of four
+                // keys come with one broadcast 16-byte load
+                const int4* colv = reinterpret_cast<const int4*>(sCol + k0 + c * 16);
+                const float s00 = __uint_as_float(rc[0]);
 #pragma unroll
-                for (int i = 0; i < 16; ++i) {
-                  const int kk = c * 16 + i;
-                  float v = __uint_as_float(rc[i]);
-                  if constexpr (HAS_BIAS) {
-                    v *= sc;
-                    if (kk < valid && q < a.N) {
-                      const int kc = k0 + kk;
-                      int idx;
-                      if (q == 0) idx = (kc == 0) ? a.T - 1 : a.T - 3;
-                      else if (kc == 0) idx = a.T - 2;
-                      else idx = rowterm - sCol[kc];
-                      v += myTab[idx];
-                    }
-                  }
-                  rc[i] = __float_as_uint(kk < valid ? v : -INFINITY);
+                for (int i4 = 0; i4 < 4; ++i4) {
+                  const int4 cc = colv[i4];
+                  rc[4 * i4 + 0] = __float_as_uint(fmaf(__uint_as_float(rc[4 * i4 + 0]), sc, myTab[rowterm - cc.x]));
+                  rc[4 * i4 + 1] = __float_as_uint(fmaf(__uint_as_float(rc[4 * i4 + 1]), sc, myTab[rowterm - cc.y]));
+                  rc[4 * i4 + 2] = __float_as_uint(fmaf(__uint_as_float(rc[4 * i4 + 2]), sc, myTab[rowterm - cc.z]));
+                  rc[4 * i4 + 3] = __float_as_uint(fmaf(__uint_as_float(rc[4 * i4 + 3]), sc, myTab[rowterm - cc.w]));
                 }
-                tmem_st_32x32b_x16(s_addr + c * 16, rc);   // pass 2 reads the finished logits
+                if (c == 0 && k0 == 0)   // the CLS column: "token to CLS" T - 2, "CLS to CLS" T - 1
+                  rc[0] = __float_as_uint(fmaf(s00, sc, myTab[q == 0 ? a.T - 1 : a.T - 2]));
+              }
+              if (partial) {
+#pragma unroll
+                for (int i = 0; i < 16; ++i)
+                  if (c * 16 + i >= valid) rc[i] = __float_as_uint(-INFINITY);
+                if constexpr (!HAS_BIAS) tmem_st_32x32b_x16(s_addr + c * 16, rc);   // pass 2 reads the masked logits
               }
 #pragma unroll
               for (int i = 0; i < 16; i += 8) {
@@ -363,9 +379,11 @@ attention_v3_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
               }
             }
           }
-          if (HAS_BIAS || (valid & 15)) tcgen05_wait_st();
+          // with a bias table the finished logits of both chunks stay in r[0] / r[1] for pass 2 (no write-back, no
+          // second read); without one pass 2 reads S again, which keeps 16 registers free for the common case
+          if (!HAS_BIAS && (valid & 15)) tcgen05_wait_st();
           A3_STAMP();
-          tmem_ld_32x32b_x16(s_addr, r[0]);   // pass 2, chunk 0
+          if constexpr (!HAS_BIAS) tmem_ld_32x32b_x16(s_addr, r[0]);   // pass 2, chunk 0
           float mt = fmaxf(fmaxf(mx0, mx1), fmaxf(mx2, mx3));
           if constexpr (!HAS_BIAS) mt *= sc;   // scale > 0: max commutes with it
           // ---- lazy running max: move it (and rescale O, l) only when it grows by more than 2^kA3LazyLog2
@@ -395,8 +413,10 @@ attention_v3_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
           for (int c = 0; c < kA3Chunks; ++c) {
             if (c < nch) {
               uint32_t (&rc)[16] = r[c & 1];
-              tmem_wait_ld16(rc);
-              if (c + 1 < nch) tmem_ld_32x32b_x16(s_addr + (c + 1) * 16, r[(c + 1) & 1]);
+              if constexpr (!HAS_BIAS) {
+                tmem_wait_ld16(rc);
+                if (c + 1 < nch) tmem_ld_32x32b_x16(s_addr + (c + 1) * 16, r[(c + 1) & 1]);
+              }
               if (!HAS_BIAS && (c + 1) * 16 > valid) {   // partial chunk: keys past the end of the image
 #pragma unroll
                 for (int i = 0; i < 16; ++i)

@@ -224,104 +224,6 @@ layernorm_bwd_kernel(const float* __restrict__ x, const float* __restrict__ gamm
   }
 }
 
-// --------------------------------------------------------------------------- attention backward
-// ctx = softmax(q k^T / 8) v per (image, head), head_dim 64 (HF:275-298).  Given dctx: dq, dk, dv.
-// One block per (image, head); thread j <-> key j (N <= 256 tokens): k_j and v_j live in the thread's registers for the
-// whole block, and so do the accumulators dk_j and dv_j.  The block walks the query rows; per row i
-//   s_j = q_i . k_j / 8,  p_j = softmax_j(s),  dp_j = dctx_i . v_j,  delta = sum_j p_j dp_j  (= dctx_i . ctx_i)
-//   ds_j = p_j (dp_j - delta);   dq_i = sum_j ds_j k_j / 8;   dk_j += ds_j q_i / 8;   dv_j += p_j dctx_i
-// with block-wide reductions for the row maximum, the row sum, delta and dq_i.  qkv / dqkv bf16 [B, N, 3D] (Q | K | V).
-// Correctness-first stand-in (no tensor cores); no relative-position bias (its table gradient is a follow-up).
-constexpr int kAbThreads = 256;
-__device__ __forceinline__ float ab_block_reduce(float v, float* red, bool is_max) {
-  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-#pragma unroll
-  for (int o = 16; o > 0; o >>= 1) { const float t = __shfl_xor_sync(0xffffffffu, v, o); v = is_max ? fmaxf(v, t) : v + t; }
-  __syncthreads();                       // red[] free (previous reduction fully consumed)
-  if (lane == 0) red[warp] = v;
-  __syncthreads();
-  float r = red[0];
-#pragma unroll
-  for (int w = 1; w < kAbThreads / 32; ++w) r = is_max ? fmaxf(r, red[w]) : r + red[w];
-  return r;
-}
-
-__global__ void __launch_bounds__(kAbThreads, 1)
-attention_bwd_kernel(const __nv_bfloat16* __restrict__ qkv, const __nv_bfloat16* __restrict__ dctx, __nv_bfloat16* __restrict__ dqkv,
-                     int N, int heads) {
-  const int D = heads * 64;
-  const int b = blockIdx.x / heads, h = blockIdx.x % heads;
-  const int j = threadIdx.x;
-  const bool valid = j < N;
-  __shared__ float sq[64], sdo[64], red[kAbThreads / 32], sdq[kAbThreads / 32][64];
-  const __nv_bfloat16* base = qkv + static_cast<size_t>(b) * N * 3 * D + h * 64;
-  uint32_t kp[32], vp[32];   // k_j, v_j as packed bf16 pairs (registers are the scarce resource here)
-  float dk[64], dv[64];
-#pragma unroll
-  for (int c = 0; c < 8; ++c) {
-    uint4 uk = make_uint4(0u, 0u, 0u, 0u), uv = make_uint4(0u, 0u, 0u, 0u);
-    if (valid) {
-      uk = __ldg(reinterpret_cast<const uint4*>(base + static_cast<size_t>(j) * 3 * D + D) + c);
-      uv = __ldg(reinterpret_cast<const uint4*>(base + static_cast<size_t>(j) * 3 * D + 2 * D) + c);
-    }
-    kp[4 * c] = uk.x; kp[4 * c + 1] = uk.y; kp[4 * c + 2] = uk.z; kp[4 * c + 3] = uk.w;
-    vp[4 * c] = uv.x; vp[4 * c + 1] = uv.y; vp[4 * c + 2] = uv.z; vp[4 * c + 3] = uv.w;
-  }
-#pragma unroll
-  for (int d = 0; d < 64; ++d) { dk[d] = 0.f; dv[d] = 0.f; }
-  auto lo = [](uint32_t u) { return __uint_as_float(u << 16); };
-  auto hi = [](uint32_t u) { return __uint_as_float(u & 0xffff0000u); };
-  for (int i = 0; i < N; ++i) {
-    __syncthreads();                     // sq / sdo / sdq of the previous row consumed
-    if (threadIdx.x < 64) sq[threadIdx.x] = __bfloat162float(base[static_cast<size_t>(i) * 3 * D + threadIdx.x]);
-    else if (threadIdx.x < 128) sdo[threadIdx.x - 64] = __bfloat162float(dctx[(static_cast<size_t>(b) * N + i) * D + h * 64 + threadIdx.x - 64]);
-    __syncthreads();
-    float s = 0.f, dp = 0.f;
-#pragma unroll
-    for (int d2 = 0; d2 < 32; ++d2) {
-      s += sq[2 * d2] * lo(kp[d2]) + sq[2 * d2 + 1] * hi(kp[d2]);
-      dp += sdo[2 * d2] * lo(vp[d2]) + sdo[2 * d2 + 1] * hi(vp[d2]);
-    }
-    s = valid ? s * 0.125f : -INFINITY;
-    const float m = ab_block_reduce(s, red, true);
-    const float e = valid ? __expf(s - m) : 0.f;
-    const float l = ab_block_reduce(e, red, false);
-    const float p = e / l;
-    const float delta = ab_block_reduce(p * dp, red, false);
-    const float ds = p * (dp - delta) * 0.125f;     // includes the 1/8 of the chain rule through s
-    // dq_i: reduce ds_j k_j over the block -- warp shuffles, then the 8 warp partials through shared memory
-    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-#pragma unroll
-    for (int d = 0; d < 64; ++d) {
-      float t = ds * ((d & 1) ? hi(kp[d >> 1]) : lo(kp[d >> 1]));
-#pragma unroll
-      for (int o = 16; o > 0; o >>= 1) t += __shfl_xor_sync(0xffffffffu, t, o);
-      if (lane == 0) sdq[warp][d] = t;
-      dk[d] += ds * sq[d];
-      dv[d] += p * sdo[d];
-    }
-    __syncthreads();
-    if (threadIdx.x < 64) {
-      float t = 0.f;
-#pragma unroll
-      for (int w = 0; w < kAbThreads / 32; ++w) t += sdq[w][threadIdx.x];
-      dqkv[(static_cast<size_t>(b) * N + i) * 3 * D + h * 64 + threadIdx.x] = __float2bfloat16_rn(t);
-    }
-  }
-  if (valid) {
-    __nv_bfloat16* ok = dqkv + (static_cast<size_t>(b) * N + j) * 3 * D + D + h * 64;
-    __nv_bfloat16* ov = ok + D;
-#pragma unroll
-    for (int c = 0; c < 8; ++c) {
-      float t[8];
-#pragma unroll
-      for (int e = 0; e < 8; ++e) t[e] = dk[8 * c + e];
-      reinterpret_cast<uint4*>(ok)[c] = pack8(t);
-#pragma unroll
-      for (int e = 0; e < 8; ++e) t[e] = dv[8 * c + e];
-      reinterpret_cast<uint4*>(ov)[c] = pack8(t);
-    }
-  }
-}
+// The attention backward lives in attention_bwd_tc.cuh (tcgen05).
 
 }  // namespace ldit

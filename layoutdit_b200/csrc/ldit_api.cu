@@ -15,6 +15,7 @@
 #include "../../include/ldit.h"
 #include "attention_v3.cuh"
 #include "backward.cuh"
+#include "attention_bwd_tc.cuh"
 #include "gemm.cuh"
 #include "rowwise.cuh"
 // Superseded / experimental kernels (round-1 attention variants, the fused fc1+fc2 kernel): measured slower than the
@@ -949,7 +950,7 @@ int ldit_attention(const void* qkv, void* ctx, const void* bias_table, int B, in
     rc = make_tmap_rows_3d(&tmO, ctx, B, N, D, 32);   // ctx as [B, N, D]: box 32 rows x 64 cols
     if (rc) return rc;
     size_t smem = 1024 + kA3SmemTiles + (kA3NumBars + 2) * 8;
-    if (bias_table) smem += (2 * static_cast<size_t>(T) + N) * 4;
+    if (bias_table) smem += (2 * static_cast<size_t>(a3_ext_len(Gh, Gw, T)) + static_cast<size_t>(a.n_ktiles) * kA3KT) * 4;
     if (smem > 227 * 1024) return LDIT_E_SHAPE;
     const int per_sm = smem <= 113 * 1024 ? 2 : 1;   // the kernel is sized to be resident twice per SM
     const int slots = per_sm * num_sms();
@@ -1238,10 +1239,24 @@ int ldit_layernorm_bwd(const void* x, const void* gamma, const void* dy, const v
 int ldit_attention_bwd(const void* qkv, const void* dctx, void* dqkv, int B, int N, int heads, void* stream) {
   if (!qkv || !dctx || !dqkv) return LDIT_E_NULL;
   if (B <= 0 || heads <= 0 || N <= 0) return LDIT_E_SHAPE;
-  if (N > kAbThreads) return LDIT_E_UNSUPPORTED;   // the stand-in kernel maps one thread to one key
+  if (N > 256) return LDIT_E_UNSUPPORTED;   // two 128-row query tiles x two 128-key halves per CTA (224 x 224 pages: 197 tokens)
   if (!aligned16(qkv) || !aligned16(dctx) || !aligned16(dqkv)) return LDIT_E_ALIGN;
-  attention_bwd_kernel<<<B * heads, kAbThreads, 0, static_cast<cudaStream_t>(stream)>>>(
-      static_cast<const __nv_bfloat16*>(qkv), static_cast<const __nv_bfloat16*>(dctx), static_cast<__nv_bfloat16*>(dqkv), N, heads);
+  const int D = heads * 64;
+  AttnBwdArgs a{};
+  a.qkv = static_cast<const __nv_bfloat16*>(qkv);
+  a.dqkv = static_cast<__nv_bfloat16*>(dqkv);
+  a.B = B; a.N = N; a.heads = heads; a.D = D;
+  a.scale = 0.125f;
+  a.scale_log2e = 0.125f * 1.4426950408889634f;
+  CUtensorMap tmQKV, tmDO;
+  int rc = make_tmap_qkv_3d(&tmQKV, qkv, B, N, 3 * D, 128);
+  if (rc) return rc;
+  rc = make_tmap_rows_3d(&tmDO, dctx, B, N, D, 128);
+  if (rc) return rc;
+  const size_t smem = 1024 + kAbtSmemTiles + 64;
+  cudaError_t e = ensure_smem(attention_bwd_tc_kernel, smem, false);
+  if (e != cudaSuccess) return static_cast<int>(e);
+  attention_bwd_tc_kernel<<<B * heads, kAbtThreads, smem, static_cast<cudaStream_t>(stream)>>>(tmQKV, tmDO, a);
   return check_launch();
 }
 

@@ -111,3 +111,43 @@ def test_bucketed_gradient_all_reduce_world2():
         for r in range(world):
             torch.testing.assert_close(out[r][n], want, rtol=1e-6, atol=1e-7)
     assert "3.bias" not in out[0]
+
+
+def _peer_worker(rank, world, port, out):
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    torch.cuda.set_device(rank)
+    dev = torch.device("cuda", rank)
+    dist.init_process_group("nccl", rank=rank, world_size=world, device_id=dev)
+    try:
+        from layoutdit_b200.sharding import PeerGather
+        g = torch.Generator().manual_seed(11)
+        full = torch.randn(world * 3, 7, 7, 64, generator=g).to(torch.bfloat16)
+        mine = full[rank * 3: (rank + 1) * 3].to(dev)
+        pg = PeerGather(tuple(mine.shape), mine.dtype, dev)
+        ok = True
+        for it in range(3):                                  # repeated use: the closing barrier frees the staging buffers
+            got = pg(mine * (it + 1))
+            torch.cuda.synchronize(dev)
+            ok &= torch.equal(got.cpu(), (full.to(dev) * (it + 1)).cpu())
+        ref = gather_tap(mine.permute(0, 3, 1, 2)).permute(0, 2, 3, 1)     # the NCCL path agrees
+        ok &= torch.equal(pg(mine).cpu(), ref.cpu())
+        out.put((rank, bool(ok)))
+    finally:
+        dist.destroy_process_group()
+
+
+@pytest.mark.gpu
+def test_peer_gather_matches_nccl_on_two_gpus():
+    """sharding.PeerGather (copy-engine pulls out of symmetric memory) against the NCCL all-gather; needs 2 GPUs."""
+    if not torch.cuda.is_available() or torch.cuda.device_count() < 2:
+        pytest.skip("needs two GPUs on one node")
+    ctx = mp.get_context("spawn")
+    out = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_peer_worker, args=(r, 2, port, out)) for r in range(2)]
+    for p in procs:
+        p.start()
+    res = sorted(out.get(timeout=180) for _ in procs)
+    for p in procs:
+        p.join(timeout=60)
+    assert res == [(0, True), (1, True)]
