@@ -233,6 +233,93 @@ def run_fpn_line(args, cfg, fac, B, H, W, dev, rank, world, peaks):
         dist.destroy_process_group()
 
 
+def run_train_line(args, cfg, fac, B, H, W, dev, rank, world, peaks):
+    """Secondary line for SURVEY 8 row f2 (BASELINE config 5, backbone part): one data-parallel TRAINING step of the
+    backbone -- forward, a loss on the four taps, the hand-written backward (layoutdit_b200.train), bucketed gradient
+    all-reduce (NCCL) and a fused AdamW step -- against the reference's way of doing the same step on this GPU: HF
+    BeitModel under torch autocast bf16 + torch.autograd (+ DistributedDataParallel when N > 1), same loss and optimizer."""
+    import torch.distributed as dist
+    from layoutdit_b200.config import flops_per_image
+    from layoutdit_b200.dit_params import DiTParameters
+    from layoutdit_b200.synth import make_state_dict, synthetic_pages
+    from layoutdit_b200.train import GradientBuckets, TrainableBackbone
+    sd = make_state_dict(cfg, 0, False)
+    pages = synthetic_pages(B, H, W, 1234 + rank).to(dev)
+
+    def loss_of(feats):   # stand-in for the detection head's loss: touches every tap densely
+        return sum(f.float().square().mean() for f in feats.values())
+
+    def timed(step):
+        for _ in range(args.warmup):
+            step()
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize(dev)
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(args.steps):
+            step()
+        e1.record()
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize(dev)
+        ms = torch.tensor([e0.elapsed_time(e1)], dtype=torch.float64, device=dev)
+        if world > 1:
+            dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+        return float(ms.item()) / args.steps
+
+    tree = DiTParameters(cfg)
+    tree.load_state_dict(sd, strict=False)
+    tree = tree.to(dev)
+    model = TrainableBackbone(tree, cfg)
+    trainable = [p for n, p in tree.named_parameters() if not n.startswith("pooler")]
+    opt = torch.optim.AdamW(trainable, lr=1e-5, fused=True)
+    buckets = GradientBuckets(trainable)
+
+    def ours():
+        opt.zero_grad(set_to_none=True)
+        loss_of(model(pages)).backward()
+        buckets.all_reduce()
+        opt.step()
+    ms_ours = timed(ours)
+    del model, opt, buckets, tree
+    torch.cuda.empty_cache()
+
+    from oracle import hf_reference   # comparator only: never on the product path
+    hf = hf_reference.build(cfg.to_dict(), sd).to(dev).eval()   # eval(): drop-path off, the same arithmetic as ours; autograd still runs
+    hf_params = [p for n, p in hf.named_parameters() if "pooler" not in n]
+    wrapped = torch.nn.parallel.DistributedDataParallel(hf, device_ids=[dev.index], find_unused_parameters=True) if world > 1 else hf
+    hopt = torch.optim.AdamW(hf_params, lr=1e-5, fused=True)
+
+    def theirs():
+        hopt.zero_grad(set_to_none=True)
+        with torch.autocast("cuda", dtype=torch.bfloat16):
+            feats = wrapped(pages)
+        loss_of(feats).backward()
+        hopt.step()
+    ms_hf = timed(theirs)
+    fl = 3.0 * flops_per_image(cfg, H, W)      # forward + backward (dgrad + wgrad) of the GEMM / attention work
+    value = world * B / (ms_ours / 1e3)
+    if rank == 0:
+        print(json.dumps({
+            "metric": "DiT backbone training step throughput", "value": round(value, 1), "unit": "images/s", "n_gpus": world,
+            "steps": args.steps, "warmup": args.warmup, "ms_per_step": round(ms_ours, 3), "higher_is_better": True,
+            "scaling": "weak", "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
+            "config": {"workload": f"{args.workload} training step: {fac} backbone forward + loss on the four taps + backward + "
+                                   f"gradient all-reduce + fused AdamW, batch {B} per GPU, {H}x{W}, random-init weights; no detection head "
+                                   f"(BASELINE config 5 is backbone + head at 1024x1024: the attention backward covers <= 256 tokens)",
+                       "global_batch": world * B, "parallelism": f"dp{world}",
+                       "timing": "stream launches (no CUDA graph), CUDA events around all steps, max over ranks, no L2 flush"},
+            "model_tflops": round(fl * value / 1e12, 1), "model_frac_of_peak": round(fl * value / 1e12 / (world * peaks["bf16_tflops"]), 4),
+            "gpu_library_baseline": {"value": round(world * B / (ms_hf / 1e3), 1), "unit": "images/s", "ms_per_step": round(ms_hf, 3),
+                                     "ours_over_library": round(ms_hf / ms_ours, 3),
+                                     "what": "HF BeitModel wrapped as R:dit_backbone.py:38-62, torch autocast bf16 + autograd"
+                                             + (" + DistributedDataParallel" if world > 1 else "") + ", same pages, loss and optimizer"},
+        }), file=_RESULT, flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
 _RESULT = sys.stdout   # where the ONE JSON line goes; main() re-points it at the real stdout
 
 
@@ -583,6 +670,9 @@ def main():
     ap.add_argument("--head", default="taps", choices=["taps", "fpn"],
                     help="taps (default, BASELINE.json's metric): DiTBackbone, four D-channel taps; fpn: DiTWithFPN "
                          "(SURVEY 8 row f1: laterals, top-down merges, 3x3 convolutions, pool) -- device-resident value only")
+    ap.add_argument("--mode", default="forward", choices=["forward", "train"],
+                    help="forward (default, BASELINE.json's metric) or train: one data-parallel training step of the backbone "
+                         "(SURVEY 8 row f2) against HF autocast training on the same GPU")
     ap.add_argument("--no-graph", dest="graph", action="store_false",
                     help="enqueue the launch plan on the stream every step instead of replaying its captured CUDA graph "
                          "(same device time within noise once the launches carry the PDL attribute, but exposed to host jitter)")
@@ -612,6 +702,9 @@ def main():
 
     if args.head == "fpn":
         run_fpn_line(args, cfg, fac, B, H, W, dev, rank, world, peaks)
+        return
+    if args.mode == "train":
+        run_train_line(args, cfg, fac, B, H, W, dev, rank, world, peaks)
         return
 
     def barrier():

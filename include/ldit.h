@@ -202,8 +202,14 @@ int ldit_scale_residual_bwd(const void* dy, const void* branch, const void* lam,
 int ldit_layernorm_bwd(const void* x, const void* gamma, const void* dy, const void* dx_in, void* dx_out, void* dgamma, void* dbeta,
                        int rows, int D, float eps, void* stream);
 /* Backward of ldit_attention without relative-position bias: dqkv bf16 [B*N, 3D] from qkv and dctx bf16 [B*N, D].
- * Correctness-first stand-in (CUDA cores, one block per (image, head), N <= 256; LDIT_E_UNSUPPORTED beyond). */
+ * tcgen05 kernel, one CTA per (image, head), P recomputed from qkv (nothing else is kept from the forward);
+ * N <= 256 (two 128-row query tiles x two 128-key halves fill TMEM), LDIT_E_UNSUPPORTED beyond. */
 int ldit_attention_bwd(const void* qkv, const void* dctx, void* dqkv, int B, int N, int heads, void* stream);
+/* Adjoint of ldit_resample_taps (R:dit_backbone.py:50-61 under autograd): dout bf16 [B, floor(Gh*scale), floor(Gw*scale), D]
+ * channels-last -> dx f32 [B, Gh*Gw + 1, D], rows 1..P written (the CLS row is left as it is: zero it first). */
+int ldit_resample_taps_bwd(const void* dout, void* dx, int B, int Gh, int Gw, int D, float scale, void* stream);
+/* out f32 [R] += sum over b of x f32 [B, R]  (gradients of the position / CLS embeddings, HF:161-184; R % 4 == 0) */
+int ldit_batch_sum(const void* x, void* out, int B, int R, void* stream);
 
 /* Bytes of the im2col scratch ldit_patch_embed needs. */
 size_t ldit_patch_embed_scratch_bytes(int B, int H, int W);

@@ -30,6 +30,8 @@ SIGNATURES = {
     "ldit_scale_residual_bwd": (_i, [_vp, _vp, _vp, _vp, _vp, _i, _i, _vp]),
     "ldit_layernorm_bwd": (_i, [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _i, _i, _f, _vp]),
     "ldit_attention_bwd": (_i, [_vp, _vp, _vp, _i, _i, _i, _vp]),
+    "ldit_resample_taps_bwd": (_i, [_vp, _vp, _i, _i, _i, _i, _f, _vp]),
+    "ldit_batch_sum": (_i, [_vp, _vp, _i, _i, _vp]),
     "ldit_mlp_clusters": (_i, []),
     "ldit_mlp_schedule": (_i, [_i, _i, _i, _vp, _i]),
     "ldit_mlp_fused": (_i, [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _i, _i, _i, _vp, _i, _vp, _vp]),

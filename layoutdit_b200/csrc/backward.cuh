@@ -29,19 +29,39 @@ __device__ __forceinline__ uint4 pack8(const float (&v)[8]) {
 
 // ---------------------------------------------------------------------------------- transpose
 // in bf16 [R, C] -> out bf16 [C, ldo] (ldo >= R: the row pitch of a TMA operand must be a multiple of 16 bytes; the
-// caller zero-fills the padding once).  32 x 32 tiles through padded shared memory; block (32, 8).
+// caller zero-fills the padding once).  64 x 64 tiles through padded shared memory, block (32, 8); both global sides
+// move 4 bytes per thread (128-byte warp rows) when C, R and ldo are even, element by element otherwise.
 __global__ void __launch_bounds__(256)
 transpose_bf16_kernel(const __nv_bfloat16* __restrict__ in, __nv_bfloat16* __restrict__ out, int R, int C, int ldo) {
-  __shared__ __nv_bfloat16 tile[32][34];
-  const int c0 = blockIdx.x * 32, r0 = blockIdx.y * 32;
-  for (int i = threadIdx.y; i < 32; i += 8) {
-    const int r = r0 + i, c = c0 + threadIdx.x;
-    tile[i][threadIdx.x] = (r < R && c < C) ? in[static_cast<size_t>(r) * C + c] : __float2bfloat16(0.f);
+  __shared__ __nv_bfloat16 tile[64][66];
+  const int c0 = blockIdx.x * 64, r0 = blockIdx.y * 64;
+  const int tx = threadIdx.x, ty = threadIdx.y;
+  const bool in_pairs = (C & 1) == 0, out_pairs = (ldo & 1) == 0;
+  for (int i = ty; i < 64; i += 8) {
+    const int r = r0 + i, c = c0 + 2 * tx;
+    __nv_bfloat162 v = __floats2bfloat162_rn(0.f, 0.f);
+    if (r < R) {
+      if (in_pairs && c + 1 < C) v = *reinterpret_cast<const __nv_bfloat162*>(in + static_cast<size_t>(r) * C + c);
+      else {
+        if (c < C) v.x = in[static_cast<size_t>(r) * C + c];
+        if (c + 1 < C) v.y = in[static_cast<size_t>(r) * C + c + 1];
+      }
+    }
+    *reinterpret_cast<__nv_bfloat162*>(&tile[i][2 * tx]) = v;
   }
   __syncthreads();
-  for (int i = threadIdx.y; i < 32; i += 8) {
-    const int c = c0 + i, r = r0 + threadIdx.x;
-    if (c < C && r < R) out[static_cast<size_t>(c) * ldo + r] = tile[threadIdx.x][i];
+  for (int i = ty; i < 64; i += 8) {
+    const int c = c0 + i, r = r0 + 2 * tx;
+    if (c >= C) continue;
+    __nv_bfloat162 v;
+    v.x = tile[2 * tx][i];
+    v.y = tile[2 * tx + 1][i];
+    __nv_bfloat16* dst = out + static_cast<size_t>(c) * ldo + r;
+    if (out_pairs && r + 1 < R) *reinterpret_cast<__nv_bfloat162*>(dst) = v;
+    else {
+      if (r < R) dst[0] = v.x;
+      if (r + 1 < R) dst[1] = v.y;
+    }
   }
 }
 
@@ -216,14 +236,94 @@ layernorm_bwd_kernel(const float* __restrict__ x, const float* __restrict__ gamm
       outr[lane + 32 * i] = o;
     }
   }
+  // per-lane partials -> one sum per block in shared memory (warps take turns: no shared atomics) -> one atomicAdd per
+  // column and block.  (One atomicAdd per column and WARP was 7 M atomics on 1536 addresses: 220 us at 12608 x 768.)
+  __shared__ float red[2][D];
+  const int wib = threadIdx.x >> 5;
+  for (int w = 0; w < static_cast<int>(blockDim.x >> 5); ++w) {
+    if (wib == w) {
 #pragma unroll
-  for (int i = 0; i < VPL; ++i) {
-    const int c = (lane + 32 * i) * 4;
-    atomicAdd(dgamma + c, pg[i].x); atomicAdd(dgamma + c + 1, pg[i].y); atomicAdd(dgamma + c + 2, pg[i].z); atomicAdd(dgamma + c + 3, pg[i].w);
-    atomicAdd(dbeta + c, pb[i].x); atomicAdd(dbeta + c + 1, pb[i].y); atomicAdd(dbeta + c + 2, pb[i].z); atomicAdd(dbeta + c + 3, pb[i].w);
+      for (int i = 0; i < VPL; ++i) {
+        float4* rg = reinterpret_cast<float4*>(&red[0][0]) + lane + 32 * i;
+        float4* rb = reinterpret_cast<float4*>(&red[1][0]) + lane + 32 * i;
+        if (w == 0) { *rg = pg[i]; *rb = pb[i]; }
+        else {
+          float4 a = *rg, b = *rb;
+          a.x += pg[i].x; a.y += pg[i].y; a.z += pg[i].z; a.w += pg[i].w;
+          b.x += pb[i].x; b.y += pb[i].y; b.z += pb[i].z; b.w += pb[i].w;
+          *rg = a; *rb = b;
+        }
+      }
+    }
+    __syncthreads();
+  }
+  for (int c = threadIdx.x; c < D; c += blockDim.x) {
+    atomicAdd(dgamma + c, red[0][c]);
+    atomicAdd(dbeta + c, red[1][c]);
   }
 }
 
 // The attention backward lives in attention_bwd_tc.cuh (tcgen05).
+
+// ------------------------------------------------------------------------------- taps backward
+// Adjoint of ldit_resample_taps (R:dit_backbone.py:50-61): dout bf16 [B, oh, ow, D] (channels-last, the forward's
+// output layout) -> dx f32 [B, N, D] rows 1..P (the CLS row is not read by a tap: the caller zeroes it).  Gather form,
+// no atomics: the thread of token cell (gy, gx) walks the output pixels whose bilinear footprint (ATen rule,
+// align_corners = False, exactly as resample_taps_kernel) contains the cell and sums weight x gradient.
+// blockDim = (D/8, kTapPix), gridDim = (ceil(Gh*Gw / kTapPix), B).
+__device__ __forceinline__ float tap_axis_weight(int o, int g, int G, float inv_scale) {
+  const float s = fmaxf((o + 0.5f) * inv_scale - 0.5f, 0.f);
+  const int i0 = min(static_cast<int>(s), G - 1), i1 = min(i0 + 1, G - 1);
+  const float l = s - i0;
+  return (i0 == g ? 1.f - l : 0.f) + (i1 == g ? l : 0.f);
+}
+__global__ void __launch_bounds__(1024)
+resample_taps_bwd_kernel(const __nv_bfloat16* __restrict__ dout, float* __restrict__ dx, int N, int D, int Gh, int Gw, int oh, int ow,
+                         float inv_scale, float scale) {
+  const int cell = blockIdx.x * blockDim.y + threadIdx.y;
+  if (cell >= Gh * Gw) return;
+  const int b = blockIdx.y;
+  const int gy = cell / Gw, gx = cell - gy * Gw;
+  // candidate outputs: source coordinate within one cell of (gy, gx); everything towards the border at the border cells
+  const int oy_lo = gy == 0 ? 0 : max(0, static_cast<int>(floorf((gy - 0.5f) * scale - 0.5f)) - 1);
+  const int oy_hi = gy == Gh - 1 ? oh - 1 : min(oh - 1, static_cast<int>(ceilf((gy + 1.5f) * scale - 0.5f)) + 1);
+  const int ox_lo = gx == 0 ? 0 : max(0, static_cast<int>(floorf((gx - 0.5f) * scale - 0.5f)) - 1);
+  const int ox_hi = gx == Gw - 1 ? ow - 1 : min(ow - 1, static_cast<int>(ceilf((gx + 1.5f) * scale - 0.5f)) + 1);
+  float acc[8];
+#pragma unroll
+  for (int i = 0; i < 8; ++i) acc[i] = 0.f;
+  const __nv_bfloat16* base = dout + static_cast<size_t>(b) * oh * ow * D + threadIdx.x * 8;
+  for (int oy = oy_lo; oy <= oy_hi; ++oy) {
+    const float wy = tap_axis_weight(oy, gy, Gh, inv_scale);
+    if (wy == 0.f) continue;
+    for (int ox = ox_lo; ox <= ox_hi; ++ox) {
+      const float w = wy * tap_axis_weight(ox, gx, Gw, inv_scale);
+      if (w == 0.f) continue;
+      float v[8];
+      unpack8(__ldg(reinterpret_cast<const uint4*>(base + static_cast<size_t>(oy * ow + ox) * D)), v);
+#pragma unroll
+      for (int i = 0; i < 8; ++i) acc[i] = fmaf(w, v[i], acc[i]);
+    }
+  }
+  float4* dst = reinterpret_cast<float4*>(dx + (static_cast<size_t>(b) * N + 1 + cell) * D + threadIdx.x * 8);
+  dst[0] = make_float4(acc[0], acc[1], acc[2], acc[3]);
+  dst[1] = make_float4(acc[4], acc[5], acc[6], acc[7]);
+}
+
+// out f32 [R] += sum over b of x f32 [B, R]   (position / CLS embedding gradients: every image adds the same rows; R % 4 == 0)
+__global__ void __launch_bounds__(256)
+batch_sum_kernel(const float* __restrict__ x, float* __restrict__ out, int B, int R) {
+  const int i = (blockIdx.x * blockDim.x + threadIdx.x) * 4;
+  if (i >= R) return;
+  float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+  for (int b = 0; b < B; ++b) {
+    const float4 v = __ldg(reinterpret_cast<const float4*>(x + static_cast<size_t>(b) * R + i));
+    acc.x += v.x; acc.y += v.y; acc.z += v.z; acc.w += v.w;
+  }
+  float4* o = reinterpret_cast<float4*>(out + i);
+  float4 c = *o;
+  c.x += acc.x; c.y += acc.y; c.z += acc.z; c.w += acc.w;
+  *o = c;
+}
 
 }  // namespace ldit

@@ -1157,7 +1157,7 @@ int ldit_conv3x3_bias_f32(const void* in, const void* w, const void* bias, void*
 int ldit_transpose_bf16(const void* in, void* out, int R, int C, int ld_out, void* stream) {
   if (!in || !out) return LDIT_E_NULL;
   if (R <= 0 || C <= 0 || ld_out < R) return LDIT_E_SHAPE;
-  transpose_bf16_kernel<<<dim3((C + 31) / 32, (R + 31) / 32), dim3(32, 8), 0, static_cast<cudaStream_t>(stream)>>>(
+  transpose_bf16_kernel<<<dim3((C + 63) / 64, (R + 63) / 64), dim3(32, 8), 0, static_cast<cudaStream_t>(stream)>>>(
       static_cast<const __nv_bfloat16*>(in), static_cast<__nv_bfloat16*>(out), R, C, ld_out);
   return check_launch();
 }
@@ -1257,6 +1257,27 @@ int ldit_attention_bwd(const void* qkv, const void* dctx, void* dqkv, int B, int
   cudaError_t e = ensure_smem(attention_bwd_tc_kernel, smem, false);
   if (e != cudaSuccess) return static_cast<int>(e);
   attention_bwd_tc_kernel<<<B * heads, kAbtThreads, smem, static_cast<cudaStream_t>(stream)>>>(tmQKV, tmDO, a);
+  return check_launch();
+}
+
+int ldit_resample_taps_bwd(const void* dout, void* dx, int B, int Gh, int Gw, int D, float scale, void* stream) {
+  if (!dout || !dx) return LDIT_E_NULL;
+  if (B <= 0 || Gh <= 0 || Gw <= 0 || D <= 0 || (D % 8) || !(scale > 0.f)) return LDIT_E_SHAPE;
+  if (!aligned16(dout) || !aligned16(dx)) return LDIT_E_ALIGN;
+  const int oh = static_cast<int>(floorf(Gh * scale)), ow = static_cast<int>(floorf(Gw * scale));
+  if (oh <= 0 || ow <= 0 || D / 8 * kTapPix > 1024 || B > 65535) return LDIT_E_SHAPE;
+  dim3 block(D / 8, kTapPix);
+  dim3 grid((Gh * Gw + kTapPix - 1) / kTapPix, B);
+  resample_taps_bwd_kernel<<<grid, block, 0, static_cast<cudaStream_t>(stream)>>>(
+      static_cast<const __nv_bfloat16*>(dout), static_cast<float*>(dx), Gh * Gw + 1, D, Gh, Gw, oh, ow, 1.0f / scale, scale);
+  return check_launch();
+}
+
+int ldit_batch_sum(const void* x, void* out, int B, int R, void* stream) {
+  if (!x || !out) return LDIT_E_NULL;
+  if (B <= 0 || R <= 0 || (R % 4)) return LDIT_E_SHAPE;
+  if (!aligned16(x) || !aligned16(out)) return LDIT_E_ALIGN;
+  batch_sum_kernel<<<(R / 4 + 255) / 256, 256, 0, static_cast<cudaStream_t>(stream)>>>(static_cast<const float*>(x), static_cast<float*>(out), B, R);
   return check_launch();
 }
 

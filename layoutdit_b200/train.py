@@ -232,6 +232,128 @@ class TrainableEncoder(nn.Module):
         return x.reshape(B, N, D)
 
 
+# ----------------------------------------------------------------------------------- embeddings and taps
+class PatchEmbedFunction(torch.autograd.Function):
+    """``BeitEmbeddings.forward`` (HF:161-184, ``bool_masked_pos=None``, dropout 0) at the native grid:
+    ``x [B*N, D] f32 = cat(cls, conv16(pixels)) + position_embeddings``, differentiable in the projection weight / bias,
+    the CLS token and the position table (not in the pixels).  Forward = the inference entry point ``ldit_patch_embed``
+    (fp32 pages: gather pass + CLS rows + GEMM); backward: the projection's wgrad is the same transposed-copy GEMM as the
+    layers', its A operand the im2col matrix the forward left in its scratch."""
+
+    @staticmethod
+    def forward(ctx, pixels, geom, w, b, cls, pos):
+        B, H, W, D = geom
+        Gh, Gw = H // 16, W // 16
+        P, N = Gh * Gw, Gh * Gw + 1
+        dev = pixels.device
+        k = _K(dev)
+        st = _st(dev)
+        px = pixels.detach().to(torch.float32).contiguous()
+        wb = w.detach().reshape(D, -1).to(dev, _BF).contiguous()
+        bias = b.detach().to(dev, torch.float32).contiguous()
+        clsv = cls.detach().reshape(D).to(dev, torch.float32).contiguous()
+        if pos is not None:
+            if pos.shape[1] != N:
+                raise NotImplementedError("the training path runs at the native grid (the position table's bicubic resize has no backward yet)")
+            pt = pos.detach().to(dev, torch.float32).contiguous()
+            pos_bias = torch.empty(P, D, device=dev, dtype=torch.float32)
+            cls_pos = torch.empty(D, device=dev, dtype=torch.float32)
+            _lib.check(k.lib.ldit_resize_rows(pt[0, 1:].data_ptr(), pos_bias.data_ptr(), bias.data_ptr(), Gh, Gw, Gh, Gw, D, 1, st), "ldit_resize_rows")
+            _lib.check(k.lib.ldit_resize_rows(pt[0, :1].data_ptr(), cls_pos.data_ptr(), clsv.data_ptr(), 1, 1, 1, 1, D, 1, st), "ldit_resize_rows")
+        else:
+            pos_bias, cls_pos = bias.expand(P, D).contiguous(), clsv
+        scratch = torch.empty(k.lib.ldit_patch_embed_scratch_bytes(B, H, W) // 2, device=dev, dtype=_BF)
+        x = torch.empty(B * N, D, device=dev, dtype=torch.float32)
+        _lib.check(k.lib.ldit_patch_embed(px.data_ptr(), _lib.DTYPE_F32, wb.data_ptr(), pos_bias.data_ptr(), cls_pos.data_ptr(),
+                                          scratch.data_ptr(), x.data_ptr(), B, H, W, D, st), "ldit_patch_embed")
+        ctx.geom, ctx.has_pos, ctx.wshape = (B, Gh, Gw, D), pos is not None, tuple(w.shape)
+        ctx.save_for_backward(scratch)
+        return x
+
+    @staticmethod
+    def backward(ctx, dx):
+        B, Gh, Gw, D = ctx.geom
+        P, N = Gh * Gw, Gh * Gw + 1
+        (scratch,) = ctx.saved_tensors
+        dev = dx.device
+        k = _K(dev)
+        st = _st(dev)
+        dx = dx.detach().to(torch.float32).contiguous()
+        a = scratch[: B * P * 768].view(B * P, 768)                        # im2col(pixels), bf16
+        dtok = torch.empty(B * P, D, device=dev, dtype=_BF)                # patch rows of dx, bf16 (scale 1 = CLS-less cast)
+        _lib.check(k.lib.ldit_resample_taps(dx.data_ptr(), dtok.data_ptr(), B, Gh, Gw, D, 1.0, st), "ldit_resample_taps")
+        db = torch.zeros(D, device=dev, dtype=torch.float32)
+        k.colsum(dtok, db)
+        dw = torch.zeros(D, 768, device=dev, dtype=torch.float32)
+        k.gemm_acc(k.transpose(dtok), k.transpose(a), dw)                  # [D, B P] x [768, B P]^T
+        dsum = torch.zeros(N * D, device=dev, dtype=torch.float32)         # every image adds the same cls / position rows
+        _lib.check(k.lib.ldit_batch_sum(dx.data_ptr(), dsum.data_ptr(), B, N * D, st), "ldit_batch_sum")
+        dcls = dsum[:D].clone().view(1, 1, D)
+        dpos = dsum.view(1, N, D) if ctx.has_pos else None
+        return None, None, dw.view(ctx.wshape), db, dcls, dpos
+
+
+class TapFunction(torch.autograd.Function):
+    """One feature tap (R:dit_backbone.py:50-61): patch rows of a hidden state -> ``[B, D, floor(Gh s), floor(Gw s)]``
+    bf16 (channels-last memory), bilinear with ``scale_factor = s``; backward = ``ldit_resample_taps_bwd``."""
+
+    @staticmethod
+    def forward(ctx, x, geom):
+        B, Gh, Gw, D, scale = geom
+        dev = x.device
+        oh, ow = int(Gh * scale), int(Gw * scale)
+        out = torch.empty(B, oh, ow, D, device=dev, dtype=_BF)
+        xc = x.detach().contiguous()
+        _lib.check(_lib.load().ldit_resample_taps(xc.data_ptr(), out.data_ptr(), B, Gh, Gw, D, float(scale), _st(dev)), "ldit_resample_taps")
+        ctx.geom = geom
+        return out.permute(0, 3, 1, 2)
+
+    @staticmethod
+    def backward(ctx, dout):
+        B, Gh, Gw, D, scale = ctx.geom
+        dev = dout.device
+        dn = dout.detach().permute(0, 2, 3, 1).to(_BF).contiguous()
+        dx = torch.zeros(B * (Gh * Gw + 1), D, device=dev, dtype=torch.float32)
+        _lib.check(_lib.load().ldit_resample_taps_bwd(dn.data_ptr(), dx.data_ptr(), B, Gh, Gw, D, float(scale), _st(dev)), "ldit_resample_taps_bwd")
+        return dx, None
+
+
+class TrainableBackbone(nn.Module):
+    """``DiTBackbone.forward`` (R:dit_backbone.py:38-62) differentiable end to end through the library's kernels:
+    embeddings -> L x ``BeitLayerFunction`` -> four taps.  Same outputs as the inference module
+    (``OrderedDict{p2..p5}``, bf16, channels-last); same restrictions as ``TrainableEncoder`` plus the native grid."""
+
+    SCALES = (4.0, 2.0, 1.0, 0.5)
+
+    def __init__(self, params: DiTParameters, cfg: DiTConfig):
+        super().__init__()
+        self.encoder = TrainableEncoder(params, cfg)     # validates the configuration
+        self.params_tree, self.cfg = params, cfg
+        d = cfg.num_hidden_layers
+        self.layer_idxs = [d // 3, d // 2, 2 * d // 3, d]
+
+    def forward(self, pixels: torch.Tensor):
+        from collections import OrderedDict
+        if pixels.dim() != 4 or pixels.shape[1] != 3 or pixels.shape[2] % 16 or pixels.shape[3] % 16:
+            raise ValueError("pixels must be [B, 3, H, W] with H and W multiples of 16")
+        if not pixels.is_cuda:
+            raise _lib.LditError("TrainableBackbone needs CUDA tensors (there is no CPU path)")
+        B, _, H, W = pixels.shape
+        cfg, e = self.cfg, self.params_tree.embeddings
+        D, Gh, Gw = cfg.hidden_size, H // 16, W // 16
+        pos = getattr(e, "position_embeddings", None)
+        x = PatchEmbedFunction.apply(pixels, (B, H, W, D), e.patch_embeddings.projection.weight, e.patch_embeddings.projection.bias,
+                                     e.cls_token, pos)
+        geom = (B, Gh * Gw + 1, cfg.num_attention_heads, Gh, Gw, float(cfg.layer_norm_eps))
+        taps = {}
+        for i, layer in enumerate(self.params_tree.encoder.layer, start=1):
+            x = BeitLayerFunction.apply(x, geom, *layer_params(layer))
+            for j, idx in enumerate(self.layer_idxs):          # shallow models tap one layer more than once
+                if idx == i:
+                    taps[j] = TapFunction.apply(x, (B, Gh, Gw, D, self.SCALES[j]))
+        return OrderedDict((f"p{j + 2}", taps[j]) for j in range(4))
+
+
 # ----------------------------------------------------------------------------------- data-parallel gradients
 class GradientBuckets:
     """Bucketed gradient all-reduce of a data-parallel step (BASELINE config 5): parameters are packed, in reverse

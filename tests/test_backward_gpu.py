@@ -182,3 +182,66 @@ def test_base_size_layer_gradients(cuda_device):
         if name.startswith("encoder.layer.0."):
             e = _rel(p.grad, sdg[name].grad)
             assert e < GRAD_TOL, f"{name}: {e:.3e}"
+
+
+# --------------------------------------------------------------------- taps, embeddings, the whole backbone
+@pytest.mark.parametrize("scale", [4.0, 2.0, 1.0, 0.5])
+@pytest.mark.parametrize("B,Gh,Gw,D", [(2, 4, 4, 128), (1, 5, 7, 128), (2, 14, 14, 768)])
+def test_taps_backward_is_the_adjoint_of_interpolate(lib, B, Gh, Gw, D, scale):
+    import torch.nn.functional as F
+    N = Gh * Gw + 1
+    oh, ow = int(Gh * scale), int(Gw * scale)
+    g = torch.Generator(device="cuda").manual_seed(int(scale * 10) + Gh)
+    dout = torch.randn(B, oh, ow, D, device="cuda", generator=g).to(torch.bfloat16)
+    dx = torch.full((B * N, D), float("nan"), device="cuda")
+    dx.view(B, N, D)[:, 0] = 0
+    _lib.check(lib.ldit_resample_taps_bwd(dout.data_ptr(), dx.data_ptr(), B, Gh, Gw, D, scale, _st()), "taps_bwd")
+    x = torch.zeros(B, N, D, device="cuda", dtype=torch.float64, requires_grad=True)
+    t = x[:, 1:].permute(0, 2, 1).reshape(B, D, Gh, Gw)
+    y = t if scale == 1.0 else F.interpolate(t, scale_factor=scale, mode="bilinear", align_corners=False)
+    y.backward(dout.permute(0, 3, 1, 2).double())
+    assert torch.isfinite(dx).all()
+    torch.testing.assert_close(dx.view(B, N, D).double(), x.grad, rtol=1e-5, atol=1e-5)
+
+
+@pytest.mark.parametrize("layer_scale,B,G,abs_pos", [(0.1, 2, 4, True), (0.1, 2, 14, True), (0.0, 1, 4, False)])
+def test_backbone_gradients_match_oracle_autograd(cuda_device, layer_scale, B, G, abs_pos):
+    """DiTBackbone.forward end to end (embeddings, 6 layers, 4 taps) under a dense upstream gradient on every tap:
+    every parameter gradient against torch.autograd through the fp64 oracle."""
+    from layoutdit_b200.train import TrainableBackbone
+    cfg = DiTConfig(hidden_size=128, num_hidden_layers=6, num_attention_heads=2, intermediate_size=256, image_size=G * 16,
+                    layer_scale_init_value=layer_scale, use_absolute_position_embeddings=abs_pos)
+    sd = make_state_dict(cfg, 79, True)
+    gen = torch.Generator().manual_seed(7)
+    pages = torch.rand(B, 3, G * 16, G * 16, generator=gen)
+    tree = DiTParameters(cfg)
+    tree.load_state_dict(sd)
+    tree = tree.cuda()
+    feats = TrainableBackbone(tree, cfg)(pages.cuda())
+    wts = {k: torch.randn(v.shape, generator=gen) for k, v in feats.items()}
+    sum((feats[k].float() * wts[k].cuda()).sum() for k in feats).backward()
+
+    sd64 = {k: v.double().requires_grad_(True) for k, v in sd.items() if v.is_floating_point()}
+    cd = cfg.to_dict()
+    hs = dit_oracle.hidden_states(sd64, cd, pages.double())
+    loss = 0.0
+    for j, (idx, scale) in enumerate(zip(dit_oracle.tap_layer_indices(cfg.num_hidden_layers), dit_oracle.TAP_SCALES)):
+        t = hs[idx][:, 1:, :].permute(0, 2, 1).reshape(B, cfg.hidden_size, G, G)
+        if scale != 1.0:
+            t = dit_oracle.resample_bilinear(t, scale)
+        assert _rel(feats[f"p{j + 2}"].detach().float(), t.detach()) < 1e-2
+        loss = loss + (t * wts[f"p{j + 2}"].double()).sum()
+    loss.backward()
+    worst, seen = 0.0, 0
+    for name, p in tree.named_parameters():
+        if name.startswith("pooler") or name not in sd64:
+            continue
+        ref = sd64[name].grad
+        if ref is None:
+            continue
+        assert p.grad is not None, name
+        e = _rel(p.grad, ref)
+        worst, seen = max(worst, e), seen + 1
+        assert e < GRAD_TOL, f"{name}: rel-Frobenius {e:.3e}"
+    assert seen == 6 * (17 if layer_scale > 0 else 15) + 3 + int(abs_pos)   # every layer tensor, projection w / b, cls (, positions)
+    print(f"{seen} parameter gradients, worst rel-Fro {worst:.2e}")
