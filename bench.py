@@ -247,7 +247,7 @@ def run_train_line(args, cfg, fac, B, H, W, dev, rank, world, peaks):
     pages = synthetic_pages(B, H, W, 1234 + rank).to(dev)
 
     def loss_of(feats):   # stand-in for the detection head's loss: touches every tap densely
-        return sum(f.float().square().mean() for f in feats.values())
+        return sum(f.square().mean(dtype=torch.float32) for f in feats.values())
 
     def timed(step):
         for _ in range(args.warmup):

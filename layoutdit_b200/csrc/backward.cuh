@@ -155,6 +155,7 @@ scale_residual_bwd_kernel(const float* __restrict__ dy, const __nv_bfloat16* __r
     l[0] = l0.x; l[1] = l0.y; l[2] = l0.z; l[3] = l0.w; l[4] = l1.x; l[5] = l1.y; l[6] = l1.z; l[7] = l1.w;
   }
   const int r_lo = blockIdx.y * rows_per_block, r_hi = min(R, r_lo + rows_per_block);
+#pragma unroll 4
   for (int r = r_lo; r < r_hi; ++r) {
     const size_t i = static_cast<size_t>(r) * d8 + cg;
     const float4 g0 = __ldg(reinterpret_cast<const float4*>(dy) + 2 * i), g1 = __ldg(reinterpret_cast<const float4*>(dy) + 2 * i + 1);
