@@ -201,6 +201,10 @@ int ldit_scale_residual_bwd(const void* dy, const void* branch, const void* lam,
  * dx_in may be NULL and may alias dx_out.  Row statistics are recomputed from x. */
 int ldit_layernorm_bwd(const void* x, const void* gamma, const void* dy, const void* dx_in, void* dx_out, void* dgamma, void* dbeta,
                        int rows, int D, float eps, void* stream);
+/* Weight gradient of nn.Linear: dW f32 [Nw, Kw] += dY^T A with dY bf16 [T, Nw], A bf16 [T, Kw] row-major (T = tokens).
+ * tcgen05 GEMM with MN-major operands (no transposed copies) and a split contraction (fp32 reduce-add; the summation
+ * order of the pieces is not fixed).  Nw, Kw multiples of 8. */
+int ldit_gemm_wgrad(const void* dY, const void* A, void* dW, int T, int Nw, int Kw, void* stream);
 /* Backward of ldit_attention without relative-position bias: dqkv bf16 [B*N, 3D] from qkv and dctx bf16 [B*N, D].
  * tcgen05 kernel, one CTA per (image, head), P recomputed from qkv (nothing else is kept from the forward);
  * N <= 256 (two 128-row query tiles x two 128-key halves fill TMEM), LDIT_E_UNSUPPORTED beyond. */

@@ -34,6 +34,11 @@ constexpr int kAbtTile = 16384;                         // one 128 x 64 bf16 til
 constexpr int kAbtSmemTiles = 14 * kAbtTile;            // Q, K, V, dO (2 each) + P^T, dS^T, dS (2 atoms each)
 constexpr int kAbtTmemCols = 512;
 
+__device__ __forceinline__ float abt_ex2(float x) {   // MUFU.EX2 (2 ulp; exp2(-inf) = +0), as the forward
+  float y;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
 // element (row r, column c) of a [128 x 64] bf16 tile with rows of 128 B and the 128-byte swizzle: byte offset
 __device__ __forceinline__ uint32_t abt_sw128(int r, int c) {
   return static_cast<uint32_t>(r * 128 + ((((c >> 3) ^ (r & 7)) << 4) | ((c & 7) << 1)));
@@ -135,9 +140,9 @@ attention_bwd_tc_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_
         cm = fmaxf(cm, s);
       }
       if (cm != -INFINITY) {                             // a chunk entirely past the last key contributes nothing
-        if (cm > m) { l *= exp2f(m - cm); m = cm; }    // first chunk: 0 * exp2(-inf) = 0
+        if (cm > m) { l *= abt_ex2(m - cm); m = cm; }    // first chunk: 0 * exp2(-inf) = 0
 #pragma unroll
-        for (int i = 0; i < 16; ++i) l += exp2f(__uint_as_float(r[i]) - m);
+        for (int i = 0; i < 16; ++i) l += abt_ex2(__uint_as_float(r[i]) - m);
       }
     }
     xch[(half * 128 + row) * 2] = m;
@@ -146,7 +151,7 @@ attention_bwd_tc_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_
     {
       const float m2 = xch[((half ^ 1) * 128 + row) * 2], l2 = xch[((half ^ 1) * 128 + row) * 2 + 1];
       const float mm = fmaxf(m, m2);                     // key 0 always exists: at least one of the two is finite
-      l = ((m == -INFINITY) ? 0.f : l * exp2f(m - mm)) + ((m2 == -INFINITY) ? 0.f : l2 * exp2f(m2 - mm));
+      l = ((m == -INFINITY) ? 0.f : l * abt_ex2(m - mm)) + ((m2 == -INFINITY) ? 0.f : l2 * abt_ex2(m2 - mm));
       m = mm;
     }
     __syncthreads();
@@ -161,7 +166,7 @@ attention_bwd_tc_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_
       tmem_wait_ld16(q);
 #pragma unroll
       for (int i = 0; i < 16; ++i)
-        if (c * 16 + i < a.N) dl = fmaf(exp2f(__uint_as_float(r[i]) * a.scale_log2e - m) * linv, __uint_as_float(q[i]), dl);
+        if (c * 16 + i < a.N) dl = fmaf(abt_ex2(__uint_as_float(r[i]) * a.scale_log2e - m) * linv, __uint_as_float(q[i]), dl);
     }
     xch[half * 128 + row] = dl;
     __syncthreads();
@@ -194,7 +199,7 @@ attention_bwd_tc_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_
 #pragma unroll
           for (int e = 0; e < 2; ++e) {
             const int key = kh * 128 + c * 16 + i + e;
-            p[e] = (key < a.N) ? exp2f(__uint_as_float(r[i + e]) * a.scale_log2e - m) * linv : 0.f;
+            p[e] = (key < a.N) ? abt_ex2(__uint_as_float(r[i + e]) * a.scale_log2e - m) * linv : 0.f;
             ds[e] = p[e] * (__uint_as_float(q[i + e]) - dl) * a.scale;
             const int kl = c * 16 + i + e;                // key inside the half = row of the transposed tiles
             const uint32_t off = static_cast<uint32_t>(row >> 6) * kAbtTile + abt_sw128(kl, row & 63);

@@ -141,34 +141,47 @@ scale_residual_fwd_kernel(const float* __restrict__ x, const __nv_bfloat16* __re
   reinterpret_cast<float4*>(y)[2 * i + 1] = make_float4(x1.x + l[4] * b[4], x1.y + l[5] * b[5], x1.z + l[6] * b[6], x1.w + l[7] * b[7]);
 }
 // backward: dbranch bf16 = lam (.) dy;  dlam f32 [D] += column sums of dy (.) branch (skipped when dlam == nullptr).
-// Block (D/8 column groups up to 128, rows slice): thread owns 8 columns, walks its slice of the rows.
-__global__ void __launch_bounds__(256)
+// Block (min(D/8, 128) column groups, 8 row lanes) owns rows_per_block rows: thread (cg, ry) walks rows ry, ry + 8, ..
+// of the slice, the 8 row lanes are summed through shared memory, one atomicAdd per column and block.
+__global__ void __launch_bounds__(1024)
 scale_residual_bwd_kernel(const float* __restrict__ dy, const __nv_bfloat16* __restrict__ branch, const float* __restrict__ lam,
                           __nv_bfloat16* __restrict__ dbranch, float* __restrict__ dlam, int R, int D, int rows_per_block) {
+  __shared__ float red[8][128 * 8 + 8];
   const int d8 = D / 8;
   const int cg = blockIdx.x * blockDim.x + threadIdx.x;      // column group
-  if (cg >= d8) return;
+  const bool live = cg < d8;
   const int c = cg * 8;
   float l[8] = {1.f, 1.f, 1.f, 1.f, 1.f, 1.f, 1.f, 1.f}, acc[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
-  if (lam != nullptr) {
+  if (live && lam != nullptr) {
     const float4 l0 = __ldg(reinterpret_cast<const float4*>(lam + c)), l1 = __ldg(reinterpret_cast<const float4*>(lam + c) + 1);
     l[0] = l0.x; l[1] = l0.y; l[2] = l0.z; l[3] = l0.w; l[4] = l1.x; l[5] = l1.y; l[6] = l1.z; l[7] = l1.w;
   }
   const int r_lo = blockIdx.y * rows_per_block, r_hi = min(R, r_lo + rows_per_block);
-#pragma unroll 4
-  for (int r = r_lo; r < r_hi; ++r) {
-    const size_t i = static_cast<size_t>(r) * d8 + cg;
-    const float4 g0 = __ldg(reinterpret_cast<const float4*>(dy) + 2 * i), g1 = __ldg(reinterpret_cast<const float4*>(dy) + 2 * i + 1);
-    const float g[8] = {g0.x, g0.y, g0.z, g0.w, g1.x, g1.y, g1.z, g1.w};
-    float b[8], o[8];
-    unpack8(__ldg(reinterpret_cast<const uint4*>(branch) + i), b);
+  if (live) {
+#pragma unroll 2
+    for (int r = r_lo + threadIdx.y; r < r_hi; r += 8) {
+      const size_t i = static_cast<size_t>(r) * d8 + cg;
+      const float4 g0 = __ldg(reinterpret_cast<const float4*>(dy) + 2 * i), g1 = __ldg(reinterpret_cast<const float4*>(dy) + 2 * i + 1);
+      const float g[8] = {g0.x, g0.y, g0.z, g0.w, g1.x, g1.y, g1.z, g1.w};
+      float b[8], o[8];
+      unpack8(__ldg(reinterpret_cast<const uint4*>(branch) + i), b);
 #pragma unroll
-    for (int e = 0; e < 8; ++e) { o[e] = l[e] * g[e]; acc[e] += g[e] * b[e]; }
-    reinterpret_cast<uint4*>(dbranch)[i] = pack8(o);
+      for (int e = 0; e < 8; ++e) { o[e] = l[e] * g[e]; acc[e] += g[e] * b[e]; }
+      reinterpret_cast<uint4*>(dbranch)[i] = pack8(o);
+    }
   }
-  if (dlam != nullptr) {
+  if (dlam == nullptr) return;
 #pragma unroll
-    for (int e = 0; e < 8; ++e) atomicAdd(dlam + c + e, acc[e]);
+  for (int e = 0; e < 8; ++e) red[threadIdx.y][threadIdx.x * 8 + e] = acc[e];
+  __syncthreads();
+  if (threadIdx.y == 0 && live) {
+#pragma unroll
+    for (int e = 0; e < 8; ++e) {
+      float t = 0.f;
+#pragma unroll
+      for (int y = 0; y < 8; ++y) t += red[y][threadIdx.x * 8 + e];
+      atomicAdd(dlam + c + e, t);
+    }
   }
 }
 
@@ -178,7 +191,7 @@ scale_residual_bwd_kernel(const float* __restrict__ dy, const __nv_bfloat16* __r
 //   dgamma += sum_r dy xhat,  dbeta += sum_r dy        (per-lane partials, one atomicAdd per column and warp at the end)
 // dx_in may be nullptr (= 0) and may alias dx_out.  Statistics are recomputed from x (two-pass, as the forward).
 template <int VPL>
-__global__ void __launch_bounds__(256)
+__global__ void __launch_bounds__(256, (VPL <= 6) ? 2 : 1)   // 152 registers unconstrained at VPL = 6: one block per SM
 layernorm_bwd_kernel(const float* __restrict__ x, const float* __restrict__ gamma, const __nv_bfloat16* __restrict__ dy,
                      const float* dx_in, float* dx_out, float* __restrict__ dgamma, float* __restrict__ dbeta, int rows, float eps) {
   constexpr int D = 128 * VPL;
@@ -191,6 +204,16 @@ layernorm_bwd_kernel(const float* __restrict__ x, const float* __restrict__ gamm
   for (int row = warp; row < rows; row += nwarps) {
     const float4* xr = reinterpret_cast<const float4*>(x + static_cast<size_t>(row) * D);
     const uint2* gr = reinterpret_cast<const uint2*>(dy + static_cast<size_t>(row) * D);
+    if (row + nwarps < rows) {
+      // the three streams of this warp's NEXT row into L2 while this row's dependent load / reduce phases run
+      // (one 128-byte line per lane and pass; no registers are held)
+      const size_t nxt = static_cast<size_t>(row + nwarps) * D;
+      for (int l = lane * 32; l < D; l += 32 * 32) {
+        asm volatile("prefetch.global.L2 [%0];" ::"l"(x + nxt + l));
+        if (dx_in) asm volatile("prefetch.global.L2 [%0];" ::"l"(dx_in + nxt + l));
+      }
+      for (int l = lane * 64; l < D; l += 32 * 64) asm volatile("prefetch.global.L2 [%0];" ::"l"(dy + nxt + l));
+    }
     float4 v[VPL], g[VPL];
     float sum = 0.f;
 #pragma unroll

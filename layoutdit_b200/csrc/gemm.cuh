@@ -34,13 +34,16 @@
 
 namespace ldit {
 
-enum : int { EPI_BIAS = 0, EPI_BIAS_GELU = 1, EPI_SCALE_RESID = 2, EPI_PATCH = 3, EPI_CONV_BIAS = 4, EPI_CONV_BIAS_F32 = 5, EPI_BIAS_SCALE = 6, EPI_PATCH_TMA = 7 };
+enum : int { EPI_BIAS = 0, EPI_BIAS_GELU = 1, EPI_SCALE_RESID = 2, EPI_PATCH = 3, EPI_CONV_BIAS = 4, EPI_CONV_BIAS_F32 = 5, EPI_BIAS_SCALE = 6, EPI_PATCH_TMA = 7,
+              EPI_WGRAD = 8 };   // EPI_WGRAD: C f32 [M, N] += A^T B with A [K, M] and B [K, N] row-major (both operands MN-major in smem);
+                                 // the epilogue is EPI_SCALE_RESID's fp32 reduce-add without bias / scale / rounding
+__host__ __device__ constexpr bool epi_is_resid(int epi) { return epi == EPI_SCALE_RESID || epi == EPI_WGRAD; }
 // EPI_PATCH_TMA: the patch embedding with its A operand gathered by TMA straight out of the NCHW page batch (16-bit pixels):
 // no im2col matrix, CLS rows written by the same kernel
 __host__ __device__ constexpr bool epi_is_patch(int epi) { return epi == EPI_PATCH || epi == EPI_PATCH_TMA; }
 // EPI_BIAS_SCALE: bf16 out = scale (.) (acc + bias) -- the layer-scaled branch of a residual block, stored for a fused
 // residual-add + LayerNorm kernel to pick up (rowwise.cuh) instead of being reduce-added into the fp32 stream here
-__host__ __device__ constexpr bool epi_has_scale(int epi) { return epi == EPI_SCALE_RESID || epi == EPI_BIAS_SCALE; }
+__host__ __device__ constexpr bool epi_has_scale(int epi) { return epi == EPI_SCALE_RESID || epi == EPI_BIAS_SCALE || epi == EPI_WGRAD; }
 // EPI_CONV_BIAS_F32: the same convolution with an fp32 output map (the detection heads behind the FPN hold fp32 weights)
 __host__ __device__ constexpr bool epi_is_conv(int epi) { return epi == EPI_CONV_BIAS || epi == EPI_CONV_BIAS_F32; }
 
@@ -63,6 +66,7 @@ struct GemmArgs {
   int a_f16;           // both operands fp16 (pixels as the reference feeds them under autocast + an fp16 copy of the weights)
   const float* cls;    // [N] fp32 = cls_token + position row 0, written to token row 0 of every image
   int num_m_blocks, num_n_blocks;
+  int ksplit, kb_per_split;   // EPI_WGRAD: pieces of the K range and 64-wide k-blocks per piece
   int round_bf16;      // EPI_SCALE_RESID: round scale * (acc + bias) to bf16 before the fp32 reduce-add, so that the residual stream
                        // gets bit for bit what the deferred form (EPI_BIAS_SCALE + add_layernorm_kernel) adds -- the forward's
                        // numbers then do not depend on which of the two forms a geometry uses.  0 for the wgrad accumulation.
@@ -123,7 +127,7 @@ template <int BN, int EPI, int CTAS>
 struct GemmCfg {
   static_assert(BN == 128 || BN == 192 || BN == 256, "BN");
   static_assert(CTAS == 1 || CTAS == 2, "CTAS");
-  static constexpr bool OUT_F32 = (EPI == EPI_SCALE_RESID || epi_is_patch(EPI) || EPI == EPI_CONV_BIAS_F32);
+  static constexpr bool OUT_F32 = (epi_is_resid(EPI) || epi_is_patch(EPI) || EPI == EPI_CONV_BIAS_F32);
   static constexpr int TILE_M = kBM * CTAS;
   static constexpr int A_BYTES = kBM * kBK * 2;
   static constexpr int B_ROWS = BN / CTAS;            // rows of W staged by each CTA
@@ -255,7 +259,10 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
   pdl_wait();   // the prologue above touched no global memory; everything below may
   const uint32_t tmem_base = *tmem_slot;
 
-  const int num_tiles = g.num_m_blocks * g.num_n_blocks;
+  // EPI_WGRAD: the contraction (tokens) is long and the output small, so the K range is cut into g.ksplit pieces that all
+  // reduce-add into the same fp32 tile; work item = (k piece, m block, n block)
+  const int mn_tiles = g.num_m_blocks * g.num_n_blocks;
+  const int num_tiles = (EPI == EPI_WGRAD) ? mn_tiles * g.ksplit : mn_tiles;
   const int nkb = (g.K + kBK - 1) / kBK;
 
   // Producer and MMA loops are executed by ALL lanes of their warp (warp-uniform control flow,
@@ -271,7 +278,10 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
     int stage = 0;
     uint32_t phase = 0;
     int pti = 0;
-    for (int tile = cluster_id; tile < num_tiles; tile += num_clusters, ++pti) {
+    for (int item = cluster_id; item < num_tiles; item += num_clusters, ++pti) {
+      const int tile = (EPI == EPI_WGRAD) ? item % mn_tiles : item;
+      const int kb0 = (EPI == EPI_WGRAD) ? (item / mn_tiles) * g.kb_per_split : 0;
+      const int kb1 = (EPI == EPI_WGRAD) ? min(nkb, kb0 + g.kb_per_split) : nkb;
       const int mblk = g.m_reverse ? g.num_m_blocks - 1 - tile / g.num_n_blocks : tile / g.num_n_blocks;
       const int m0 = mblk * Cfg::TILE_M + static_cast<int>(rank) * kBM;
       const int n0 = (tile % g.num_n_blocks) * BN + static_cast<int>(rank) * Cfg::B_ROWS;
@@ -292,11 +302,11 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
       }
       long long* ptl = (LDIT_TL(g) != nullptr && rank == 0 && lane == 0 && pti < 16) ? LDIT_TL(g) + (static_cast<size_t>(cluster_id) * 16 + pti) * 16 : nullptr;
       long long wempty = 0;
-      for (int kb = 0; kb < nkb; kb += kstep) {
+      for (int kb = kb0; kb < kb1; kb += kstep) {
         const long long w0 = ptl ? clock64() : 0;
         mbar_wait(&empty_bar[stage], phase ^ 1);
         if (kstep == 2) mbar_wait(&empty_bar[stage + 1], phase ^ 1);
-        if (ptl) { wempty += clock64() - w0; if (kb + kstep >= nkb) ptl[9] = wempty; }
+        if (ptl) { wempty += clock64() - w0; if (kb + kstep >= kb1) ptl[9] = wempty; }
         if (elect_one_sync()) {
           for (int j = 0; j < kstep; ++j) {
             const int st = stage + j;
@@ -310,13 +320,30 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
                 for (int q = 0; q < 4; ++q)
                   tma_load_5d_cg2(sA + st * Cfg::A_BYTES + q * (Cfg::A_BYTES / 4), &tmA, leader_full, 0, cvx, ((kb + j) & 3) * 4 + q, cvy,
                                   cvb * 3 + ((kb + j) >> 2));
+              } else if constexpr (EPI == EPI_WGRAD) {
+                // MN-major operands: a stage holds [64 k-rows x 64 columns] atoms of 8 KB, one per 64 columns of the tile
+                tma_load_2d_cg2(sA + st * Cfg::A_BYTES, &tmA, leader_full, m0, (kb + j) * kBK);
+                tma_load_2d_cg2(sA + st * Cfg::A_BYTES + 8192, &tmA, leader_full, m0 + 64, (kb + j) * kBK);
               } else
                 tma_load_2d_cg2(sA + st * Cfg::A_BYTES, &tmA, leader_full, (kb + j) * kBK, m0);
-              tma_load_2d_cg2(sB + st * Cfg::B_BYTES, &tmB, leader_full, (kb + j) * kBK, n0);
+              if constexpr (EPI == EPI_WGRAD) {
+#pragma unroll
+                for (int q = 0; q < Cfg::B_ROWS / 64; ++q)
+                  tma_load_2d_cg2(sB + st * Cfg::B_BYTES + q * 8192, &tmB, leader_full, n0 + 64 * q, (kb + j) * kBK);
+              } else
+                tma_load_2d_cg2(sB + st * Cfg::B_BYTES, &tmB, leader_full, (kb + j) * kBK, n0);
             } else {
               mbar_arrive_expect_tx(&full_bar[st], Cfg::STAGE_BYTES);
-              tma_load_2d(sA + st * Cfg::A_BYTES, &tmA, &full_bar[st], (kb + j) * kBK, m0);
-              tma_load_2d(sB + st * Cfg::B_BYTES, &tmB, &full_bar[st], (kb + j) * kBK, n0);
+              if constexpr (EPI == EPI_WGRAD) {
+                tma_load_2d(sA + st * Cfg::A_BYTES, &tmA, &full_bar[st], m0, (kb + j) * kBK);
+                tma_load_2d(sA + st * Cfg::A_BYTES + 8192, &tmA, &full_bar[st], m0 + 64, (kb + j) * kBK);
+#pragma unroll
+                for (int q = 0; q < Cfg::B_ROWS / 64; ++q)
+                  tma_load_2d(sB + st * Cfg::B_BYTES + q * 8192, &tmB, &full_bar[st], n0 + 64 * q, (kb + j) * kBK);
+              } else {
+                tma_load_2d(sA + st * Cfg::A_BYTES, &tmA, &full_bar[st], (kb + j) * kBK, m0);
+                tma_load_2d(sB + st * Cfg::B_BYTES, &tmB, &full_bar[st], (kb + j) * kBK, n0);
+              }
             }
           }
         }
@@ -330,18 +357,22 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
     }
   } else if (warp == kWarpMma) {
     if (rank == 0) {
-      constexpr uint32_t idesc_bf16 = umma_idesc_bf16(Cfg::TILE_M, BN, 0, 0);
+      constexpr uint32_t idesc_bf16 = umma_idesc_bf16(Cfg::TILE_M, BN, EPI == EPI_WGRAD ? 1 : 0, EPI == EPI_WGRAD ? 1 : 0);
       // EPI_PATCH_TMA with fp16 pixels: both operand format fields ([7,10) A, [10,13) B) = 0 (f16); the weights are then an
       // fp16 copy (mixing an f16 A with a bf16 B traps with "illegal instruction" on sm_100a, measured)
       const uint32_t idesc = (EPI == EPI_PATCH_TMA && g.a_f16) ? (idesc_bf16 & ~((7u << 7) | (7u << 10))) : idesc_bf16;
-      const uint64_t adesc0 = (EPI == EPI_PATCH_TMA) ? umma_desc_kmajor_sw32(smem_u32(sA)) : umma_desc_kmajor_sw128(smem_u32(sA));
-      const uint64_t bdesc0 = umma_desc_kmajor_sw128(smem_u32(sB));
+      const uint64_t adesc0 = (EPI == EPI_PATCH_TMA) ? umma_desc_kmajor_sw32(smem_u32(sA))
+                            : (EPI == EPI_WGRAD)   ? umma_desc_mnmajor_sw128_atoms(smem_u32(sA), 8192)
+                                                   : umma_desc_kmajor_sw128(smem_u32(sA));
+      const uint64_t bdesc0 = (EPI == EPI_WGRAD) ? umma_desc_mnmajor_sw128_atoms(smem_u32(sB), 8192) : umma_desc_kmajor_sw128(smem_u32(sB));
       int stage = 0;
       uint32_t phase = 0;
       int acc = 0;
       uint32_t acc_phase = 0;
       int ti = 0;
-      for (int tile = cluster_id; tile < num_tiles; tile += num_clusters, ++ti) {
+      for (int item = cluster_id; item < num_tiles; item += num_clusters, ++ti) {
+        const int kb0 = (EPI == EPI_WGRAD) ? (item / mn_tiles) * g.kb_per_split : 0;
+        const int kb1 = (EPI == EPI_WGRAD) ? min(nkb, kb0 + g.kb_per_split) : nkb;
         long long* tl = (LDIT_TL(g) != nullptr && lane == 0 && ti < 16) ? LDIT_TL(g) + (static_cast<size_t>(cluster_id) * 16 + ti) * 16 : nullptr;
         if (tl) tl[0] = clock64();
         mbar_wait(&tempty_bar[acc], acc_phase ^ 1);
@@ -349,7 +380,7 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
         if (tl) tl[1] = clock64();
         const uint32_t d_tmem = tmem_base + acc * kAccStride;
         long long wfull = 0;
-        for (int kb = 0; kb < nkb; kb += kstep) {
+        for (int kb = kb0; kb < kb1; kb += kstep) {
           const long long w0 = tl ? clock64() : 0;
           mbar_wait(&full_bar[stage], phase);
           if (kstep == 2) mbar_wait(&full_bar[stage + 1], phase);
@@ -362,17 +393,19 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
               const uint64_t bdesc = bdesc0 + static_cast<uint32_t>(st * (Cfg::B_BYTES >> 4));
               // A advances by 32 B inside the 128-byte swizzle atom per UMMA_K step; the TMA-gathered patch operand instead
               // holds one 32-byte-swizzled [128 x 16] sub-tile per step (A_BYTES / 4 apart)
-              constexpr uint32_t a_step = (EPI == EPI_PATCH_TMA) ? (Cfg::A_BYTES / 4) >> 4 : 2;
+              // MN-major operands (EPI_WGRAD) advance by 16 k-rows of 128 B
+              constexpr uint32_t a_step = (EPI == EPI_PATCH_TMA) ? (Cfg::A_BYTES / 4) >> 4 : (EPI == EPI_WGRAD) ? 128 : 2;
+              constexpr uint32_t b_step = (EPI == EPI_WGRAD) ? 128 : 2;
 #pragma unroll
               for (int k = 0; k < kBK / kUmmaK; ++k) {
-                if constexpr (CTAS == 2) umma_bf16_ss_cg2(d_tmem, adesc + a_step * k, bdesc + 2 * k, idesc, (kb | j | k) != 0);
-                else umma_bf16_ss(d_tmem, adesc + a_step * k, bdesc + 2 * k, idesc, (kb | j | k) != 0);
+                if constexpr (CTAS == 2) umma_bf16_ss_cg2(d_tmem, adesc + a_step * k, bdesc + b_step * k, idesc, ((kb - kb0) | j | k) != 0);
+                else umma_bf16_ss(d_tmem, adesc + a_step * k, bdesc + b_step * k, idesc, ((kb - kb0) | j | k) != 0);
               }
               // smem slot reusable (in both CTAs) once these MMAs have read it
               if constexpr (CTAS == 2) tcgen05_commit_cg2(&empty_bar[st], 3); else tcgen05_commit(&empty_bar[st]);
             }
             // last k-block: the accumulator is complete (both CTAs' epilogues)
-            if (kb + kstep >= nkb) {
+            if (kb + kstep >= kb1) {
               if constexpr (CTAS == 2) tcgen05_commit_cg2(&tfull_bar[acc], 3); else tcgen05_commit(&tfull_bar[acc]);
             }
           }
@@ -420,7 +453,8 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
     };
 
     int ti = 0;
-    for (int tile = cluster_id; tile < num_tiles; tile += num_clusters, ++ti) {
+    for (int item = cluster_id; item < num_tiles; item += num_clusters, ++ti) {
+      const int tile = (EPI == EPI_WGRAD) ? item % mn_tiles : item;
       const int row0 = (g.m_reverse ? g.num_m_blocks - 1 - tile / g.num_n_blocks : tile / g.num_n_blocks) * Cfg::TILE_M + row_in_tile;
       const int col0 = (tile % g.num_n_blocks) * BN + cgrp * Cfg::CG_COLS;
       int cvx = 0, cvy = 0, cvb = 0;   // EPI_CONV_BIAS: first pixel of this warp's 32 rows (32 / cv_tw image rows of cv_tw pixels)
@@ -489,7 +523,7 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
       // tail; its MMAs have completed (tfull) and no further load will be issued, i.e. the operand ring is free,
       // and every chunk can have a staging buffer of its own there (no per-chunk wait for the previous TMA
       // store to have read the single regular buffer).  Measured: no change -- the tail is not bound by that wait.
-      const bool last_tile = LDIT_TAIL_RING && (tile + num_clusters >= num_tiles);
+      const bool last_tile = LDIT_TAIL_RING && (item + num_clusters >= num_tiles);
       uint8_t* tail_stage = smem + static_cast<size_t>(warp) * kChunks * Cfg::CHUNK_BYTES;
       if (tl) tl[5] = clock64();
       const uint32_t taddr = tmem_base + acc * kAccStride + cgrp * Cfg::CG_COLS + (static_cast<uint32_t>(quarter * 32) << 16);
@@ -578,7 +612,7 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
           for (int j = 0; j < 4; ++j) {
             o[j] = make_float4(__uint_as_float(rc[4 * j + 0]), __uint_as_float(rc[4 * j + 1]),
                                __uint_as_float(rc[4 * j + 2]), __uint_as_float(rc[4 * j + 3]));
-            if constexpr (EPI == EPI_SCALE_RESID) {
+            if constexpr (epi_is_resid(EPI)) {
               o[j].x = s4[j].x * (o[j].x + b4[j].x);
               o[j].y = s4[j].y * (o[j].y + b4[j].y);
               o[j].z = s4[j].z * (o[j].z + b4[j].z);
@@ -593,7 +627,7 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
               o[j].x += b4[j].x; o[j].y += b4[j].y; o[j].z += b4[j].z; o[j].w += b4[j].w;
             }
           }
-          if constexpr (EPI == EPI_SCALE_RESID || EPI == EPI_CONV_BIAS_F32) {
+          if constexpr (epi_is_resid(EPI) || EPI == EPI_CONV_BIAS_F32) {
             if (lane == 0 && !last_tile) tma_store_wait_read<LDIT_EPI_BUFS - 1>();
           }
           __syncwarp();  // EPI_PATCH: every lane has finished reading this buffer (chunk gc-2) long ago; keeps the warp converged
@@ -623,7 +657,7 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
           fence_proxy_async_smem();  // generic-proxy smem writes -> visible to the TMA engine
           __syncwarp();
           if (lane == 0 && col_ok && !LDIT_DBG(g, 2)) {
-            if constexpr (EPI == EPI_SCALE_RESID) { if (LDIT_DBG(g, 32)) tma_store_2d(&tmC, buf, col, row0); else tma_reduce_add_2d(&tmC, buf, col, row0); }
+            if constexpr (epi_is_resid(EPI)) { if (LDIT_DBG(g, 32)) tma_store_2d(&tmC, buf, col, row0); else tma_reduce_add_2d(&tmC, buf, col, row0); }
             else if constexpr (epi_is_conv(EPI)) tma_store_4d(&tmC, buf, col, cvx, cvy, cvb);   // pixels past the image edge are clipped
             else tma_store_2d(&tmC, buf, col, row0);
             tma_store_commit();

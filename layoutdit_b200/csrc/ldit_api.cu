@@ -578,6 +578,34 @@ int patch_embed_tma(const void* pixels, bool f16, const void* w, const void* pos
 
 }  // namespace
 
+// dW f32 [Nw, Kw] += dY^T A with dY bf16 [T, Nw] and A bf16 [T, Kw], both row-major as the forward / backward kernels
+// wrote them: the GEMM's operands are MN-major in shared memory (no transposed copies), the token dimension T is the
+// contraction and is cut into pieces that reduce-add into the same output tile (a [768, 768] gradient is 18 tiles for
+// 74 CTA pairs otherwise).
+template <int BN>
+int launch_wgrad(const void* dY, const void* A, GemmArgs g, int T, cudaStream_t st) {
+  using Cfg = GemmCfg<BN, EPI_WGRAD, 2>;
+  CUtensorMap tmA, tmB, tmC;
+  int rc = make_tmap_2d(&tmA, dY, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, T, g.M, g.M, 64, 64, CU_TENSOR_MAP_SWIZZLE_128B);
+  if (rc) return rc;
+  rc = make_tmap_2d(&tmB, A, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, T, g.N, g.N, 64, 64, CU_TENSOR_MAP_SWIZZLE_128B);
+  if (rc) return rc;
+  rc = make_tmap_2d(&tmC, g.out, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, g.M, g.N, g.ldo, 32, kEpiCols, CU_TENSOR_MAP_SWIZZLE_64B);
+  if (rc) return rc;
+  g.num_m_blocks = (g.M + Cfg::TILE_M - 1) / Cfg::TILE_M;
+  g.num_n_blocks = (g.N + BN - 1) / BN;
+  const int nkb = (T + kBK - 1) / kBK;
+  const int units = num_sms() / 2;
+  const int mn = g.num_m_blocks * g.num_n_blocks;
+  int want = (2 * units + mn - 1) / mn;                 // about two work items per CTA pair
+  if (want < 1) want = 1;
+  if (want > nkb / 8) want = nkb / 8 > 0 ? nkb / 8 : 1; // at least 8 k-blocks per piece: the pipeline fill is paid per piece
+  g.kb_per_split = (nkb + want - 1) / want;
+  g.ksplit = (nkb + g.kb_per_split - 1) / g.kb_per_split;   // every piece non-empty
+  return launch_gemm_maps<BN, EPI_WGRAD, 2>(tmA, tmB, tmC, g, st);
+}
+
+
 extern "C" {
 
 int ldit_version(void) { return 100; }
@@ -780,6 +808,19 @@ int ldit_gemm_accumulate(const void* A, const void* W, void* acc, int M, int N, 
   g.M = M; g.N = N; g.K = K;
   g.out = acc; g.ldo = N;
   return launch_gemm<EPI_SCALE_RESID>(A, W, g, static_cast<cudaStream_t>(stream));   // unrounded fp32 reduce-add
+}
+
+int ldit_gemm_wgrad(const void* dY, const void* A, void* dW, int T, int Nw, int Kw, void* stream) {
+  if (!dY || !A || !dW) return LDIT_E_NULL;
+  if (T <= 0 || Nw <= 0 || Kw <= 0 || (Nw % 8) || (Kw % 8)) return LDIT_E_SHAPE;
+  if (!aligned16(dY) || !aligned16(A) || !aligned16(dW)) return LDIT_E_ALIGN;
+  GemmArgs g{};
+  g.M = Nw; g.N = Kw; g.K = T;
+  g.out = dW; g.ldo = Kw;
+  // 128-wide tiles unless the output is large enough to fill the machine with 256-wide ones
+  const long tiles256 = static_cast<long>((Nw + 255) / 256) * ((Kw + 255) / 256);
+  if (tiles256 >= num_sms() / 2) return launch_wgrad<256>(dY, A, g, T, static_cast<cudaStream_t>(stream));
+  return launch_wgrad<128>(dY, A, g, T, static_cast<cudaStream_t>(stream));
 }
 
 #ifdef LDIT_EXPERIMENTAL
@@ -1204,8 +1245,8 @@ int ldit_scale_residual_bwd(const void* dy, const void* branch, const void* lam,
   if (!dy || !branch || !dbranch) return LDIT_E_NULL;
   if (rows <= 0 || D <= 0 || (D % 8)) return LDIT_E_SHAPE;
   if (!aligned16(dy) || !aligned16(branch) || !aligned16(lam) || !aligned16(dbranch) || !aligned16(dlam)) return LDIT_E_ALIGN;
-  const int rpb = 16, threads = 128;   // 788 blocks at 12608 rows: enough loads in flight (64 rows per block ran at 1.6 TB/s)
-  scale_residual_bwd_kernel<<<dim3((D / 8 + threads - 1) / threads, (rows + rpb - 1) / rpb), threads, 0, static_cast<cudaStream_t>(stream)>>>(
+  const int rpb = 64, threads = (D / 8 < 128) ? D / 8 : 128;
+  scale_residual_bwd_kernel<<<dim3((D / 8 + threads - 1) / threads, (rows + rpb - 1) / rpb), dim3(threads, 8), 0, static_cast<cudaStream_t>(stream)>>>(
       static_cast<const float*>(dy), static_cast<const __nv_bfloat16*>(branch), static_cast<const float*>(lam),
       static_cast<__nv_bfloat16*>(dbranch), static_cast<float*>(dlam), rows, D, rpb);
   return check_launch();

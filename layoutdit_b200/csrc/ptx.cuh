@@ -363,6 +363,18 @@ __device__ __forceinline__ uint64_t umma_desc_mnmajor_sw128(uint32_t smem_addr) 
   return d;
 }
 
+// MN-major operand spanning several 64-element atoms along MN (wgrad GEMM: both operands are read straight out of
+// row-major [K, MN] matrices): each atom is [k rows x 128 B] with 8-row groups SBO = 1024 B apart, atoms LBO bytes apart.
+__device__ __forceinline__ uint64_t umma_desc_mnmajor_sw128_atoms(uint32_t smem_addr, uint32_t atom_stride_bytes) {
+  uint64_t d = 0;
+  d |= static_cast<uint64_t>((smem_addr & 0x3FFFFu) >> 4);
+  d |= static_cast<uint64_t>(atom_stride_bytes >> 4) << 16;  // LBO: stride between MN atoms
+  d |= static_cast<uint64_t>(1024 >> 4) << 32;               // SBO: stride between 8-row groups along K
+  d |= static_cast<uint64_t>(1) << 46;
+  d |= static_cast<uint64_t>(2) << 61;
+  return d;
+}
+
 // Instruction descriptor, kind::f16: bf16 A/B, fp32 accumulate, dense.
 // [4,6) D fmt (1=f32) [7,10) A fmt (1=bf16) [10,13) B fmt (1=bf16) [15] A major [16] B major
 // (0=K, 1=MN) [17,23) N>>3 [24,29) M>>4

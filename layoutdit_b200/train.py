@@ -63,6 +63,12 @@ class _K:
         N = w.shape[0]
         _lib.check(self.lib.ldit_gemm_accumulate(a.data_ptr(), w.data_ptr(), acc.data_ptr(), M, N, K, _st(self.dev)), "ldit_gemm_accumulate")
 
+    def wgrad(self, dy, a, acc):
+        """acc f32 [Nw, Kw] += dy^T a for dy bf16 [T, Nw], a bf16 [T, Kw] (no transposed copies)."""
+        T, Nw = dy.shape
+        Kw = a.shape[1]
+        _lib.check(self.lib.ldit_gemm_wgrad(dy.data_ptr(), a.data_ptr(), acc.data_ptr(), T, Nw, Kw, _st(self.dev)), "ldit_gemm_wgrad")
+
     def attention(self, qkv, B, N, heads, Gh, Gw):
         D = heads * 64
         ctx = torch.empty(B * N, D, device=self.dev, dtype=_BF)
@@ -182,11 +188,11 @@ class BeitLayerFunction(torch.autograd.Function):
         dlam2 = z(D) if lam2 is not None else None
         g2 = k.scale_residual_bwd(dy, br2, lam2, dlam2)                    # d(branch 2), bf16
         db2 = z(D); k.colsum(g2, db2)
-        dw2 = z(D, I); k.gemm_acc(k.transpose(g2), k.transpose(h), dw2)    # [D, M] x [I, M]^T
+        dw2 = z(D, I); k.wgrad(g2, h, dw2)                                 # [M, D]^T [M, I]
         dh = k.gemm(g2, tr(w2))                                            # [M, D] x (W2^T [I, D])^T
         dpre = k.gelu_bwd(dh, pre)
         db1 = z(I); k.colsum(dpre, db1)
-        dw1 = z(I, D); k.gemm_acc(k.transpose(dpre), k.transpose(a2), dw1)
+        dw1 = z(I, D); k.wgrad(dpre, a2, dw1)
         da2 = k.gemm(dpre, tr(w1))                                         # [M, I] x (W1^T [D, I])^T
         dg2, dbt2 = z(D), z(D)
         dxm = k.layernorm_bwd(xm, g2w, da2, dy, dg2, dbt2, eps)            # dy (residual path) + LayerNorm-2 path
@@ -195,11 +201,11 @@ class BeitLayerFunction(torch.autograd.Function):
         dlam1 = z(D) if lam1 is not None else None
         g1 = k.scale_residual_bwd(dxm, br1, lam1, dlam1)
         dbo = z(D); k.colsum(g1, dbo)
-        dwo = z(D, D); k.gemm_acc(k.transpose(g1), k.transpose(att), dwo)
+        dwo = z(D, D); k.wgrad(g1, att, dwo)
         datt = k.gemm(g1, tr(wo))
         dqkv = k.attention_bwd(qkv, datt, B, N, heads)
         dbqkv = z(3 * D); k.colsum(dqkv, dbqkv)
-        dwqkv = z(3 * D, D); k.gemm_acc(k.transpose(dqkv), k.transpose(a1), dwqkv)
+        dwqkv = z(3 * D, D); k.wgrad(dqkv, a1, dwqkv)
         da1 = k.gemm(dqkv, tr(wqkv))
         dg1, dbt1 = z(D), z(D)
         dx = k.layernorm_bwd(x, g1w, da1, dxm, dg1, dbt1, eps)
@@ -285,7 +291,7 @@ class PatchEmbedFunction(torch.autograd.Function):
         db = torch.zeros(D, device=dev, dtype=torch.float32)
         k.colsum(dtok, db)
         dw = torch.zeros(D, 768, device=dev, dtype=torch.float32)
-        k.gemm_acc(k.transpose(dtok), k.transpose(a), dw)                  # [D, B P] x [768, B P]^T
+        k.wgrad(dtok, a, dw)                                               # [B P, D]^T [B P, 768]
         dsum = torch.zeros(N * D, device=dev, dtype=torch.float32)         # every image adds the same cls / position rows
         _lib.check(k.lib.ldit_batch_sum(dx.data_ptr(), dsum.data_ptr(), B, N * D, st), "ldit_batch_sum")
         dcls = dsum[:D].clone().view(1, 1, D)

@@ -245,3 +245,17 @@ def test_backbone_gradients_match_oracle_autograd(cuda_device, layer_scale, B, G
         assert e < GRAD_TOL, f"{name}: rel-Frobenius {e:.3e}"
     assert seen == 6 * (17 if layer_scale > 0 else 15) + 3 + int(abs_pos)   # every layer tensor, projection w / b, cls (, positions)
     print(f"{seen} parameter gradients, worst rel-Fro {worst:.2e}")
+
+
+@pytest.mark.parametrize("T,Nw,Kw", [(12608, 768, 768), (1576, 3072, 768), (197, 768, 3072), (300, 128, 256), (64, 256, 128), (5000, 2304, 768)])
+def test_wgrad_gemm_without_transposed_copies(lib, T, Nw, Kw):
+    """dW += dY^T A straight from the row-major operands (MN-major shared-memory descriptors, split contraction)."""
+    g = torch.Generator(device="cuda").manual_seed(T + Nw)
+    dy = torch.randn(T, Nw, device="cuda", generator=g).to(torch.bfloat16)
+    a = torch.randn(T, Kw, device="cuda", generator=g).to(torch.bfloat16)
+    dw = torch.full((Nw, Kw), 0.5, device="cuda")
+    _lib.check(lib.ldit_gemm_wgrad(dy.data_ptr(), a.data_ptr(), dw.data_ptr(), T, Nw, Kw, _st()), "wgrad")
+    ref = 0.5 + dy.double().t() @ a.double()
+    assert torch.isfinite(dw).all()
+    assert _rel(dw.double(), ref) < 1e-5
+    torch.testing.assert_close(dw.double(), ref, rtol=1e-4, atol=2e-3 * (T ** 0.5) / 10)
