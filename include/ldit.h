@@ -201,6 +201,9 @@ int ldit_scale_residual_bwd(const void* dy, const void* branch, const void* lam,
  * dx_in may be NULL and may alias dx_out.  Row statistics are recomputed from x. */
 int ldit_layernorm_bwd(const void* x, const void* gamma, const void* dy, const void* dx_in, void* dx_out, void* dgamma, void* dbeta,
                        int rows, int D, float eps, void* stream);
+/* Input gradient of nn.Linear: dA bf16 [M, Kin] = dY bf16 [M, Nout] x W bf16 [Nout, Kin], W exactly as the forward holds it
+ * (MN-major B operand: no transposed weight copy).  Nout, Kin multiples of 8. */
+int ldit_gemm_dgrad(const void* dY, const void* W, void* dA, int M, int Nout, int Kin, void* stream);
 /* Weight gradient of nn.Linear: dW f32 [Nw, Kw] += dY^T A with dY bf16 [T, Nw], A bf16 [T, Kw] row-major (T = tokens).
  * tcgen05 GEMM with MN-major operands (no transposed copies) and a split contraction (fp32 reduce-add; the summation
  * order of the pieces is not fixed).  Nw, Kw multiples of 8. */

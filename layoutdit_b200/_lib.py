@@ -30,6 +30,7 @@ SIGNATURES = {
     "ldit_scale_residual_bwd": (_i, [_vp, _vp, _vp, _vp, _vp, _i, _i, _vp]),
     "ldit_layernorm_bwd": (_i, [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _i, _i, _f, _vp]),
     "ldit_gemm_wgrad": (_i, [_vp, _vp, _vp, _i, _i, _i, _vp]),
+    "ldit_gemm_dgrad": (_i, [_vp, _vp, _vp, _i, _i, _i, _vp]),
     "ldit_attention_bwd": (_i, [_vp, _vp, _vp, _i, _i, _i, _vp]),
     "ldit_resample_taps_bwd": (_i, [_vp, _vp, _i, _i, _i, _i, _f, _vp]),
     "ldit_batch_sum": (_i, [_vp, _vp, _i, _i, _vp]),

@@ -35,9 +35,12 @@
 namespace ldit {
 
 enum : int { EPI_BIAS = 0, EPI_BIAS_GELU = 1, EPI_SCALE_RESID = 2, EPI_PATCH = 3, EPI_CONV_BIAS = 4, EPI_CONV_BIAS_F32 = 5, EPI_BIAS_SCALE = 6, EPI_PATCH_TMA = 7,
-              EPI_WGRAD = 8 };   // EPI_WGRAD: C f32 [M, N] += A^T B with A [K, M] and B [K, N] row-major (both operands MN-major in smem);
+              EPI_WGRAD = 8, EPI_DGRAD = 9 };   // EPI_WGRAD: C f32 [M, N] += A^T B with A [K, M] and B [K, N] row-major (both operands MN-major in smem);
                                  // the epilogue is EPI_SCALE_RESID's fp32 reduce-add without bias / scale / rounding
+// EPI_DGRAD: C bf16 [M, N] = A B with A [M, K] K-major as usual and B [K, N] row-major (MN-major in smem): dA = dY W for
+// nn.Linear's W [N_out, K_in] as it is stored -- no transposed weight copy; the epilogue is EPI_BIAS's (bias = nullptr)
 __host__ __device__ constexpr bool epi_is_resid(int epi) { return epi == EPI_SCALE_RESID || epi == EPI_WGRAD; }
+__host__ __device__ constexpr bool epi_b_mn(int epi) { return epi == EPI_WGRAD || epi == EPI_DGRAD; }
 // EPI_PATCH_TMA: the patch embedding with its A operand gathered by TMA straight out of the NCHW page batch (16-bit pixels):
 // no im2col matrix, CLS rows written by the same kernel
 __host__ __device__ constexpr bool epi_is_patch(int epi) { return epi == EPI_PATCH || epi == EPI_PATCH_TMA; }
@@ -326,7 +329,7 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
                 tma_load_2d_cg2(sA + st * Cfg::A_BYTES + 8192, &tmA, leader_full, m0 + 64, (kb + j) * kBK);
               } else
                 tma_load_2d_cg2(sA + st * Cfg::A_BYTES, &tmA, leader_full, (kb + j) * kBK, m0);
-              if constexpr (EPI == EPI_WGRAD) {
+              if constexpr (epi_b_mn(EPI)) {
 #pragma unroll
                 for (int q = 0; q < Cfg::B_ROWS / 64; ++q)
                   tma_load_2d_cg2(sB + st * Cfg::B_BYTES + q * 8192, &tmB, leader_full, n0 + 64 * q, (kb + j) * kBK);
@@ -342,7 +345,12 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
                   tma_load_2d(sB + st * Cfg::B_BYTES + q * 8192, &tmB, &full_bar[st], n0 + 64 * q, (kb + j) * kBK);
               } else {
                 tma_load_2d(sA + st * Cfg::A_BYTES, &tmA, &full_bar[st], (kb + j) * kBK, m0);
-                tma_load_2d(sB + st * Cfg::B_BYTES, &tmB, &full_bar[st], (kb + j) * kBK, n0);
+                if constexpr (epi_b_mn(EPI)) {
+#pragma unroll
+                  for (int q = 0; q < Cfg::B_ROWS / 64; ++q)
+                    tma_load_2d(sB + st * Cfg::B_BYTES + q * 8192, &tmB, &full_bar[st], n0 + 64 * q, (kb + j) * kBK);
+                } else
+                  tma_load_2d(sB + st * Cfg::B_BYTES, &tmB, &full_bar[st], (kb + j) * kBK, n0);
               }
             }
           }
@@ -357,14 +365,14 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
     }
   } else if (warp == kWarpMma) {
     if (rank == 0) {
-      constexpr uint32_t idesc_bf16 = umma_idesc_bf16(Cfg::TILE_M, BN, EPI == EPI_WGRAD ? 1 : 0, EPI == EPI_WGRAD ? 1 : 0);
+      constexpr uint32_t idesc_bf16 = umma_idesc_bf16(Cfg::TILE_M, BN, EPI == EPI_WGRAD ? 1 : 0, epi_b_mn(EPI) ? 1 : 0);
       // EPI_PATCH_TMA with fp16 pixels: both operand format fields ([7,10) A, [10,13) B) = 0 (f16); the weights are then an
       // fp16 copy (mixing an f16 A with a bf16 B traps with "illegal instruction" on sm_100a, measured)
       const uint32_t idesc = (EPI == EPI_PATCH_TMA && g.a_f16) ? (idesc_bf16 & ~((7u << 7) | (7u << 10))) : idesc_bf16;
       const uint64_t adesc0 = (EPI == EPI_PATCH_TMA) ? umma_desc_kmajor_sw32(smem_u32(sA))
                             : (EPI == EPI_WGRAD)   ? umma_desc_mnmajor_sw128_atoms(smem_u32(sA), 8192)
                                                    : umma_desc_kmajor_sw128(smem_u32(sA));
-      const uint64_t bdesc0 = (EPI == EPI_WGRAD) ? umma_desc_mnmajor_sw128_atoms(smem_u32(sB), 8192) : umma_desc_kmajor_sw128(smem_u32(sB));
+      const uint64_t bdesc0 = epi_b_mn(EPI) ? umma_desc_mnmajor_sw128_atoms(smem_u32(sB), 8192) : umma_desc_kmajor_sw128(smem_u32(sB));
       int stage = 0;
       uint32_t phase = 0;
       int acc = 0;
@@ -395,7 +403,7 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
               // holds one 32-byte-swizzled [128 x 16] sub-tile per step (A_BYTES / 4 apart)
               // MN-major operands (EPI_WGRAD) advance by 16 k-rows of 128 B
               constexpr uint32_t a_step = (EPI == EPI_PATCH_TMA) ? (Cfg::A_BYTES / 4) >> 4 : (EPI == EPI_WGRAD) ? 128 : 2;
-              constexpr uint32_t b_step = (EPI == EPI_WGRAD) ? 128 : 2;
+              constexpr uint32_t b_step = epi_b_mn(EPI) ? 128 : 2;
 #pragma unroll
               for (int k = 0; k < kBK / kUmmaK; ++k) {
                 if constexpr (CTAS == 2) umma_bf16_ss_cg2(d_tmem, adesc + a_step * k, bdesc + b_step * k, idesc, ((kb - kb0) | j | k) != 0);

@@ -606,6 +606,21 @@ int launch_wgrad(const void* dY, const void* A, GemmArgs g, int T, cudaStream_t 
 }
 
 
+// dA bf16 [M, Kin] = dY [M, Nout] x W [Nout, Kin], W read as nn.Linear stores it (MN-major B operand)
+template <int BN>
+int launch_dgrad(const void* dY, const void* W, GemmArgs g, cudaStream_t st) {
+  using Cfg = GemmCfg<BN, EPI_DGRAD, 2>;
+  CUtensorMap tmA, tmB, tmC;
+  int rc = make_tmap_bf16_2d(&tmA, dY, g.M, g.K, kBM);
+  if (rc) return rc;
+  rc = make_tmap_2d(&tmB, W, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, g.K, g.N, g.N, 64, 64, CU_TENSOR_MAP_SWIZZLE_128B);
+  if (rc) return rc;
+  rc = make_tmap_2d(&tmC, g.out, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, g.M, g.N, g.ldo, 32, kEpiCols, CU_TENSOR_MAP_SWIZZLE_32B);
+  if (rc) return rc;
+  g.num_m_blocks = (g.M + Cfg::TILE_M - 1) / Cfg::TILE_M;
+  return launch_gemm_maps<BN, EPI_DGRAD, 2>(tmA, tmB, tmC, g, st);
+}
+
 extern "C" {
 
 int ldit_version(void) { return 100; }
@@ -808,6 +823,21 @@ int ldit_gemm_accumulate(const void* A, const void* W, void* acc, int M, int N, 
   g.M = M; g.N = N; g.K = K;
   g.out = acc; g.ldo = N;
   return launch_gemm<EPI_SCALE_RESID>(A, W, g, static_cast<cudaStream_t>(stream));   // unrounded fp32 reduce-add
+}
+
+int ldit_gemm_dgrad(const void* dY, const void* W, void* dA, int M, int Nout, int Kin, void* stream) {
+  if (!dY || !W || !dA) return LDIT_E_NULL;
+  if (M <= 0 || Nout <= 0 || Kin <= 0 || (Nout % 8) || (Kin % 8)) return LDIT_E_SHAPE;
+  if (!aligned16(dY) || !aligned16(W) || !aligned16(dA)) return LDIT_E_ALIGN;
+  GemmArgs g{};
+  g.M = M; g.N = Kin; g.K = Nout;
+  g.out = dA; g.ldo = Kin;
+  // tile widths whose per-CTA half is a whole number of 64-column atoms: 128 or 256, fewest schedule rounds x width
+  const int units = num_sms() / 2, mb = (M + 255) / 256;
+  const long c128 = ((static_cast<long>(mb) * ((Kin + 127) / 128) + units - 1) / units) * (128 + 16);
+  const long c256 = ((static_cast<long>(mb) * ((Kin + 255) / 256) + units - 1) / units) * (256 + 16);
+  if (c256 <= c128) return launch_dgrad<256>(dY, W, g, static_cast<cudaStream_t>(stream));
+  return launch_dgrad<128>(dY, W, g, static_cast<cudaStream_t>(stream));
 }
 
 int ldit_gemm_wgrad(const void* dY, const void* A, void* dW, int T, int Nw, int Kw, void* stream) {

@@ -63,6 +63,14 @@ class _K:
         N = w.shape[0]
         _lib.check(self.lib.ldit_gemm_accumulate(a.data_ptr(), w.data_ptr(), acc.data_ptr(), M, N, K, _st(self.dev)), "ldit_gemm_accumulate")
 
+    def dgrad(self, dy, w):
+        """bf16 [M, Kin] = dy [M, Nout] x w [Nout, Kin] (w as the forward holds it: no transposed copy)."""
+        M, Nout = dy.shape
+        Kin = w.shape[1]
+        out = torch.empty(M, Kin, device=self.dev, dtype=_BF)
+        _lib.check(self.lib.ldit_gemm_dgrad(dy.data_ptr(), w.data_ptr(), out.data_ptr(), M, Nout, Kin, _st(self.dev)), "ldit_gemm_dgrad")
+        return out
+
     def wgrad(self, dy, a, acc):
         """acc f32 [Nw, Kw] += dy^T a for dy bf16 [T, Nw], a bf16 [T, Kw] (no transposed copies)."""
         T, Nw = dy.shape
@@ -182,18 +190,17 @@ class BeitLayerFunction(torch.autograd.Function):
         I = w1.shape[0]
         dy = dy.detach().to(torch.float32).contiguous()
         z = lambda *s: torch.zeros(*s, device=dev, dtype=torch.float32)
-        tr = lambda w: w.t().contiguous()                                  # weight transposes: data movement
 
         # ---- MLP half: y = xm + lam2 (.) (h W2^T + b2)
         dlam2 = z(D) if lam2 is not None else None
         g2 = k.scale_residual_bwd(dy, br2, lam2, dlam2)                    # d(branch 2), bf16
         db2 = z(D); k.colsum(g2, db2)
         dw2 = z(D, I); k.wgrad(g2, h, dw2)                                 # [M, D]^T [M, I]
-        dh = k.gemm(g2, tr(w2))                                            # [M, D] x (W2^T [I, D])^T
+        dh = k.dgrad(g2, w2)                                               # [M, D] x W2 [D, I]
         dpre = k.gelu_bwd(dh, pre)
         db1 = z(I); k.colsum(dpre, db1)
         dw1 = z(I, D); k.wgrad(dpre, a2, dw1)
-        da2 = k.gemm(dpre, tr(w1))                                         # [M, I] x (W1^T [D, I])^T
+        da2 = k.dgrad(dpre, w1)                                            # [M, I] x W1 [I, D]
         dg2, dbt2 = z(D), z(D)
         dxm = k.layernorm_bwd(xm, g2w, da2, dy, dg2, dbt2, eps)            # dy (residual path) + LayerNorm-2 path
 
@@ -202,11 +209,11 @@ class BeitLayerFunction(torch.autograd.Function):
         g1 = k.scale_residual_bwd(dxm, br1, lam1, dlam1)
         dbo = z(D); k.colsum(g1, dbo)
         dwo = z(D, D); k.wgrad(g1, att, dwo)
-        datt = k.gemm(g1, tr(wo))
+        datt = k.dgrad(g1, wo)
         dqkv = k.attention_bwd(qkv, datt, B, N, heads)
         dbqkv = z(3 * D); k.colsum(dqkv, dbqkv)
         dwqkv = z(3 * D, D); k.wgrad(dqkv, a1, dwqkv)
-        da1 = k.gemm(dqkv, tr(wqkv))
+        da1 = k.dgrad(dqkv, wqkv)
         dg1, dbt1 = z(D), z(D)
         dx = k.layernorm_bwd(x, g1w, da1, dxm, dg1, dbt1, eps)
 

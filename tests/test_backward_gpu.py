@@ -259,3 +259,16 @@ def test_wgrad_gemm_without_transposed_copies(lib, T, Nw, Kw):
     assert torch.isfinite(dw).all()
     assert _rel(dw.double(), ref) < 1e-5
     torch.testing.assert_close(dw.double(), ref, rtol=1e-4, atol=2e-3 * (T ** 0.5) / 10)
+
+
+@pytest.mark.parametrize("M,Nout,Kin", [(12608, 768, 3072), (12608, 3072, 768), (1576, 2304, 768), (333, 128, 256), (197, 768, 768), (64, 200, 136)])
+def test_dgrad_gemm_reads_the_weight_as_stored(lib, M, Nout, Kin):
+    """dA = dY W with W [N_out, K_in] exactly as nn.Linear holds it (MN-major B operand, no transposed copy)."""
+    g = torch.Generator(device="cuda").manual_seed(M + Nout)
+    dy = torch.randn(M, Nout, device="cuda", generator=g).to(torch.bfloat16)
+    w = (torch.randn(Nout, Kin, device="cuda", generator=g) * 0.05).to(torch.bfloat16)
+    da = torch.full((M, Kin), float("nan"), device="cuda", dtype=torch.bfloat16)
+    _lib.check(lib.ldit_gemm_dgrad(dy.data_ptr(), w.data_ptr(), da.data_ptr(), M, Nout, Kin, _st()), "dgrad")
+    ref = dy.float() @ w.float()
+    assert torch.isfinite(da.float()).all()
+    assert _rel(da.float(), ref) < 4e-3
