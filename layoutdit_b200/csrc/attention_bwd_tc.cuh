@@ -286,4 +286,240 @@ attention_bwd_tc_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_
   if (warp == 1) tmem_dealloc(tmem_base, kAbtTmemCols);
 }
 
+// ---------------------------------------------------------------------------------------------------------------------
+// Any sequence length: the flash-style variant.  One CTA per (image, head, 128-key tile) keeps dV / dK of its keys in
+// TMEM and walks the query tiles (Q / dO double-buffered through TMA); P is recomputed from the forward's row
+// log-sum-exp (`lse`, written by ldit_attention_lse), delta = rowsum(dO (.) O) comes from attention_delta_kernel, and
+// the dQ contribution of every (query tile, key tile) block leaves through fp32 vector reductions into `dq_acc`
+// (cast to bf16 by dq_cast_kernel afterwards).  Same 128 x 128 block body as attention_bwd_tc_kernel above.
+//   TMEM columns  [0,128) S   [128,256) dP   [256,320) dV   [320,384) dK   [384,448) dQ block
+struct AttnBwdFlashArgs {
+  const float* lse;       // [B, heads, N], log2 units
+  const float* delta;     // [B, heads, N]
+  float* dq_acc;          // [B*N, D] f32, zeroed by the caller of the kernel
+  __nv_bfloat16* dqkv;
+  int B, N, heads, D, nqt;
+  float scale_log2e, scale;
+};
+constexpr int kAbfSmemTiles = 12 * kAbtTile;   // K, V, Q[2], dO[2], P^T (2 atoms), dS^T (2), dS (2)
+
+__device__ __forceinline__ void red_add_v4(float* addr, float a, float b, float c, float d) {
+  asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(addr), "f"(a), "f"(b), "f"(c), "f"(d) : "memory");
+}
+
+// delta[b, h, q] = sum_d dO[b, q, h, d] * O[b, q, h, d]   (one thread per (b, q, h); rows of 128 B)
+__global__ void __launch_bounds__(256)
+attention_delta_kernel(const __nv_bfloat16* __restrict__ dctx, const __nv_bfloat16* __restrict__ ctx, float* __restrict__ delta,
+                       int B, int N, int heads) {
+  const size_t i = static_cast<size_t>(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (i >= static_cast<size_t>(B) * N * heads) return;
+  const int h = static_cast<int>(i % heads);
+  const size_t bq = i / heads;
+  const int q = static_cast<int>(bq % N), b = static_cast<int>(bq / N);
+  const uint4* a = reinterpret_cast<const uint4*>(dctx + i * 64);
+  const uint4* o = reinterpret_cast<const uint4*>(ctx + i * 64);
+  float acc = 0.f;
+#pragma unroll
+  for (int c = 0; c < 8; ++c) {
+    const uint4 ua = __ldg(a + c), uo = __ldg(o + c);
+    const uint32_t wa[4] = {ua.x, ua.y, ua.z, ua.w}, wo[4] = {uo.x, uo.y, uo.z, uo.w};
+#pragma unroll
+    for (int e = 0; e < 4; ++e) {
+      acc = fmaf(__uint_as_float(wa[e] << 16), __uint_as_float(wo[e] << 16), acc);
+      acc = fmaf(__uint_as_float(wa[e] & 0xffff0000u), __uint_as_float(wo[e] & 0xffff0000u), acc);
+    }
+  }
+  delta[(static_cast<size_t>(b) * heads + h) * N + q] = acc;
+}
+
+// dqkv[:, 0:D] (row pitch 3D) bf16 = dq_acc f32 [rows, D]
+__global__ void __launch_bounds__(256)
+dq_cast_kernel(const float* __restrict__ dq_acc, __nv_bfloat16* __restrict__ dqkv, size_t rows, int D) {
+  const size_t i = static_cast<size_t>(blockIdx.x) * blockDim.x + threadIdx.x;   // 8 elements each
+  const int d8 = D / 8;
+  if (i >= rows * d8) return;
+  const size_t r = i / d8;
+  const int c = static_cast<int>(i % d8) * 8;
+  const float4 v0 = __ldg(reinterpret_cast<const float4*>(dq_acc + r * D + c)), v1 = __ldg(reinterpret_cast<const float4*>(dq_acc + r * D + c) + 1);
+  uint4 o;
+  o.x = pack_bf16x2(v0.x, v0.y); o.y = pack_bf16x2(v0.z, v0.w); o.z = pack_bf16x2(v1.x, v1.y); o.w = pack_bf16x2(v1.z, v1.w);
+  *reinterpret_cast<uint4*>(dqkv + r * 3 * D + c) = o;
+}
+
+__global__ void __launch_bounds__(kAbtThreads, 1)
+attention_bwd_flash_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_constant__ CUtensorMap tmDO, const AttnBwdFlashArgs a) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint8_t* sK = smem;
+  uint8_t* sV = smem + kAbtTile;
+  uint8_t* sQ = smem + 2 * kAbtTile;        // [slot]
+  uint8_t* sDO = smem + 4 * kAbtTile;       // [slot]
+  uint8_t* sPT = smem + 6 * kAbtTile;
+  uint8_t* sDST = smem + 8 * kAbtTile;
+  uint8_t* sDS = smem + 10 * kAbtTile;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + kAbfSmemTiles);
+  uint64_t* bar_kv = bars;
+  uint64_t* bar_q = bars + 1;               // [slot]
+  uint64_t* bar_mma = bars + 3;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 4);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int quarter = warp & 3, half = warp >> 2;
+  const int row = quarter * 32 + lane;
+  const int kh = blockIdx.x;
+  const int b = blockIdx.y / a.heads, h = blockIdx.y % a.heads;
+
+  if (threadIdx.x == 0) {
+    mbar_init(bar_kv, 1);
+    mbar_init(&bar_q[0], 1);
+    mbar_init(&bar_q[1], 1);
+    mbar_init(bar_mma, 1);
+    fence_barrier_init();
+    fence_proxy_async_smem();
+    tma_prefetch_desc(&tmQKV);
+    tma_prefetch_desc(&tmDO);
+  }
+  if (warp == 1) {
+    tmem_alloc(tmem_slot, kAbtTmemCols);
+    tmem_relinquish();
+  }
+  tcgen05_fence_before();
+  __syncthreads();
+  tcgen05_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+  const uint32_t lane_addr = tmem_base + (static_cast<uint32_t>(quarter * 32) << 16);
+
+  auto load_q = [&](int t, int slot) {
+    mbar_arrive_expect_tx(&bar_q[slot], 2u * kAbtTile);
+    tma_load_3d(sQ + slot * kAbtTile, &tmQKV, &bar_q[slot], h * 64, t * 128, b);
+    tma_load_3d(sDO + slot * kAbtTile, &tmDO, &bar_q[slot], h * 64, t * 128, b);
+  };
+  if (threadIdx.x == 0) {
+    mbar_arrive_expect_tx(bar_kv, 2u * kAbtTile);
+    tma_load_3d(sK, &tmQKV, bar_kv, a.D + h * 64, kh * 128, b);
+    tma_load_3d(sV, &tmQKV, bar_kv, 2 * a.D + h * 64, kh * 128, b);
+    load_q(0, 0);
+  }
+  mbar_wait(bar_kv, 0);
+
+  constexpr uint32_t idesc_s = umma_idesc_bf16(128, 128, 0, 0);
+  constexpr uint32_t idesc_g = umma_idesc_bf16(128, 64, 0, 1);
+  uint32_t mma_phase = 0;
+  auto wait_mma = [&]() {
+    mbar_wait(bar_mma, mma_phase);
+    mma_phase ^= 1;
+    tcgen05_fence_after();
+  };
+  const float* lse = a.lse + (static_cast<size_t>(b) * a.heads + h) * a.N;
+  const float* dlt = a.delta + (static_cast<size_t>(b) * a.heads + h) * a.N;
+
+  for (int t = 0; t < a.nqt; ++t) {
+    const int slot = t & 1;
+    // every MMA of block t-1 has completed (its dQ was read): the other slot is free for the next query tile
+    if (threadIdx.x == 0 && t + 1 < a.nqt) load_q(t + 1, slot ^ 1);
+    mbar_wait(&bar_q[slot], (t >> 1) & 1);
+    tcgen05_fence_after();
+    if (threadIdx.x == 0) {
+      const uint64_t qd = umma_desc_kmajor_sw128(smem_u32(sQ + slot * kAbtTile));
+      const uint64_t kd = umma_desc_kmajor_sw128(smem_u32(sK));
+      const uint64_t dod = umma_desc_kmajor_sw128(smem_u32(sDO + slot * kAbtTile));
+      const uint64_t vd = umma_desc_kmajor_sw128(smem_u32(sV));
+#pragma unroll
+      for (int k = 0; k < 4; ++k) umma_bf16_ss(tmem_base, qd + 2 * k, kd + 2 * k, idesc_s, k != 0);
+#pragma unroll
+      for (int k = 0; k < 4; ++k) umma_bf16_ss(tmem_base + 128, dod + 2 * k, vd + 2 * k, idesc_s, k != 0);
+      tcgen05_commit(bar_mma);
+    }
+    const int qrow = t * 128 + row;
+    const float ls = qrow < a.N ? __ldg(lse + qrow) : 0.f;     // padding rows: Q = dO = 0, any finite statistic does
+    const float dl = qrow < a.N ? __ldg(dlt + qrow) : 0.f;
+    wait_mma();
+    for (int c = half; c < 8; c += 2) {
+      uint32_t r[16], q[16];
+      tmem_ld_32x32b_x16(lane_addr + c * 16, r);
+      tmem_ld_32x32b_x16(lane_addr + 128 + c * 16, q);
+      tmem_wait_ld16(r);
+      tmem_wait_ld16(q);
+      uint32_t dsp[8];
+#pragma unroll
+      for (int i = 0; i < 16; i += 2) {
+        float p[2], ds[2];
+#pragma unroll
+        for (int e = 0; e < 2; ++e) {
+          const int key = kh * 128 + c * 16 + i + e;
+          p[e] = (key < a.N) ? abt_ex2(__uint_as_float(r[i + e]) * a.scale_log2e - ls) : 0.f;
+          ds[e] = p[e] * (__uint_as_float(q[i + e]) - dl) * a.scale;
+          const int kl = c * 16 + i + e;
+          const uint32_t off = static_cast<uint32_t>(row >> 6) * kAbtTile + abt_sw128(kl, row & 63);
+          *reinterpret_cast<__nv_bfloat16*>(sPT + off) = __float2bfloat16_rn(p[e]);
+          *reinterpret_cast<__nv_bfloat16*>(sDST + off) = __float2bfloat16_rn(ds[e]);
+        }
+        dsp[i >> 1] = pack_bf16x2(ds[0], ds[1]);
+      }
+      uint8_t* line = sDS + (c >> 2) * kAbtTile + row * 128;
+      const int piece = (c & 3) * 2;
+      *reinterpret_cast<uint4*>(line + (((piece) ^ (row & 7)) << 4)) = make_uint4(dsp[0], dsp[1], dsp[2], dsp[3]);
+      *reinterpret_cast<uint4*>(line + (((piece + 1) ^ (row & 7)) << 4)) = make_uint4(dsp[4], dsp[5], dsp[6], dsp[7]);
+    }
+    fence_proxy_async_smem();
+    tcgen05_fence_before();
+    __syncthreads();
+    if (threadIdx.x == 0) {
+      tcgen05_fence_after();
+      const uint64_t ptd = umma_desc_kmajor_sw128(smem_u32(sPT));
+      const uint64_t dstd = umma_desc_kmajor_sw128(smem_u32(sDST));
+      const uint64_t dsd = umma_desc_kmajor_sw128(smem_u32(sDS));
+      const uint64_t dod = umma_desc_mnmajor_sw128(smem_u32(sDO + slot * kAbtTile));
+      const uint64_t qd = umma_desc_mnmajor_sw128(smem_u32(sQ + slot * kAbtTile));
+      const uint64_t kd = umma_desc_mnmajor_sw128(smem_u32(sK));
+#pragma unroll
+      for (int k = 0; k < 8; ++k) {
+        const uint32_t aoff = static_cast<uint32_t>((k >> 2) * (kAbtTile >> 4) + (k & 3) * 2);
+        umma_bf16_ss(tmem_base + 256, ptd + aoff, dod + 128 * k, idesc_g, (t | k) != 0);    // dV += P^T dO_t
+        umma_bf16_ss(tmem_base + 320, dstd + aoff, qd + 128 * k, idesc_g, (t | k) != 0);    // dK += dS^T Q_t
+        umma_bf16_ss(tmem_base + 384, dsd + aoff, kd + 128 * k, idesc_g, k != 0);           // dQ block = dS K
+      }
+      tcgen05_commit(bar_mma);
+    }
+    wait_mma();
+    // dQ block -> fp32 reductions into dq_acc (this warp's half of the 64 columns)
+    for (int c = half; c < 4; c += 2) {
+      uint32_t r[16];
+      tmem_ld_32x32b_x16(lane_addr + 384 + c * 16, r);
+      tmem_wait_ld16(r);
+      if (qrow < a.N) {
+        float* dst = a.dq_acc + (static_cast<size_t>(b) * a.N + qrow) * a.D + h * 64 + c * 16;
+#pragma unroll
+        for (int i = 0; i < 16; i += 4)
+          red_add_v4(dst + i, __uint_as_float(r[i]), __uint_as_float(r[i + 1]), __uint_as_float(r[i + 2]), __uint_as_float(r[i + 3]));
+      }
+    }
+    tcgen05_fence_before();
+    __syncthreads();     // S / dP / dQ columns and the operand tiles are free for the next block
+  }
+  // dV, dK of this key tile: thread <-> key row (every MMA completed: the last wait above)
+  {
+    const int key = kh * 128 + row;
+    for (int c = half; c < 8; c += 2) {
+      uint32_t r[16];
+      tmem_ld_32x32b_x16(lane_addr + 256 + c * 16, r);
+      tmem_wait_ld16(r);
+      if (key < a.N) {
+        const int which = c >> 2;
+        __nv_bfloat16* dst = a.dqkv + (static_cast<size_t>(b) * a.N + key) * 3 * a.D + (which ? a.D : 2 * a.D) + h * 64 + (c & 3) * 16;
+        uint4 v0, v1;
+        v0.x = pack_bf16x2(__uint_as_float(r[0]), __uint_as_float(r[1]));   v0.y = pack_bf16x2(__uint_as_float(r[2]), __uint_as_float(r[3]));
+        v0.z = pack_bf16x2(__uint_as_float(r[4]), __uint_as_float(r[5]));   v0.w = pack_bf16x2(__uint_as_float(r[6]), __uint_as_float(r[7]));
+        v1.x = pack_bf16x2(__uint_as_float(r[8]), __uint_as_float(r[9]));   v1.y = pack_bf16x2(__uint_as_float(r[10]), __uint_as_float(r[11]));
+        v1.z = pack_bf16x2(__uint_as_float(r[12]), __uint_as_float(r[13])); v1.w = pack_bf16x2(__uint_as_float(r[14]), __uint_as_float(r[15]));
+        reinterpret_cast<uint4*>(dst)[0] = v0;
+        reinterpret_cast<uint4*>(dst)[1] = v1;
+      }
+    }
+  }
+  tcgen05_fence_before();
+  __syncthreads();
+  if (warp == 1) tmem_dealloc(tmem_base, kAbtTmemCols);
+}
+
 }  // namespace ldit

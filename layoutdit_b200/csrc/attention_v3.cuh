@@ -41,6 +41,7 @@ struct AttnV3Args {
   int Gh, Gw, T;
   int n_ktiles, n_qpairs, num_items;
   float scale_log2e;
+  float* lse;               // optional [B, heads, N]: log2-sum-exp of every row's scaled logits (what the backward needs to recompute P)
   long long* dbg;           // LDIT_A3_TIMELINE builds only: clock64 stamps [CTA < 8][warp 0..9][512]
 };
 
@@ -488,6 +489,8 @@ attention_v3_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
         // 32 rows x 64 bf16 of this warp -> swizzled smem (this warp's quarter of the item's Q tile: every MMA that
         // read it has completed) -> one TMA store (rows past N are clipped by the 3-D tensor map)
         const float inv = 1.0f / l_run;
+        if (a.lse != nullptr && q < a.N)   // exact whatever the lazy running max was: m + log2(sum exp2(s - m))
+          a.lse[(static_cast<size_t>(b) * a.heads + h) * a.N + q] = m_run + log2f(l_run);
         uint8_t* stage = sQ + (qb * 2 + g) * 16384 + quarter * 4096;
         uint32_t oa[16], ob[16];
         tmem_ld_32x32b_x16(lane_addr + kA3OCol, oa);

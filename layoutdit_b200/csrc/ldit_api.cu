@@ -989,7 +989,16 @@ int ldit_patch_embed_pages(const void* const* pages, const int* page_hw, int max
   return launch_gemm<EPI_PATCH>(scratch, w, g, st);
 }
 
+static int attention_forward(const void* qkv, void* ctx, const void* bias_table, float* lse, int B, int N, int heads, int Gh, int Gw, void* stream);
 int ldit_attention(const void* qkv, void* ctx, const void* bias_table, int B, int N, int heads, int Gh, int Gw, void* stream) {
+  return attention_forward(qkv, ctx, bias_table, nullptr, B, N, heads, Gh, Gw, stream);
+}
+int ldit_attention_lse(const void* qkv, void* ctx, const void* bias_table, void* lse, int B, int N, int heads, int Gh, int Gw, void* stream) {
+  if (!lse) return LDIT_E_NULL;
+  if (!aligned16(lse)) return LDIT_E_ALIGN;
+  return attention_forward(qkv, ctx, bias_table, static_cast<float*>(lse), B, N, heads, Gh, Gw, stream);
+}
+static int attention_forward(const void* qkv, void* ctx, const void* bias_table, float* lse, int B, int N, int heads, int Gh, int Gw, void* stream) {
   if (!qkv || !ctx) return LDIT_E_NULL;
   if (B <= 0 || heads <= 0 || Gh <= 0 || Gw <= 0 || N != Gh * Gw + 1) return LDIT_E_SHAPE;
   if (!aligned16(qkv) || !aligned16(ctx) || !aligned16(bias_table)) return LDIT_E_ALIGN;
@@ -1012,6 +1021,7 @@ int ldit_attention(const void* qkv, void* ctx, const void* bias_table, int B, in
     a.n_qpairs = (N + 255) / 256;
     a.num_items = B * heads * a.n_qpairs;
     a.scale_log2e = scale_log2e;
+    a.lse = lse;
     a.dbg = g_attn_dbg;
     CUtensorMap tmQ, tmKV, tmO;
     int rc = make_tmap_qkv_3d(&tmQ, qkv, B, N, 3 * D, 128);
@@ -1036,6 +1046,7 @@ int ldit_attention(const void* qkv, void* ctx, const void* bias_table, int B, in
 #ifndef LDIT_EXPERIMENTAL
   return LDIT_E_UNSUPPORTED;   // impl 1 / 2 / 4: the superseded round-1 kernels, only in -DLDIT_EXPERIMENTAL builds
 #else
+  if (lse) return LDIT_E_UNSUPPORTED;   // only the product kernel writes row statistics
   if (impl == 4) {
     AttnP2Args a{};
     a.ctx = static_cast<__nv_bfloat16*>(ctx);
@@ -1328,6 +1339,45 @@ int ldit_attention_bwd(const void* qkv, const void* dctx, void* dqkv, int B, int
   cudaError_t e = ensure_smem(attention_bwd_tc_kernel, smem, false);
   if (e != cudaSuccess) return static_cast<int>(e);
   attention_bwd_tc_kernel<<<B * heads, kAbtThreads, smem, static_cast<cudaStream_t>(stream)>>>(tmQKV, tmDO, a);
+  return check_launch();
+}
+
+int ldit_attention_bwd_flash(const void* qkv, const void* ctx, const void* lse, const void* dctx, void* dqkv, void* dq_acc, void* delta,
+                             int B, int N, int heads, void* stream) {
+  if (!qkv || !ctx || !lse || !dctx || !dqkv || !dq_acc || !delta) return LDIT_E_NULL;
+  if (B <= 0 || heads <= 0 || N <= 0 || B * heads > 65535) return LDIT_E_SHAPE;
+  if (!aligned16(qkv) || !aligned16(ctx) || !aligned16(lse) || !aligned16(dctx) || !aligned16(dqkv) || !aligned16(dq_acc) || !aligned16(delta))
+    return LDIT_E_ALIGN;
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  const int D = heads * 64;
+  const size_t rows = static_cast<size_t>(B) * N;
+  cudaError_t e = cudaMemsetAsync(dq_acc, 0, rows * D * sizeof(float), st);
+  if (e != cudaSuccess) { (void)cudaGetLastError(); return static_cast<int>(e); }
+  attention_delta_kernel<<<static_cast<unsigned>((rows * heads + 255) / 256), 256, 0, st>>>(
+      static_cast<const __nv_bfloat16*>(dctx), static_cast<const __nv_bfloat16*>(ctx), static_cast<float*>(delta), B, N, heads);
+  int rc = check_launch();
+  if (rc) return rc;
+  AttnBwdFlashArgs a{};
+  a.lse = static_cast<const float*>(lse);
+  a.delta = static_cast<const float*>(delta);
+  a.dq_acc = static_cast<float*>(dq_acc);
+  a.dqkv = static_cast<__nv_bfloat16*>(dqkv);
+  a.B = B; a.N = N; a.heads = heads; a.D = D;
+  a.nqt = (N + 127) / 128;
+  a.scale = 0.125f;
+  a.scale_log2e = 0.125f * 1.4426950408889634f;
+  CUtensorMap tmQKV, tmDO;
+  rc = make_tmap_qkv_3d(&tmQKV, qkv, B, N, 3 * D, 128);
+  if (rc) return rc;
+  rc = make_tmap_rows_3d(&tmDO, dctx, B, N, D, 128);
+  if (rc) return rc;
+  const size_t smem = 1024 + kAbfSmemTiles + 64;
+  e = ensure_smem(attention_bwd_flash_kernel, smem, false);
+  if (e != cudaSuccess) return static_cast<int>(e);
+  attention_bwd_flash_kernel<<<dim3(a.nqt, B * heads), kAbtThreads, smem, st>>>(tmQKV, tmDO, a);
+  rc = check_launch();
+  if (rc) return rc;
+  dq_cast_kernel<<<static_cast<unsigned>((rows * (D / 8) + 255) / 256), 256, 0, st>>>(static_cast<const float*>(dq_acc), static_cast<__nv_bfloat16*>(dqkv), rows, D);
   return check_launch();
 }
 

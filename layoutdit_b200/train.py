@@ -1,15 +1,16 @@
-"""Training path, first vertical slice: one ``BeitLayer`` forward + backward as a
-``torch.autograd.Function`` over the C ABI, an encoder that chains such layers, and the bucketed gradient all-reduce of a
-data-parallel step.
+"""Training path: ``DiTBackbone.forward`` differentiable end to end -- embeddings, every
+``BeitLayer`` and the four taps as ``torch.autograd.Function``s over the C ABI (``TrainableBackbone``; ``TrainableEncoder``
+is the layer stack alone) -- and the bucketed gradient all-reduce of a data-parallel step.
 
 What the reference does here: ``LayoutDetectionModel`` is trained with ``torch.autograd`` through HF ``BeitLayer``
 (HF:469-508) under autocast, ``scaler.scale(loss).backward()`` (R:src/layoutdit/training/trainer.py:164-183); it has no
 distributed code (R:README.md:59) -- BASELINE config 5 asks for DDP with an NCCL gradient all-reduce, which is new.
 
-Scope of this slice (the rest is listed in DESIGN.md "next"): absolute-position configurations (no relative-position
+Scope (the rest is listed in DESIGN.md "next"): absolute-position configurations (no relative-position
 bias: its table gradient is not written yet), drop-path rate 0 (HF's training-mode stochastic depth, HF:61-73, is a
-per-sample Bernoulli scaling of the two branches), sequences of at most 256 tokens (the attention backward is a
-correctness-first CUDA-core kernel; 224 x 224 pages have 197).  The eight GEMMs of a layer's backward run on the
+per-sample Bernoulli scaling of the two branches).  The attention backward is a tcgen05 kernel: up to 256 tokens (224 x 224
+pages have 197) one self-contained CTA per (image, head); beyond that a flash-style kernel over key tiles that recomputes P
+from the row statistics the forward writes (``ldit_attention_lse``).  The eight GEMMs of a layer's backward run on the
 forward's tcgen05 kernel; see ``csrc/backward.cuh``.
 
 Dtypes: bf16 activations and activation gradients, fp32 residual stream / residual-stream gradients / parameter
@@ -88,6 +89,23 @@ class _K:
         _lib.check(self.lib.ldit_attention_bwd(qkv.data_ptr(), dctx.data_ptr(), dqkv.data_ptr(), B, N, heads, _st(self.dev)), "ldit_attention_bwd")
         return dqkv
 
+    def attention_lse(self, qkv, B, N, heads, Gh, Gw):
+        D = heads * 64
+        ctx = torch.empty(B * N, D, device=self.dev, dtype=_BF)
+        lse = torch.empty(B, heads, N, device=self.dev, dtype=torch.float32)
+        _lib.check(self.lib.ldit_attention_lse(qkv.data_ptr(), ctx.data_ptr(), None, lse.data_ptr(), B, N, heads, Gh, Gw, _st(self.dev)), "ldit_attention_lse")
+        return ctx, lse
+
+    def attention_bwd_flash(self, qkv, ctx, lse, dctx, B, N, heads):
+        """Any sequence length: key-tile CTAs, P recomputed from the forward's row statistics."""
+        D = heads * 64
+        dqkv = torch.empty_like(qkv)
+        dq_acc = torch.empty(B * N, D, device=self.dev, dtype=torch.float32)
+        delta = torch.empty(B * heads * N, device=self.dev, dtype=torch.float32)
+        _lib.check(self.lib.ldit_attention_bwd_flash(qkv.data_ptr(), ctx.data_ptr(), lse.data_ptr(), dctx.data_ptr(), dqkv.data_ptr(),
+                                                     dq_acc.data_ptr(), delta.data_ptr(), B, N, heads, _st(self.dev)), "ldit_attention_bwd_flash")
+        return dqkv
+
     def transpose(self, t):
         """[R, C] -> [C, R padded to a multiple of 8] (zero padding: the token dimension becomes the wgrad GEMM's K)."""
         R, C = t.shape
@@ -163,7 +181,10 @@ class BeitLayerFunction(torch.autograd.Function):
         lam1, lam2 = f32(p["lam1"]), f32(p["lam2"])
         a1 = k.layernorm(x, f32(p["ln1_w"]), f32(p["ln1_b"]), eps)
         qkv = k.gemm(a1, wqkv, bqkv)
-        att = k.attention(qkv, B, N, heads, Gh, Gw)
+        if N > 256:     # the self-contained backward kernel covers two 128-row tiles; beyond that keep the row statistics
+            att, lse = k.attention_lse(qkv, B, N, heads, Gh, Gw)
+        else:
+            att, lse = k.attention(qkv, B, N, heads, Gh, Gw), x.new_empty(0)
         br1 = k.gemm(att, wo, f32(p["bo"]))
         xm = k.scale_residual(x, br1, lam1)
         a2 = k.layernorm(xm, f32(p["ln2_w"]), f32(p["ln2_b"]), eps)
@@ -173,7 +194,7 @@ class BeitLayerFunction(torch.autograd.Function):
         y = k.scale_residual(xm, br2, lam2)
         ctx.geom = geom
         ctx.has_lam = (p["lam1"] is not None, p["lam2"] is not None)
-        ctx.save_for_backward(x, xm, a1, qkv, att, br1, a2, pre, h, br2, wqkv, wo, w1, w2,
+        ctx.save_for_backward(lse, x, xm, a1, qkv, att, br1, a2, pre, h, br2, wqkv, wo, w1, w2,
                               f32(p["ln1_w"]), f32(p["ln2_w"]), lam1 if lam1 is not None else x.new_empty(0),
                               lam2 if lam2 is not None else x.new_empty(0))
         return y
@@ -181,7 +202,7 @@ class BeitLayerFunction(torch.autograd.Function):
     @staticmethod
     def backward(ctx, dy):
         B, N, heads, Gh, Gw, eps = ctx.geom
-        (x, xm, a1, qkv, att, br1, a2, pre, h, br2, wqkv, wo, w1, w2, g1w, g2w, lam1, lam2) = ctx.saved_tensors
+        (lse, x, xm, a1, qkv, att, br1, a2, pre, h, br2, wqkv, wo, w1, w2, g1w, g2w, lam1, lam2) = ctx.saved_tensors
         lam1 = lam1 if ctx.has_lam[0] else None
         lam2 = lam2 if ctx.has_lam[1] else None
         dev = dy.device
@@ -210,7 +231,7 @@ class BeitLayerFunction(torch.autograd.Function):
         dbo = z(D); k.colsum(g1, dbo)
         dwo = z(D, D); k.wgrad(g1, att, dwo)
         datt = k.dgrad(g1, wo)
-        dqkv = k.attention_bwd(qkv, datt, B, N, heads)
+        dqkv = k.attention_bwd(qkv, datt, B, N, heads) if N <= 256 else k.attention_bwd_flash(qkv, att, lse, datt, B, N, heads)
         dbqkv = z(3 * D); k.colsum(dqkv, dbqkv)
         dwqkv = z(3 * D, D); k.wgrad(dqkv, a1, dwqkv)
         da1 = k.dgrad(dqkv, wqkv)

@@ -204,7 +204,7 @@ def test_taps_backward_is_the_adjoint_of_interpolate(lib, B, Gh, Gw, D, scale):
     torch.testing.assert_close(dx.view(B, N, D).double(), x.grad, rtol=1e-5, atol=1e-5)
 
 
-@pytest.mark.parametrize("layer_scale,B,G,abs_pos", [(0.1, 2, 4, True), (0.1, 2, 14, True), (0.0, 1, 4, False)])
+@pytest.mark.parametrize("layer_scale,B,G,abs_pos", [(0.1, 2, 4, True), (0.1, 2, 14, True), (0.0, 1, 4, False), (0.1, 1, 20, True)])   # 20 x 20: 401 tokens, the flash backward
 def test_backbone_gradients_match_oracle_autograd(cuda_device, layer_scale, B, G, abs_pos):
     """DiTBackbone.forward end to end (embeddings, 6 layers, 4 taps) under a dense upstream gradient on every tap:
     every parameter gradient against torch.autograd through the fp64 oracle."""
@@ -242,7 +242,9 @@ def test_backbone_gradients_match_oracle_autograd(cuda_device, layer_scale, B, G
         assert p.grad is not None, name
         e = _rel(p.grad, ref)
         worst, seen = max(worst, e), seen + 1
-        assert e < GRAD_TOL, f"{name}: rel-Frobenius {e:.3e}"
+        # the first layers' key / query weight gradients are the ill-conditioned ones (rows of dS sum to zero: what is left
+        # after the cancellation carries the bf16 rounding of P, dS and O); 401-token rows cancel more than 17- or 197-token ones
+        assert e < (GRAD_TOL if G < 20 else 3e-2), f"{name}: rel-Frobenius {e:.3e}"
     assert seen == 6 * (17 if layer_scale > 0 else 15) + 3 + int(abs_pos)   # every layer tensor, projection w / b, cls (, positions)
     print(f"{seen} parameter gradients, worst rel-Fro {worst:.2e}")
 
@@ -272,3 +274,34 @@ def test_dgrad_gemm_reads_the_weight_as_stored(lib, M, Nout, Kin):
     ref = dy.float() @ w.float()
     assert torch.isfinite(da.float()).all()
     assert _rel(da.float(), ref) < 4e-3
+
+
+@pytest.mark.parametrize("B,heads,Gh,Gw", [(2, 2, 4, 4), (1, 12, 14, 14), (2, 3, 16, 16), (1, 2, 24, 24), (1, 4, 32, 32), (2, 1, 20, 13)])
+def test_attention_backward_any_length(lib, B, heads, Gh, Gw):
+    """ldit_attention_lse + ldit_attention_bwd_flash (key-tile CTAs, dQ through fp32 reductions) vs fp64 autograd; also
+    checks the row statistics the forward writes."""
+    N, D = Gh * Gw + 1, heads * 64
+    g = torch.Generator(device="cuda").manual_seed(N + heads)
+    qkv = torch.randn(B * N, 3 * D, device="cuda", generator=g).to(torch.bfloat16)
+    dctx = torch.randn(B * N, D, device="cuda", generator=g).to(torch.bfloat16)
+    ctx = torch.empty(B * N, D, device="cuda", dtype=torch.bfloat16)
+    lse = torch.full((B, heads, N), float("nan"), device="cuda")
+    _lib.check(lib.ldit_attention_lse(qkv.data_ptr(), ctx.data_ptr(), None, lse.data_ptr(), B, N, heads, Gh, Gw, _st()), "attn_lse")
+    x = qkv.double().requires_grad_(True)
+    q, k, v = x.reshape(B, N, 3, heads, 64).permute(2, 0, 3, 1, 4)
+    s = q @ k.transpose(-1, -2) / 8.0
+    ref_lse = torch.logsumexp(s, dim=-1) / torch.log(torch.tensor(2.0, dtype=torch.float64))
+    torch.testing.assert_close(lse.double(), ref_lse.detach(), rtol=0, atol=2e-3)
+    ref_ctx = (torch.softmax(s, dim=-1) @ v).transpose(1, 2).reshape(B * N, D)
+    ref_ctx.backward(dctx.double())
+    dqkv = torch.full_like(qkv, float("nan"))
+    dq_acc = torch.empty(B * N, D, device="cuda")
+    delta = torch.empty(B * heads * N, device="cuda")
+    _lib.check(lib.ldit_attention_bwd_flash(qkv.data_ptr(), ctx.data_ptr(), lse.data_ptr(), dctx.data_ptr(), dqkv.data_ptr(), dq_acc.data_ptr(),
+                                            delta.data_ptr(), B, N, heads, _st()), "attn_bwd_flash")
+    assert torch.isfinite(dqkv.float()).all()
+    assert _rel(dqkv.float(), x.grad) < 8e-3
+    if N <= 256:   # agrees with the self-contained two-tile kernel
+        d2 = torch.empty_like(qkv)
+        _lib.check(lib.ldit_attention_bwd(qkv.data_ptr(), dctx.data_ptr(), d2.data_ptr(), B, N, heads, _st()), "attn_bwd")
+        assert _rel(dqkv.float(), d2.float()) < 8e-3
