@@ -286,14 +286,24 @@ class PatchEmbedFunction(torch.autograd.Function):
         wb = w.detach().reshape(D, -1).to(dev, _BF).contiguous()
         bias = b.detach().to(dev, torch.float32).contiguous()
         clsv = cls.detach().reshape(D).to(dev, torch.float32).contiguous()
+        resize = None
         if pos is not None:
-            if pos.shape[1] != N:
-                raise NotImplementedError("the training path runs at the native grid (the position table's bicubic resize has no backward yet)")
+            g = int(round((pos.shape[1] - 1) ** 0.5))
+            if g * g + 1 != pos.shape[1]:
+                raise ValueError("position table must hold a square grid + the CLS row")
+            native = (Gh * Gw == g * g and H == W)             # HF:138-141
+            gh, gw = (Gh, Gw) if native else (g, g)
             pt = pos.detach().to(dev, torch.float32).contiguous()
             pos_bias = torch.empty(P, D, device=dev, dtype=torch.float32)
             cls_pos = torch.empty(D, device=dev, dtype=torch.float32)
-            _lib.check(k.lib.ldit_resize_rows(pt[0, 1:].data_ptr(), pos_bias.data_ptr(), bias.data_ptr(), Gh, Gw, Gh, Gw, D, 1, st), "ldit_resize_rows")
+            _lib.check(k.lib.ldit_resize_rows(pt[0, 1:].data_ptr(), pos_bias.data_ptr(), bias.data_ptr(), gh, gw, Gh, Gw, D, 1, st), "ldit_resize_rows")
             _lib.check(k.lib.ldit_resize_rows(pt[0, :1].data_ptr(), cls_pos.data_ptr(), clsv.data_ptr(), 1, 1, 1, 1, D, 1, st), "ldit_resize_rows")
+            if not native:
+                # the bicubic resize (HF:143-159) is linear in the table: its matrix R [P, g*g] is the resize of the identity
+                # (one unit image per native cell); the backward applies R^T
+                eye = torch.eye(g * g, device=dev, dtype=torch.float32)
+                resize = torch.empty(P, g * g, device=dev, dtype=torch.float32)
+                _lib.check(k.lib.ldit_resize_rows(eye.data_ptr(), resize.data_ptr(), None, g, g, Gh, Gw, g * g, 1, st), "ldit_resize_rows")
         else:
             pos_bias, cls_pos = bias.expand(P, D).contiguous(), clsv
         scratch = torch.empty(k.lib.ldit_patch_embed_scratch_bytes(B, H, W) // 2, device=dev, dtype=_BF)
@@ -301,14 +311,14 @@ class PatchEmbedFunction(torch.autograd.Function):
         _lib.check(k.lib.ldit_patch_embed(px.data_ptr(), _lib.DTYPE_F32, wb.data_ptr(), pos_bias.data_ptr(), cls_pos.data_ptr(),
                                           scratch.data_ptr(), x.data_ptr(), B, H, W, D, st), "ldit_patch_embed")
         ctx.geom, ctx.has_pos, ctx.wshape = (B, Gh, Gw, D), pos is not None, tuple(w.shape)
-        ctx.save_for_backward(scratch)
+        ctx.save_for_backward(scratch, resize if resize is not None else x.new_empty(0))
         return x
 
     @staticmethod
     def backward(ctx, dx):
         B, Gh, Gw, D = ctx.geom
         P, N = Gh * Gw, Gh * Gw + 1
-        (scratch,) = ctx.saved_tensors
+        scratch, resize = ctx.saved_tensors
         dev = dx.device
         k = _K(dev)
         st = _st(dev)
@@ -323,7 +333,11 @@ class PatchEmbedFunction(torch.autograd.Function):
         dsum = torch.zeros(N * D, device=dev, dtype=torch.float32)         # every image adds the same cls / position rows
         _lib.check(k.lib.ldit_batch_sum(dx.data_ptr(), dsum.data_ptr(), B, N * D, st), "ldit_batch_sum")
         dcls = dsum[:D].clone().view(1, 1, D)
-        dpos = dsum.view(1, N, D) if ctx.has_pos else None
+        dpos = None
+        if ctx.has_pos:
+            dpos = dsum.view(1, N, D)
+            if resize.numel():   # non-native grid: rows 1.. go back through the resize (a [g*g, P] x [P, D] product, fp32)
+                dpos = torch.cat([dpos[:, :1], (resize.t() @ dpos[0, 1:]).unsqueeze(0)], dim=1)
         return None, None, dw.view(ctx.wshape), db, dcls, dpos
 
 

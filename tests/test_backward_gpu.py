@@ -204,8 +204,10 @@ def test_taps_backward_is_the_adjoint_of_interpolate(lib, B, Gh, Gw, D, scale):
     torch.testing.assert_close(dx.view(B, N, D).double(), x.grad, rtol=1e-5, atol=1e-5)
 
 
-@pytest.mark.parametrize("layer_scale,B,G,abs_pos", [(0.1, 2, 4, True), (0.1, 2, 14, True), (0.0, 1, 4, False), (0.1, 1, 20, True)])   # 20 x 20: 401 tokens, the flash backward
-def test_backbone_gradients_match_oracle_autograd(cuda_device, layer_scale, B, G, abs_pos):
+@pytest.mark.parametrize("layer_scale,B,G,abs_pos,PG", [(0.1, 2, 4, True, 4), (0.1, 2, 14, True, 14), (0.0, 1, 4, False, 4),
+                                                         (0.1, 1, 20, True, 20),     # 401 tokens: the flash backward
+                                                         (0.1, 2, 4, True, 6)])      # 6 x 6 pages on a 4 x 4 table: bicubic resize adjoint
+def test_backbone_gradients_match_oracle_autograd(cuda_device, layer_scale, B, G, abs_pos, PG):
     """DiTBackbone.forward end to end (embeddings, 6 layers, 4 taps) under a dense upstream gradient on every tap:
     every parameter gradient against torch.autograd through the fp64 oracle."""
     from layoutdit_b200.train import TrainableBackbone
@@ -213,7 +215,7 @@ def test_backbone_gradients_match_oracle_autograd(cuda_device, layer_scale, B, G
                     layer_scale_init_value=layer_scale, use_absolute_position_embeddings=abs_pos)
     sd = make_state_dict(cfg, 79, True)
     gen = torch.Generator().manual_seed(7)
-    pages = torch.rand(B, 3, G * 16, G * 16, generator=gen)
+    pages = torch.rand(B, 3, PG * 16, PG * 16, generator=gen)
     tree = DiTParameters(cfg)
     tree.load_state_dict(sd)
     tree = tree.cuda()
@@ -226,7 +228,7 @@ def test_backbone_gradients_match_oracle_autograd(cuda_device, layer_scale, B, G
     hs = dit_oracle.hidden_states(sd64, cd, pages.double())
     loss = 0.0
     for j, (idx, scale) in enumerate(zip(dit_oracle.tap_layer_indices(cfg.num_hidden_layers), dit_oracle.TAP_SCALES)):
-        t = hs[idx][:, 1:, :].permute(0, 2, 1).reshape(B, cfg.hidden_size, G, G)
+        t = hs[idx][:, 1:, :].permute(0, 2, 1).reshape(B, cfg.hidden_size, PG, PG)
         if scale != 1.0:
             t = dit_oracle.resample_bilinear(t, scale)
         assert _rel(feats[f"p{j + 2}"].detach().float(), t.detach()) < 1e-2
@@ -244,7 +246,7 @@ def test_backbone_gradients_match_oracle_autograd(cuda_device, layer_scale, B, G
         worst, seen = max(worst, e), seen + 1
         # the first layers' key / query weight gradients are the ill-conditioned ones (rows of dS sum to zero: what is left
         # after the cancellation carries the bf16 rounding of P, dS and O); 401-token rows cancel more than 17- or 197-token ones
-        assert e < (GRAD_TOL if G < 20 else 3e-2), f"{name}: rel-Frobenius {e:.3e}"
+        assert e < (GRAD_TOL if G < 20 else 3e-2), f"{name}: rel-Frobenius {e:.3e} (worst so far {worst:.3e})"
     assert seen == 6 * (17 if layer_scale > 0 else 15) + 3 + int(abs_pos)   # every layer tensor, projection w / b, cls (, positions)
     print(f"{seen} parameter gradients, worst rel-Fro {worst:.2e}")
 
