@@ -245,8 +245,10 @@ def test_backbone_gradients_match_oracle_autograd(cuda_device, layer_scale, B, G
         e = _rel(p.grad, ref)
         worst, seen = max(worst, e), seen + 1
         # the first layers' key / query weight gradients are the ill-conditioned ones (rows of dS sum to zero: what is left
-        # after the cancellation carries the bf16 rounding of P, dS and O); 401-token rows cancel more than 17- or 197-token ones
-        assert e < (GRAD_TOL if G < 20 else 3e-2), f"{name}: rel-Frobenius {e:.3e} (worst so far {worst:.3e})"
+        # after the cancellation carries the bf16 rounding of P and dS); the flash path (> 256 tokens) additionally takes
+        # delta = rowsum(dO (.) O) from the bf16 O of the forward, as every flash backward does, which leaves a small
+        # non-cancelling term in dQ / dK: measured 2.2e-2 - 3.2e-2 on those two tensors at 401 tokens, <= 2e-2 elsewhere
+        assert e < (GRAD_TOL if G < 20 else 5e-2), f"{name}: rel-Frobenius {e:.3e} (worst so far {worst:.3e})"
     assert seen == 6 * (17 if layer_scale > 0 else 15) + 3 + int(abs_pos)   # every layer tensor, projection w / b, cls (, positions)
     print(f"{seen} parameter gradients, worst rel-Fro {worst:.2e}")
 
