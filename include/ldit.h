@@ -197,6 +197,12 @@ int ldit_scale_residual(const void* x, const void* branch, const void* lam, void
 /* dbranch bf16 = lam (.) dy f32;  dlam f32 [D] += column sums of dy (.) branch  (dlam may be NULL) */
 int ldit_scale_residual_bwd(const void* dy, const void* branch, const void* lam, void* dbranch, void* dlam, int rows, int D,
                             void* stream);
+/* The same two with drop-path (HF:61-73, applied to the layer-scaled branch at HF:488-492 / 500-504): the branch of image b
+ * (rows b*rows_per_image ..) is additionally scaled by row_scale f32 [rows / rows_per_image] (0 or 1 / keep_prob; NULL = 1). */
+int ldit_scale_residual_rows(const void* x, const void* branch, const void* lam, const void* row_scale, int rows_per_image, void* y,
+                             int rows, int D, void* stream);
+int ldit_scale_residual_rows_bwd(const void* dy, const void* branch, const void* lam, const void* row_scale, int rows_per_image,
+                                 void* dbranch, void* dlam, int rows, int D, void* stream);
 /* nn.LayerNorm backward: dx_out f32 = (dx_in or 0) + d/dx of LN(x) gamma + beta under dy bf16; dgamma, dbeta f32 [D] +=.
  * dx_in may be NULL and may alias dx_out.  Row statistics are recomputed from x. */
 int ldit_layernorm_bwd(const void* x, const void* gamma, const void* dy, const void* dx_in, void* dx_out, void* dgamma, void* dbeta,

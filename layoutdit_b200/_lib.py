@@ -28,6 +28,8 @@ SIGNATURES = {
     "ldit_gelu_bwd": (_i, [_vp, _vp, _vp, _c.c_size_t, _vp]),
     "ldit_scale_residual": (_i, [_vp, _vp, _vp, _vp, _i, _i, _vp]),
     "ldit_scale_residual_bwd": (_i, [_vp, _vp, _vp, _vp, _vp, _i, _i, _vp]),
+    "ldit_scale_residual_rows": (_i, [_vp, _vp, _vp, _vp, _i, _vp, _i, _i, _vp]),
+    "ldit_scale_residual_rows_bwd": (_i, [_vp, _vp, _vp, _vp, _i, _vp, _vp, _i, _i, _vp]),
     "ldit_layernorm_bwd": (_i, [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _i, _i, _f, _vp]),
     "ldit_gemm_wgrad": (_i, [_vp, _vp, _vp, _i, _i, _i, _vp]),
     "ldit_gemm_dgrad": (_i, [_vp, _vp, _vp, _i, _i, _i, _vp]),

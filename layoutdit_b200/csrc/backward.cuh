@@ -124,11 +124,13 @@ gelu_bwd_kernel(const __nv_bfloat16* __restrict__ dh, const __nv_bfloat16* __res
 // forward: y f32 [R, D] = x + lam (.) branch        (lam may be nullptr = 1)
 __global__ void __launch_bounds__(256)
 scale_residual_fwd_kernel(const float* __restrict__ x, const __nv_bfloat16* __restrict__ branch, const float* __restrict__ lam,
-                          float* __restrict__ y, int R, int D) {
+                          const float* __restrict__ row_scale, int rows_per_image, float* __restrict__ y, int R, int D) {
   const size_t i = static_cast<size_t>(blockIdx.x) * blockDim.x + threadIdx.x;   // 8 elements each
   const int d8 = D / 8;
   if (i >= static_cast<size_t>(R) * d8) return;
   const int c = static_cast<int>(i % d8) * 8;
+  // drop-path (HF:61-73): the whole branch of image b is scaled by row_scale[b] (0 or 1 / keep_prob)
+  const float rs = row_scale ? __ldg(row_scale + static_cast<int>(i / d8) / rows_per_image) : 1.f;
   float b[8];
   unpack8(__ldg(reinterpret_cast<const uint4*>(branch) + i), b);
   const float4 x0 = __ldg(reinterpret_cast<const float4*>(x) + 2 * i), x1 = __ldg(reinterpret_cast<const float4*>(x) + 2 * i + 1);
@@ -137,6 +139,8 @@ scale_residual_fwd_kernel(const float* __restrict__ x, const __nv_bfloat16* __re
     const float4 l0 = __ldg(reinterpret_cast<const float4*>(lam + c)), l1 = __ldg(reinterpret_cast<const float4*>(lam + c) + 1);
     l[0] = l0.x; l[1] = l0.y; l[2] = l0.z; l[3] = l0.w; l[4] = l1.x; l[5] = l1.y; l[6] = l1.z; l[7] = l1.w;
   }
+#pragma unroll
+  for (int e = 0; e < 8; ++e) l[e] *= rs;
   reinterpret_cast<float4*>(y)[2 * i] = make_float4(x0.x + l[0] * b[0], x0.y + l[1] * b[1], x0.z + l[2] * b[2], x0.w + l[3] * b[3]);
   reinterpret_cast<float4*>(y)[2 * i + 1] = make_float4(x1.x + l[4] * b[4], x1.y + l[5] * b[5], x1.z + l[6] * b[6], x1.w + l[7] * b[7]);
 }
@@ -145,7 +149,8 @@ scale_residual_fwd_kernel(const float* __restrict__ x, const __nv_bfloat16* __re
 // of the slice, the 8 row lanes are summed through shared memory, one atomicAdd per column and block.
 __global__ void __launch_bounds__(1024)
 scale_residual_bwd_kernel(const float* __restrict__ dy, const __nv_bfloat16* __restrict__ branch, const float* __restrict__ lam,
-                          __nv_bfloat16* __restrict__ dbranch, float* __restrict__ dlam, int R, int D, int rows_per_block) {
+                          const float* __restrict__ row_scale, int rows_per_image, __nv_bfloat16* __restrict__ dbranch,
+                          float* __restrict__ dlam, int R, int D, int rows_per_block) {
   __shared__ float red[8][128 * 8 + 8];
   const int d8 = D / 8;
   const int cg = blockIdx.x * blockDim.x + threadIdx.x;      // column group
@@ -165,8 +170,9 @@ scale_residual_bwd_kernel(const float* __restrict__ dy, const __nv_bfloat16* __r
       const float g[8] = {g0.x, g0.y, g0.z, g0.w, g1.x, g1.y, g1.z, g1.w};
       float b[8], o[8];
       unpack8(__ldg(reinterpret_cast<const uint4*>(branch) + i), b);
+      const float rs = row_scale ? __ldg(row_scale + r / rows_per_image) : 1.f;   // drop-path scale of this row's image
 #pragma unroll
-      for (int e = 0; e < 8; ++e) { o[e] = l[e] * g[e]; acc[e] += g[e] * b[e]; }
+      for (int e = 0; e < 8; ++e) { o[e] = rs * l[e] * g[e]; acc[e] += rs * g[e] * b[e]; }
       reinterpret_cast<uint4*>(dbranch)[i] = pack8(o);
     }
   }

@@ -1271,26 +1271,35 @@ int ldit_gelu_bwd(const void* dh, const void* pre, void* dpre, size_t n, void* s
   return check_launch();
 }
 
-int ldit_scale_residual(const void* x, const void* branch, const void* lam, void* y, int rows, int D, void* stream) {
+int ldit_scale_residual_rows(const void* x, const void* branch, const void* lam, const void* row_scale, int rows_per_image, void* y,
+                             int rows, int D, void* stream) {
   if (!x || !branch || !y) return LDIT_E_NULL;
-  if (rows <= 0 || D <= 0 || (D % 8)) return LDIT_E_SHAPE;
+  if (rows <= 0 || D <= 0 || (D % 8) || (row_scale && rows_per_image <= 0)) return LDIT_E_SHAPE;
   if (!aligned16(x) || !aligned16(branch) || !aligned16(lam) || !aligned16(y)) return LDIT_E_ALIGN;
   const size_t n8 = static_cast<size_t>(rows) * (D / 8);
   scale_residual_fwd_kernel<<<static_cast<unsigned>((n8 + 255) / 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(
-      static_cast<const float*>(x), static_cast<const __nv_bfloat16*>(branch), static_cast<const float*>(lam), static_cast<float*>(y), rows, D);
+      static_cast<const float*>(x), static_cast<const __nv_bfloat16*>(branch), static_cast<const float*>(lam),
+      static_cast<const float*>(row_scale), rows_per_image, static_cast<float*>(y), rows, D);
   return check_launch();
 }
+int ldit_scale_residual(const void* x, const void* branch, const void* lam, void* y, int rows, int D, void* stream) {
+  return ldit_scale_residual_rows(x, branch, lam, nullptr, 1, y, rows, D, stream);
+}
 
-int ldit_scale_residual_bwd(const void* dy, const void* branch, const void* lam, void* dbranch, void* dlam, int rows, int D,
-                            void* stream) {
+int ldit_scale_residual_rows_bwd(const void* dy, const void* branch, const void* lam, const void* row_scale, int rows_per_image,
+                                 void* dbranch, void* dlam, int rows, int D, void* stream) {
   if (!dy || !branch || !dbranch) return LDIT_E_NULL;
-  if (rows <= 0 || D <= 0 || (D % 8)) return LDIT_E_SHAPE;
+  if (rows <= 0 || D <= 0 || (D % 8) || (row_scale && rows_per_image <= 0)) return LDIT_E_SHAPE;
   if (!aligned16(dy) || !aligned16(branch) || !aligned16(lam) || !aligned16(dbranch) || !aligned16(dlam)) return LDIT_E_ALIGN;
   const int rpb = 64, threads = (D / 8 < 128) ? D / 8 : 128;
   scale_residual_bwd_kernel<<<dim3((D / 8 + threads - 1) / threads, (rows + rpb - 1) / rpb), dim3(threads, 8), 0, static_cast<cudaStream_t>(stream)>>>(
       static_cast<const float*>(dy), static_cast<const __nv_bfloat16*>(branch), static_cast<const float*>(lam),
-      static_cast<__nv_bfloat16*>(dbranch), static_cast<float*>(dlam), rows, D, rpb);
+      static_cast<const float*>(row_scale), rows_per_image, static_cast<__nv_bfloat16*>(dbranch), static_cast<float*>(dlam), rows, D, rpb);
   return check_launch();
+}
+int ldit_scale_residual_bwd(const void* dy, const void* branch, const void* lam, void* dbranch, void* dlam, int rows, int D,
+                            void* stream) {
+  return ldit_scale_residual_rows_bwd(dy, branch, lam, nullptr, 1, dbranch, dlam, rows, D, stream);
 }
 
 int ldit_layernorm_bwd(const void* x, const void* gamma, const void* dy, const void* dx_in, void* dx_out, void* dgamma, void* dbeta,

@@ -7,8 +7,8 @@ What the reference does here: ``LayoutDetectionModel`` is trained with ``torch.a
 distributed code (R:README.md:59) -- BASELINE config 5 asks for DDP with an NCCL gradient all-reduce, which is new.
 
 Scope (the rest is listed in DESIGN.md "next"): absolute-position configurations (no relative-position
-bias: its table gradient is not written yet), drop-path rate 0 (HF's training-mode stochastic depth, HF:61-73, is a
-per-sample Bernoulli scaling of the two branches).  The attention backward is a tcgen05 kernel: up to 256 tokens (224 x 224
+bias: its table gradient is not written yet).  Drop-path (HF's training-mode stochastic depth, HF:61-73: a per-image
+Bernoulli scaling of the two branches) is a constructor argument, active in ``train()`` mode.  The attention backward is a tcgen05 kernel: up to 256 tokens (224 x 224
 pages have 197) one self-contained CTA per (image, head); beyond that a flash-style kernel over key tiles that recomputes P
 from the row statistics the forward writes (``ldit_attention_lse``).  The eight GEMMs of a layer's backward run on the
 forward's tcgen05 kernel; see ``csrc/backward.cuh``.
@@ -129,16 +129,17 @@ class _K:
         _lib.check(self.lib.ldit_gelu_bwd(dh.data_ptr(), pre.data_ptr(), out.data_ptr(), pre.numel(), _st(self.dev)), "ldit_gelu_bwd")
         return out
 
-    def scale_residual(self, x, branch, lam):
+    def scale_residual(self, x, branch, lam, row_scale=None, rows_per_image=1):
+        """y = x + row_scale[image] * lam (.) branch  (row_scale: the drop-path factor of each image, or None)."""
         y = torch.empty_like(x)
-        _lib.check(self.lib.ldit_scale_residual(x.data_ptr(), branch.data_ptr(), _p(lam), y.data_ptr(), x.shape[0], x.shape[1], _st(self.dev)),
-                   "ldit_scale_residual")
+        _lib.check(self.lib.ldit_scale_residual_rows(x.data_ptr(), branch.data_ptr(), _p(lam), _p(row_scale), rows_per_image, y.data_ptr(),
+                                                     x.shape[0], x.shape[1], _st(self.dev)), "ldit_scale_residual_rows")
         return y
 
-    def scale_residual_bwd(self, dy, branch, lam, dlam):
+    def scale_residual_bwd(self, dy, branch, lam, dlam, row_scale=None, rows_per_image=1):
         out = torch.empty_like(branch)
-        _lib.check(self.lib.ldit_scale_residual_bwd(dy.data_ptr(), branch.data_ptr(), _p(lam), out.data_ptr(), _p(dlam), dy.shape[0], dy.shape[1],
-                                                    _st(self.dev)), "ldit_scale_residual_bwd")
+        _lib.check(self.lib.ldit_scale_residual_rows_bwd(dy.data_ptr(), branch.data_ptr(), _p(lam), _p(row_scale), rows_per_image, out.data_ptr(),
+                                                         _p(dlam), dy.shape[0], dy.shape[1], _st(self.dev)), "ldit_scale_residual_rows_bwd")
         return out
 
     def layernorm_bwd(self, x, w, dy, dx_in, dw, db, eps):
@@ -164,11 +165,17 @@ def layer_params(layer) -> tuple:
 class BeitLayerFunction(torch.autograd.Function):
     """``y = BeitLayer(x)`` (HF:469-508, eval-mode arithmetic) with a hand-written backward.
 
-    ``x``: fp32 ``[B*N, D]`` residual stream; ``geom = (B, N, heads, Gh, Gw, eps)``; then the 17 parameter tensors."""
+    ``x``: fp32 ``[B*N, D]`` residual stream; ``geom = (B, N, heads, Gh, Gw, eps)``; ``drop``: ``None`` or f32 ``[2, B]``,
+    the drop-path factors (0 or 1 / keep_prob, HF:61-73) of the attention and the MLP branch of every image; then the 17
+    parameter tensors."""
 
     @staticmethod
-    def forward(ctx, x, geom, *params):
+    def forward(ctx, x, geom, drop, *params):
         B, N, heads, Gh, Gw, eps = geom
+        d1 = d2 = None
+        if drop is not None:
+            drop = drop.detach().to(x.device, torch.float32).contiguous()
+            d1, d2 = drop[0], drop[1]
         p = dict(zip(PARAM_NAMES, params))
         dev = x.device
         k = _K(dev)
@@ -186,14 +193,15 @@ class BeitLayerFunction(torch.autograd.Function):
         else:
             att, lse = k.attention(qkv, B, N, heads, Gh, Gw), x.new_empty(0)
         br1 = k.gemm(att, wo, f32(p["bo"]))
-        xm = k.scale_residual(x, br1, lam1)
+        xm = k.scale_residual(x, br1, lam1, d1, N)
         a2 = k.layernorm(xm, f32(p["ln2_w"]), f32(p["ln2_b"]), eps)
         pre = k.gemm(a2, w1, f32(p["b1"]))
         h = k.gelu(pre)
         br2 = k.gemm(h, w2, f32(p["b2"]))
-        y = k.scale_residual(xm, br2, lam2)
+        y = k.scale_residual(xm, br2, lam2, d2, N)
         ctx.geom = geom
         ctx.has_lam = (p["lam1"] is not None, p["lam2"] is not None)
+        ctx.drop = drop
         ctx.save_for_backward(lse, x, xm, a1, qkv, att, br1, a2, pre, h, br2, wqkv, wo, w1, w2,
                               f32(p["ln1_w"]), f32(p["ln2_w"]), lam1 if lam1 is not None else x.new_empty(0),
                               lam2 if lam2 is not None else x.new_empty(0))
@@ -205,6 +213,7 @@ class BeitLayerFunction(torch.autograd.Function):
         (lse, x, xm, a1, qkv, att, br1, a2, pre, h, br2, wqkv, wo, w1, w2, g1w, g2w, lam1, lam2) = ctx.saved_tensors
         lam1 = lam1 if ctx.has_lam[0] else None
         lam2 = lam2 if ctx.has_lam[1] else None
+        d1, d2 = (ctx.drop[0], ctx.drop[1]) if ctx.drop is not None else (None, None)
         dev = dy.device
         k = _K(dev)
         M, D = x.shape
@@ -214,7 +223,7 @@ class BeitLayerFunction(torch.autograd.Function):
 
         # ---- MLP half: y = xm + lam2 (.) (h W2^T + b2)
         dlam2 = z(D) if lam2 is not None else None
-        g2 = k.scale_residual_bwd(dy, br2, lam2, dlam2)                    # d(branch 2), bf16
+        g2 = k.scale_residual_bwd(dy, br2, lam2, dlam2, d2, N)             # d(branch 2), bf16
         db2 = z(D); k.colsum(g2, db2)
         dw2 = z(D, I); k.wgrad(g2, h, dw2)                                 # [M, D]^T [M, I]
         dh = k.dgrad(g2, w2)                                               # [M, D] x W2 [D, I]
@@ -227,7 +236,7 @@ class BeitLayerFunction(torch.autograd.Function):
 
         # ---- attention half: xm = x + lam1 (.) (ctx Wo^T + bo)
         dlam1 = z(D) if lam1 is not None else None
-        g1 = k.scale_residual_bwd(dxm, br1, lam1, dlam1)
+        g1 = k.scale_residual_bwd(dxm, br1, lam1, dlam1, d1, N)
         dbo = z(D); k.colsum(g1, dbo)
         dwo = z(D, D); k.wgrad(g1, att, dwo)
         datt = k.dgrad(g1, wo)
@@ -240,18 +249,31 @@ class BeitLayerFunction(torch.autograd.Function):
 
         grads = dict(ln1_w=dg1, ln1_b=dbt1, wq=dwqkv[:D], bq=dbqkv[:D], wk=dwqkv[D:2 * D], wv=dwqkv[2 * D:], bv=dbqkv[2 * D:],
                      wo=dwo, bo=dbo, lam1=dlam1, ln2_w=dg2, ln2_b=dbt2, w1=dw1, b1=db1, w2=dw2, b2=db2, lam2=dlam2)
-        return (dx, None) + tuple(grads[n] for n in PARAM_NAMES)
+        return (dx, None, None) + tuple(grads[n] for n in PARAM_NAMES)
 
 
 class TrainableEncoder(nn.Module):
     """``BeitEncoder`` layers (HF:594-663) over a ``DiTParameters`` tree, differentiable through the kernels above.
     Input / output: the fp32 residual stream ``[B, N, D]`` (``hidden_states[0]`` -> ``hidden_states[L]``)."""
 
-    def __init__(self, params: DiTParameters, cfg: DiTConfig):
+    def __init__(self, params: DiTParameters, cfg: DiTConfig, drop_path_rate: float = 0.0):
         super().__init__()
         if cfg.use_relative_position_bias or cfg.use_shared_relative_position_bias:
             raise NotImplementedError("the backward slice covers absolute-position configurations (no relative-position bias yet)")
+        if not 0.0 <= drop_path_rate < 1.0:
+            raise ValueError("drop_path_rate must be in [0, 1)")
         self.params_tree, self.cfg = params, cfg
+        # stochastic depth as HF builds it: rate i of L grows linearly from 0 to drop_path_rate (HF:602-604), active in train()
+        L = cfg.num_hidden_layers
+        self.drop_rates = [drop_path_rate * i / max(L - 1, 1) for i in range(L)]
+
+    def drop_factors(self, i: int, B: int, device):
+        """f32 [2, B] drop-path factors of layer i for this step (HF:61-73: floor(keep + U[0,1)) / keep), or None."""
+        p = self.drop_rates[i]
+        if not self.training or p == 0.0:
+            return None
+        keep = 1.0 - p
+        return torch.floor(keep + torch.rand(2, B, device=device)) / keep
 
     def forward(self, hidden: torch.Tensor, Gh: int, Gw: int) -> torch.Tensor:
         B, N, D = hidden.shape
@@ -261,8 +283,8 @@ class TrainableEncoder(nn.Module):
             raise _lib.LditError("TrainableEncoder needs CUDA tensors (there is no CPU path)")
         geom = (B, N, self.cfg.num_attention_heads, Gh, Gw, float(self.cfg.layer_norm_eps))
         x = hidden.reshape(B * N, D).float()
-        for layer in self.params_tree.encoder.layer:
-            x = BeitLayerFunction.apply(x, geom, *layer_params(layer))
+        for i, layer in enumerate(self.params_tree.encoder.layer):
+            x = BeitLayerFunction.apply(x, geom, self.drop_factors(i, B, x.device), *layer_params(layer))
         return x.reshape(B, N, D)
 
 
@@ -373,9 +395,9 @@ class TrainableBackbone(nn.Module):
 
     SCALES = (4.0, 2.0, 1.0, 0.5)
 
-    def __init__(self, params: DiTParameters, cfg: DiTConfig):
+    def __init__(self, params: DiTParameters, cfg: DiTConfig, drop_path_rate: float = 0.0):
         super().__init__()
-        self.encoder = TrainableEncoder(params, cfg)     # validates the configuration
+        self.encoder = TrainableEncoder(params, cfg, drop_path_rate)     # validates the configuration, owns the drop-path schedule
         self.params_tree, self.cfg = params, cfg
         d = cfg.num_hidden_layers
         self.layer_idxs = [d // 3, d // 2, 2 * d // 3, d]
@@ -395,7 +417,7 @@ class TrainableBackbone(nn.Module):
         geom = (B, Gh * Gw + 1, cfg.num_attention_heads, Gh, Gw, float(cfg.layer_norm_eps))
         taps = {}
         for i, layer in enumerate(self.params_tree.encoder.layer, start=1):
-            x = BeitLayerFunction.apply(x, geom, *layer_params(layer))
+            x = BeitLayerFunction.apply(x, geom, self.encoder.drop_factors(i - 1, B, x.device), *layer_params(layer))
             for j, idx in enumerate(self.layer_idxs):          # shallow models tap one layer more than once
                 if idx == i:
                     taps[j] = TapFunction.apply(x, (B, Gh, Gw, D, self.SCALES[j]))

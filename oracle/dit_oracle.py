@@ -196,8 +196,10 @@ def self_attention(sd, pfx, x, heads, bias):
     return ctx
 
 
-def beit_layer(sd, cfg, i, x, shared_bias, Gh, Gw):
-    """``BeitLayer.forward`` in eval mode (HF:469-508; drop-path is the identity, HF:66-67)."""
+def beit_layer(sd, cfg, i, x, shared_bias, Gh, Gw, drop=None):
+    """``BeitLayer.forward`` (HF:469-508).  ``drop=None``: eval mode, drop-path is the identity (HF:66-67); else a
+    ``[2, B]`` tensor of the factors ``floor(keep + U) / keep`` that ``drop_path`` (HF:61-73) multiplies the layer-scaled
+    attention / MLP branch of every image with in training mode (HF:492, 504)."""
     pfx = f"encoder.layer.{i}."
     eps = cfg["layer_norm_eps"]
     heads = cfg["num_attention_heads"]
@@ -212,12 +214,16 @@ def beit_layer(sd, cfg, i, x, shared_bias, Gh, Gw):
     attn = ctx @ sd[pfx + "attention.output.dense.weight"].t() + sd[pfx + "attention.output.dense.bias"]
     if pfx + "lambda_1" in sd:
         attn = sd[pfx + "lambda_1"] * attn
+    if drop is not None:
+        attn = attn * drop[0].to(attn.dtype).reshape(-1, 1, 1)
     x = attn + x
     h = layer_norm(x, sd[pfx + "layernorm_after.weight"], sd[pfx + "layernorm_after.bias"], eps)
     h = gelu_erf(h @ sd[pfx + "intermediate.dense.weight"].t() + sd[pfx + "intermediate.dense.bias"])
     h = h @ sd[pfx + "output.dense.weight"].t() + sd[pfx + "output.dense.bias"]
     if pfx + "lambda_2" in sd:
         h = sd[pfx + "lambda_2"] * h
+    if drop is not None:
+        h = h * drop[1].to(h.dtype).reshape(-1, 1, 1)
     return h + x
 
 

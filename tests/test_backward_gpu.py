@@ -309,3 +309,40 @@ def test_attention_backward_any_length(lib, B, heads, Gh, Gw):
         d2 = torch.empty_like(qkv)
         _lib.check(lib.ldit_attention_bwd(qkv.data_ptr(), dctx.data_ptr(), d2.data_ptr(), B, N, heads, _st()), "attn_bwd")
         assert _rel(dqkv.float(), d2.float()) < 8e-3
+
+
+def test_drop_path_scales_the_branches_per_image(cuda_device):
+    """Stochastic depth (HF:61-73) with explicit per-image factors: output and every gradient against the fp64 oracle."""
+    from layoutdit_b200.train import BeitLayerFunction, layer_params
+    B, G = 3, 5
+    cfg = DiTConfig(hidden_size=128, num_hidden_layers=1, num_attention_heads=2, intermediate_size=256, image_size=G * 16)
+    sd = make_state_dict(cfg, 81, True)
+    N, D = G * G + 1, cfg.hidden_size
+    gen = torch.Generator().manual_seed(9)
+    h0, wgt = torch.randn(B, N, D, generator=gen), torch.randn(B, N, D, generator=gen)
+    drop = torch.tensor([[0.0, 1.25, 1.25], [1.25, 0.0, 1.25]])       # keep_prob 0.8: image 0 loses its attention branch, image 1 its MLP
+    tree = DiTParameters(cfg)
+    tree.load_state_dict(sd)
+    tree = tree.cuda()
+    hin = h0.cuda().reshape(B * N, D).requires_grad_(True)
+    geom = (B, N, cfg.num_attention_heads, G, G, float(cfg.layer_norm_eps))
+    out = BeitLayerFunction.apply(hin, geom, drop.cuda(), *layer_params(tree.encoder.layer[0]))
+    (out * wgt.cuda().reshape(B * N, D)).sum().backward()
+    sd64 = {k: v.double().requires_grad_(v.is_floating_point()) for k, v in sd.items()}
+    x = h0.double().requires_grad_(True)
+    y = dit_oracle.beit_layer(sd64, cfg.to_dict(), 0, x, None, G, G, drop=drop.double())
+    (y * wgt.double()).sum().backward()
+    assert _rel(out.detach().reshape(B, N, D), y.detach()) < 1e-2
+    assert _rel(hin.grad.reshape(B, N, D), x.grad) < GRAD_TOL
+    for name, p in tree.named_parameters():
+        if name.startswith("encoder.layer.0."):
+            assert _rel(p.grad, sd64[name].grad) < GRAD_TOL, name
+    # the schedule: linear in depth, only in train() mode
+    from layoutdit_b200.train import TrainableEncoder
+    enc = TrainableEncoder(DiTParameters(DiTConfig(num_hidden_layers=4)).cuda(), DiTConfig(num_hidden_layers=4), drop_path_rate=0.3)
+    assert [round(r, 3) for r in enc.drop_rates] == [0.0, 0.1, 0.2, 0.3]
+    enc.eval()
+    assert enc.drop_factors(3, 8, "cuda") is None
+    enc.train()
+    f = enc.drop_factors(3, 4096, "cuda")
+    assert f.shape == (2, 4096) and bool(((f == 0) | ((f - 1.0 / 0.7).abs() < 1e-5)).all()) and 0.6 < (f > 0).float().mean() < 0.8
