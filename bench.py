@@ -320,6 +320,122 @@ def run_train_line(args, cfg, fac, B, H, W, dev, rank, world, peaks):
         dist.destroy_process_group()
 
 
+def run_detector_train_line(args, cfg, fac, dev, rank, world, peaks):
+    """BASELINE config 5: a full LayoutDiT training step -- torchvision FasterRCNN built as R:model.py:33-56 (5 classes,
+    fixed_size 224, mean/std 0.5) around the DiT-base backbone + FPN, synthetic 1024 x 1024 pages with 1-12 boxes each,
+    loss, backward, gradient all-reduce, fused AdamW -- with OUR differentiable backbone inside the detector, against the
+    same detector around the reference's HF backbone under torch autocast bf16 (+ DistributedDataParallel when N > 1).
+    FPN, RPN, RoI heads and losses are torchvision's on both sides."""
+    import numpy as np
+    import torch.distributed as dist
+    from torchvision.models.detection import FasterRCNN
+    from torchvision.models.detection.rpn import AnchorGenerator
+    from torchvision.ops import FeaturePyramidNetwork, MultiScaleRoIAlign
+    from torchvision.ops.feature_pyramid_network import LastLevelMaxPool
+    from layoutdit_b200.synth import make_fpn_state_dict, make_state_dict, raw_pages
+    from layoutdit_b200.train import GradientBuckets, TrainableDiTWithFPN
+    B = 16
+    sd, fsd = make_state_dict(cfg, 0, False), make_fpn_state_dict(cfg.hidden_size, 256, 0, False)
+    pages = [p.to(dev) for p in raw_pages([(1024, 1024)] * B, seed=77 + rank)]
+    rng = np.random.default_rng(5 + rank)
+    targets = []
+    for _ in range(B):
+        n = int(rng.integers(1, 13))
+        x0, y0 = rng.uniform(0, 800, n), rng.uniform(0, 800, n)
+        w, h = rng.uniform(40, 220, n), rng.uniform(20, 220, n)
+        targets.append({"boxes": torch.tensor(np.stack([x0, y0, x0 + w, y0 + h], 1), dtype=torch.float32, device=dev),
+                        "labels": torch.tensor(rng.integers(1, 6, n), dtype=torch.int64, device=dev)})
+
+    def detector(backbone):
+        roi = MultiScaleRoIAlign(featmap_names=["p2", "p3", "p4", "p5", "pool"], output_size=7, sampling_ratio=2)
+        anchors = AnchorGenerator(sizes=((32,), (64,), (128,), (256,), (512,)), aspect_ratios=((0.5, 1.0, 2.0),) * 5)
+        return FasterRCNN(backbone, num_classes=5 + 1, rpn_anchor_generator=anchors, box_roi_pool=roi, max_size=224, min_size=224,
+                          fixed_size=(224, 224), image_mean=(0.5, 0.5, 0.5), image_std=(0.5, 0.5, 0.5)).to(dev).train()
+
+    def timed(step):
+        for _ in range(args.warmup):
+            step()
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize(dev)
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(args.steps):
+            step()
+        e1.record()
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize(dev)
+        ms = torch.tensor([e0.elapsed_time(e1)], dtype=torch.float64, device=dev)
+        if world > 1:
+            dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+        return float(ms.item()) / args.steps
+
+    ours_bb = TrainableDiTWithFPN(cfg)
+    ours_bb.backbone.dit.load_state_dict(sd, strict=False)
+    ours_bb.fpn.load_state_dict(fsd, strict=True)
+    det = detector(ours_bb)
+    params = [p for n, p in det.named_parameters() if p.requires_grad and ".pooler." not in n]
+    opt = torch.optim.AdamW(params, lr=1e-5, fused=True)
+    buckets = GradientBuckets(params)
+
+    def ours():
+        opt.zero_grad(set_to_none=True)
+        with torch.autocast("cuda", dtype=torch.bfloat16):
+            losses = det(pages, targets)
+        sum(losses.values()).backward()
+        buckets.all_reduce()
+        opt.step()
+    ms_ours = timed(ours)
+    del det, opt, buckets, ours_bb, params
+    torch.cuda.empty_cache()
+
+    from oracle import hf_reference   # comparator only
+
+    class RefBackbone(torch.nn.Module):   # R:dit_backbone.py:65-95 with the hub fetch replaced
+        def __init__(self):
+            super().__init__()
+            self.backbone = hf_reference.build(cfg.to_dict(), sd)
+            self.fpn = FeaturePyramidNetwork([cfg.hidden_size] * 4, 256, extra_blocks=LastLevelMaxPool())
+            self.fpn.load_state_dict(fsd, strict=True)
+            self.out_channels = 256
+
+        def forward(self, x):
+            return self.fpn(self.backbone(x))
+    ref = detector(RefBackbone())
+    ref.backbone.backbone.eval()          # drop-path off in the HF backbone: the same arithmetic as ours
+    rparams = [p for n, p in ref.named_parameters() if p.requires_grad and "pooler" not in n]
+    wrapped = torch.nn.parallel.DistributedDataParallel(ref, device_ids=[dev.index], find_unused_parameters=True) if world > 1 else ref
+    ropt = torch.optim.AdamW(rparams, lr=1e-5, fused=True)
+
+    def theirs():
+        ropt.zero_grad(set_to_none=True)
+        with torch.autocast("cuda", dtype=torch.bfloat16):
+            losses = wrapped(pages, targets)
+        sum(losses.values()).backward()
+        ropt.step()
+    ms_hf = timed(theirs)
+    value = world * B / (ms_ours / 1e3)
+    if rank == 0:
+        print(json.dumps({
+            "metric": "LayoutDiT detector training step throughput", "value": round(value, 1), "unit": "images/s", "n_gpus": world,
+            "steps": args.steps, "warmup": args.warmup, "ms_per_step": round(ms_ours, 3), "higher_is_better": True,
+            "scaling": "weak", "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
+            "config": {"workload": f"BASELINE config 5: FasterRCNN(R:model.py:33-56) around {fac} + FPN, {B} synthetic 1024x1024 pages per GPU "
+                                   "(resized to 224x224 by the detector's transform), 1-12 boxes per page, 5 classes; forward + losses + backward + "
+                                   "gradient all-reduce + fused AdamW; backbone = layoutdit_b200.train (hand-written backward), FPN / RPN / RoI "
+                                   "heads / losses = torchvision under autocast bf16",
+                       "global_batch": world * B, "parallelism": f"dp{world}",
+                       "timing": "stream launches, CUDA events around all steps, max over ranks"},
+            "gpu_library_baseline": {"value": round(world * B / (ms_hf / 1e3), 1), "unit": "images/s", "ms_per_step": round(ms_hf, 3),
+                                     "ours_over_library": round(ms_hf / ms_ours, 3),
+                                     "what": "the same detector around HF BeitModel (R:dit_backbone.py:38-62), torch autocast bf16 + autograd"
+                                             + (" + DistributedDataParallel" if world > 1 else "")},
+        }), file=_RESULT, flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
 _RESULT = sys.stdout   # where the ONE JSON line goes; main() re-points it at the real stdout
 
 
@@ -670,7 +786,7 @@ def main():
     ap.add_argument("--head", default="taps", choices=["taps", "fpn"],
                     help="taps (default, BASELINE.json's metric): DiTBackbone, four D-channel taps; fpn: DiTWithFPN "
                          "(SURVEY 8 row f1: laterals, top-down merges, 3x3 convolutions, pool) -- device-resident value only")
-    ap.add_argument("--mode", default="forward", choices=["forward", "train"],
+    ap.add_argument("--mode", default="forward", choices=["forward", "train", "train-detector"],
                     help="forward (default, BASELINE.json's metric) or train: one data-parallel training step of the backbone "
                          "(SURVEY 8 row f2) against HF autocast training on the same GPU")
     ap.add_argument("--no-graph", dest="graph", action="store_false",
@@ -705,6 +821,9 @@ def main():
         return
     if args.mode == "train":
         run_train_line(args, cfg, fac, B, H, W, dev, rank, world, peaks)
+        return
+    if args.mode == "train-detector":
+        run_detector_train_line(args, cfg, fac, dev, rank, world, peaks)
         return
 
     def barrier():

@@ -424,6 +424,34 @@ class TrainableBackbone(nn.Module):
         return OrderedDict((f"p{j + 2}", taps[j]) for j in range(4))
 
 
+class TrainableDiTWithFPN(nn.Module):
+    """The training-time counterpart of ``DiTWithFPN`` (R:dit_backbone.py:65-95): ``.backbone`` is the differentiable
+    ``TrainableBackbone`` over a ``DiTParameters`` tree exposed as ``.backbone.dit`` (the attribute the reference loads
+    checkpoints into, R:model.py:70), ``.fpn`` is torchvision's own ``FeaturePyramidNetwork`` + ``LastLevelMaxPool`` under
+    torch autograd (the library's FPN kernels are inference-only so far), ``out_channels = 256``.  It is what
+    ``FasterRCNN(backbone=...)`` takes in ``R:model.py:33-56`` when the detector is trained."""
+
+    class _Backbone(nn.Module):
+        def __init__(self, cfg, drop_path_rate):
+            super().__init__()
+            self.dit = DiTParameters(cfg)
+            self.net = TrainableBackbone(self.dit, cfg, drop_path_rate)
+
+        def forward(self, x):
+            return self.net(x)
+
+    def __init__(self, cfg: DiTConfig, out_channels: int = 256, drop_path_rate: float = 0.0):
+        super().__init__()
+        from torchvision.ops import FeaturePyramidNetwork
+        from torchvision.ops.feature_pyramid_network import LastLevelMaxPool
+        self.backbone = self._Backbone(cfg, drop_path_rate)
+        self.fpn = FeaturePyramidNetwork([cfg.hidden_size] * 4, out_channels, extra_blocks=LastLevelMaxPool())
+        self.out_channels = out_channels
+
+    def forward(self, x):
+        return self.fpn(self.backbone(x))
+
+
 # ----------------------------------------------------------------------------------- data-parallel gradients
 class GradientBuckets:
     """Bucketed gradient all-reduce of a data-parallel step (BASELINE config 5): parameters are packed, in reverse
