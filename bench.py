@@ -274,7 +274,8 @@ def run_train_line(args, cfg, fac, B, H, W, dev, rank, world, peaks):
     model = TrainableBackbone(tree, cfg)
     trainable = [p for n, p in tree.named_parameters() if not n.startswith("pooler")]
     opt = torch.optim.AdamW(trainable, lr=1e-5, fused=True)
-    buckets = GradientBuckets(trainable)
+    overlap = os.environ.get("LDIT_TRAIN_OVERLAP", "1") != "0"      # buckets go out from autograd hooks, under the rest of the backward
+    buckets = GradientBuckets(trainable, overlap=overlap)
 
     def ours():
         opt.zero_grad(set_to_none=True)
@@ -309,6 +310,8 @@ def run_train_line(args, cfg, fac, B, H, W, dev, rank, world, peaks):
                                    f"gradient all-reduce + fused AdamW, batch {B} per GPU, {H}x{W}, random-init weights; no detection head "
                                    f"(BASELINE config 5 is backbone + head at 1024x1024: the attention backward covers <= 256 tokens)",
                        "global_batch": world * B, "parallelism": f"dp{world}",
+                       "gradient_all_reduce": ("bucketed NCCL all-reduce launched from autograd hooks, under the backward" if overlap
+                                               else "bucketed NCCL all-reduce after the backward") if world > 1 else "none",
                        "timing": "stream launches (no CUDA graph), CUDA events around all steps, max over ranks, no L2 flush"},
             "model_tflops": round(fl * value / 1e12, 1), "model_frac_of_peak": round(fl * value / 1e12 / (world * peaks["bf16_tflops"]), 4),
             "gpu_library_baseline": {"value": round(world * B / (ms_hf / 1e3), 1), "unit": "images/s", "ms_per_step": round(ms_hf, 3),

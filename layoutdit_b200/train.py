@@ -460,7 +460,10 @@ class GradientBuckets:
     GPUs, gloo in the CPU tests), divides by the world size and scatters the averages back into ``.grad``.
     Parameters without a gradient contribute zeros (every rank must reduce the same buckets)."""
 
-    def __init__(self, params, bucket_bytes: int = 25 << 20, group=None):
+    def __init__(self, params, bucket_bytes: int = 25 << 20, group=None, overlap: bool = False):
+        """``overlap=True``: every parameter gets a post-accumulate-grad hook and a bucket's all-reduce is launched the
+        moment its last gradient of the step has been written, i.e. under the rest of the backward (what DDP does);
+        ``all_reduce()`` then launches whatever is left, waits and scatters the averages back."""
         self.params = [p for p in params if p.requires_grad][::-1]
         self.group = group
         self.buckets, cur, size = [], [], 0
@@ -472,28 +475,49 @@ class GradientBuckets:
         if cur:
             self.buckets.append(cur)
         self._flat = [None] * len(self.buckets)
+        self._works = [None] * len(self.buckets)
+        self._pending = [len(b) for b in self.buckets]
+        self._bucket_of = {id(p): i for i, b in enumerate(self.buckets) for p in b}
+        self._hooks = []
+        if overlap:
+            for p in self.params:
+                self._hooks.append(p.register_post_accumulate_grad_hook(self._on_grad))
+
+    def _active(self):
+        return dist.is_initialized() and dist.get_world_size(self.group) > 1
+
+    def _on_grad(self, p):
+        i = self._bucket_of[id(p)]
+        self._pending[i] -= 1
+        if self._pending[i] == 0 and self._active():
+            self._launch(i)
+
+    def _launch(self, i):
+        bucket = self.buckets[i]
+        dev = bucket[0].device
+        n = sum(p.numel() for p in bucket)
+        if self._flat[i] is None or self._flat[i].device != dev:
+            self._flat[i] = torch.empty(n, device=dev, dtype=torch.float32)
+        flat, off = self._flat[i], 0
+        for p in bucket:
+            seg = flat[off: off + p.numel()]
+            if p.grad is None:
+                seg.zero_()
+            else:
+                seg.copy_(p.grad.detach().reshape(-1))
+            off += p.numel()
+        self._works[i] = dist.all_reduce(flat, op=dist.ReduceOp.SUM, group=self.group, async_op=True)
 
     def all_reduce(self):
-        if not dist.is_initialized() or dist.get_world_size(self.group) == 1:
+        if not self._active():
+            self._pending = [len(b) for b in self.buckets]
             return
         world = dist.get_world_size(self.group)
-        works = []
+        for i in range(len(self.buckets)):
+            if self._works[i] is None:          # not launched by a hook (no overlap, or a parameter without a gradient this step)
+                self._launch(i)
         for i, bucket in enumerate(self.buckets):
-            dev = bucket[0].device
-            n = sum(p.numel() for p in bucket)
-            if self._flat[i] is None or self._flat[i].device != dev:
-                self._flat[i] = torch.empty(n, device=dev, dtype=torch.float32)
-            flat, off = self._flat[i], 0
-            for p in bucket:
-                seg = flat[off: off + p.numel()]
-                if p.grad is None:
-                    seg.zero_()
-                else:
-                    seg.copy_(p.grad.detach().reshape(-1))
-                off += p.numel()
-            works.append(dist.all_reduce(flat, op=dist.ReduceOp.SUM, group=self.group, async_op=True))
-        for i, (bucket, work) in enumerate(zip(self.buckets, works)):
-            work.wait()
+            self._works[i].wait()
             flat, off = self._flat[i], 0
             flat.div_(world)
             for p in bucket:
@@ -503,3 +527,5 @@ class GradientBuckets:
                 else:
                     p.grad.copy_(seg)
                 off += p.numel()
+            self._works[i] = None
+        self._pending = [len(b) for b in self.buckets]

@@ -151,3 +151,41 @@ def test_peer_gather_matches_nccl_on_two_gpus():
     for p in procs:
         p.join(timeout=60)
     assert res == [(0, True), (1, True)]
+
+
+def _ddp_overlap_worker(rank, world, port, out):
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        from layoutdit_b200.train import GradientBuckets
+        torch.manual_seed(0)
+        model = torch.nn.Sequential(torch.nn.Linear(16, 32), torch.nn.ReLU(), torch.nn.Linear(32, 8), torch.nn.Linear(8, 4))
+        buckets = GradientBuckets(model.parameters(), bucket_bytes=1024, overlap=True)   # hooks launch the buckets during backward
+        g = torch.Generator().manual_seed(100)
+        xs, ys = torch.randn(8, 16, generator=g), torch.randn(8, 4, generator=g)
+        sl = rank_slice(8, rank, world)
+        for step in range(2):                                          # the second step checks that the counters re-arm
+            model.zero_grad(set_to_none=True)
+            (((model(xs[sl]) - ys[sl]) ** 2).sum() / 8).backward()
+            launched = sum(w is not None for w in buckets._works)
+            buckets.all_reduce()
+        out[rank] = ({n: p.grad.clone() for n, p in model.named_parameters()}, launched, len(buckets.buckets))
+    finally:
+        dist.destroy_process_group()
+
+
+def test_bucketed_gradient_all_reduce_overlapped_with_backward_world2():
+    world = 2
+    mgr = mp.Manager()
+    out = mgr.dict()
+    mp.spawn(_ddp_overlap_worker, args=(world, _free_port(), out), nprocs=world, join=True)
+    torch.manual_seed(0)
+    model = torch.nn.Sequential(torch.nn.Linear(16, 32), torch.nn.ReLU(), torch.nn.Linear(32, 8), torch.nn.Linear(8, 4))
+    g = torch.Generator().manual_seed(100)
+    xs, ys = torch.randn(8, 16, generator=g), torch.randn(8, 4, generator=g)
+    (((model(xs) - ys) ** 2).sum() / 8 / world).backward()             # mean over ranks of the per-rank gradients
+    for r in range(world):
+        grads, launched, nb = out[r]
+        assert launched == nb                                          # every bucket went out from a hook, before all_reduce()
+        for n, p in model.named_parameters():
+            torch.testing.assert_close(grads[n], p.grad, rtol=1e-5, atol=1e-6)
