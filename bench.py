@@ -274,7 +274,7 @@ def run_train_line(args, cfg, fac, B, H, W, dev, rank, world, peaks):
     model = TrainableBackbone(tree, cfg)
     trainable = [p for n, p in tree.named_parameters() if not n.startswith("pooler")]
     opt = torch.optim.AdamW(trainable, lr=1e-5, fused=True)
-    overlap = os.environ.get("LDIT_TRAIN_OVERLAP", "1") != "0"      # buckets go out from autograd hooks, under the rest of the backward
+    overlap = os.environ.get("LDIT_TRAIN_OVERLAP", "0") == "1"      # 1: buckets go out from autograd hooks, under the rest of the backward (measured neutral)
     buckets = GradientBuckets(trainable, overlap=overlap)
 
     def ours():
