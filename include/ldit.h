@@ -222,12 +222,14 @@ int ldit_attention_bwd(const void* qkv, const void* dctx, void* dqkv, int B, int
  * what ldit_attention_bwd_flash needs to recompute P. */
 int ldit_attention_lse(const void* qkv, void* ctx, const void* bias_table, void* lse, int B, int N, int heads, int Gh, int Gw,
                        void* stream);
-/* Backward of ldit_attention for ANY sequence length (no relative-position bias): flash-style, one CTA per (image, head,
+/* Backward of ldit_attention for ANY sequence length, optionally with the relative-position table the forward used
+ * (bias_table f32 [heads, T] as for ldit_attention; dbias f32 [heads, T] += its gradient, HF:522-544 index rule; both NULL
+ * without a table): flash-style, one CTA per (image, head,
  * 128-key tile) with dV / dK in TMEM, walking the query tiles; P recomputed from `lse` (ldit_attention_lse), delta from
  * ctx (the forward's output) and dctx; dQ contributions are fp32 vector reductions into the workspace dq_acc
  * f32 [B*N, D] (zeroed here; summation order not fixed), cast into dqkv at the end.  delta: workspace f32 [B*heads*N]. */
 int ldit_attention_bwd_flash(const void* qkv, const void* ctx, const void* lse, const void* dctx, void* dqkv, void* dq_acc, void* delta,
-                             int B, int N, int heads, void* stream);
+                             const void* bias_table, void* dbias, int B, int N, int heads, int Gh, int Gw, void* stream);
 /* Adjoint of ldit_resample_taps (R:dit_backbone.py:50-61 under autograd): dout bf16 [B, floor(Gh*scale), floor(Gw*scale), D]
  * channels-last -> dx f32 [B, Gh*Gw + 1, D], rows 1..P written (the CLS row is left as it is: zero it first). */
 int ldit_resample_taps_bwd(const void* dout, void* dx, int B, int Gh, int Gw, int D, float scale, void* stream);

@@ -35,7 +35,7 @@ SIGNATURES = {
     "ldit_gemm_dgrad": (_i, [_vp, _vp, _vp, _i, _i, _i, _vp]),
     "ldit_attention_bwd": (_i, [_vp, _vp, _vp, _i, _i, _i, _vp]),
     "ldit_attention_lse": (_i, [_vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _vp]),
-    "ldit_attention_bwd_flash": (_i, [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _i, _i, _i, _vp]),
+    "ldit_attention_bwd_flash": (_i, [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _vp]),
     "ldit_resample_taps_bwd": (_i, [_vp, _vp, _i, _i, _i, _i, _f, _vp]),
     "ldit_batch_sum": (_i, [_vp, _vp, _i, _i, _vp]),
     "ldit_mlp_clusters": (_i, []),

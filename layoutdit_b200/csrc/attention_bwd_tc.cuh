@@ -300,6 +300,10 @@ struct AttnBwdFlashArgs {
   __nv_bfloat16* dqkv;
   int B, N, heads, D, nqt;
   float scale_log2e, scale;
+  // relative-position bias (HAS_BIAS): table [heads, T] in natural units as the forward takes it, its gradient (+=)
+  const float* bias_table;
+  float* dbias;
+  int Gh, Gw, T;
 };
 constexpr int kAbfSmemTiles = 12 * kAbtTile;   // K, V, Q[2], dO[2], P^T (2 atoms), dS^T (2), dS (2)
 
@@ -346,6 +350,7 @@ dq_cast_kernel(const float* __restrict__ dq_acc, __nv_bfloat16* __restrict__ dqk
   *reinterpret_cast<uint4*>(dqkv + r * 3 * D + c) = o;
 }
 
+template <bool HAS_BIAS>
 __global__ void __launch_bounds__(kAbtThreads, 1)
 attention_bwd_flash_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_constant__ CUtensorMap tmDO, const AttnBwdFlashArgs a) {
   extern __shared__ uint8_t smem_raw[];
@@ -362,6 +367,10 @@ attention_bwd_flash_kernel(const __grid_constant__ CUtensorMap tmQKV, const __gr
   uint64_t* bar_q = bars + 1;               // [slot]
   uint64_t* bar_mma = bars + 3;
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 4);
+  // HAS_BIAS: the head's table (x log2 e), its gradient accumulator, the column terms of this CTA's 128 keys (HF:522-544)
+  float* sTab = reinterpret_cast<float*>(bars + 6);
+  float* sGrad = sTab + (HAS_BIAS ? a.T : 0);
+  int* sColK = reinterpret_cast<int*>(sGrad + (HAS_BIAS ? a.T : 0));
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int quarter = warp & 3, half = warp >> 2;
@@ -400,6 +409,15 @@ attention_bwd_flash_kernel(const __grid_constant__ CUtensorMap tmQKV, const __gr
     tma_load_3d(sV, &tmQKV, bar_kv, 2 * a.D + h * 64, kh * 128, b);
     load_q(0, 0);
   }
+  if constexpr (HAS_BIAS) {
+    const float* tab = a.bias_table + static_cast<size_t>(h) * a.T;
+    for (int i = threadIdx.x; i < a.T; i += kAbtThreads) { sTab[i] = tab[i] * 1.4426950408889634f; sGrad[i] = 0.f; }
+    if (threadIdx.x < 128) {
+      const int key = kh * 128 + threadIdx.x, p = key - 1;
+      sColK[threadIdx.x] = (key == 0 || key >= a.N) ? 0 : (p / a.Gw) * (2 * a.Gw - 1) + (p % a.Gw);
+    }
+    __syncthreads();
+  }
   mbar_wait(bar_kv, 0);
 
   constexpr uint32_t idesc_s = umma_idesc_bf16(128, 128, 0, 0);
@@ -433,6 +451,10 @@ attention_bwd_flash_kernel(const __grid_constant__ CUtensorMap tmQKV, const __gr
     const int qrow = t * 128 + row;
     const float ls = qrow < a.N ? __ldg(lse + qrow) : 0.f;     // padding rows: Q = dO = 0, any finite statistic does
     const float dl = qrow < a.N ? __ldg(dlt + qrow) : 0.f;
+    int rowterm = 0;
+    if constexpr (HAS_BIAS) {
+      if (qrow >= 1 && qrow < a.N) { const int pp = qrow - 1; rowterm = (pp / a.Gw + a.Gh - 1) * (2 * a.Gw - 1) + (pp % a.Gw) + a.Gw - 1; }
+    }
     wait_mma();
     for (int c = half; c < 8; c += 2) {
       uint32_t r[16], q[16];
@@ -447,9 +469,19 @@ attention_bwd_flash_kernel(const __grid_constant__ CUtensorMap tmQKV, const __gr
 #pragma unroll
         for (int e = 0; e < 2; ++e) {
           const int key = kh * 128 + c * 16 + i + e;
-          p[e] = (key < a.N) ? abt_ex2(__uint_as_float(r[i + e]) * a.scale_log2e - ls) : 0.f;
-          ds[e] = p[e] * (__uint_as_float(q[i + e]) - dl) * a.scale;
           const int kl = c * 16 + i + e;
+          float logit = __uint_as_float(r[i + e]) * a.scale_log2e;
+          int idx = 0;
+          if constexpr (HAS_BIAS) {     // the index rule of HF:522-544: CLS row / column entries T-3, T-2, T-1
+            idx = (qrow == 0 || qrow >= a.N) ? (key == 0 ? a.T - 1 : a.T - 3) : (key == 0 ? a.T - 2 : rowterm - sColK[kl]);
+            logit += sTab[idx];
+          }
+          p[e] = (key < a.N) ? abt_ex2(logit - ls) : 0.f;
+          const float dsn = p[e] * (__uint_as_float(q[i + e]) - dl);     // d loss / d logit (natural units) = d loss / d bias
+          ds[e] = dsn * a.scale;
+          if constexpr (HAS_BIAS) {
+            if (key < a.N && qrow < a.N) atomicAdd(&sGrad[idx], dsn);
+          }
           const uint32_t off = static_cast<uint32_t>(row >> 6) * kAbtTile + abt_sw128(kl, row & 63);
           *reinterpret_cast<__nv_bfloat16*>(sPT + off) = __float2bfloat16_rn(p[e]);
           *reinterpret_cast<__nv_bfloat16*>(sDST + off) = __float2bfloat16_rn(ds[e]);
@@ -519,6 +551,13 @@ attention_bwd_flash_kernel(const __grid_constant__ CUtensorMap tmQKV, const __gr
   }
   tcgen05_fence_before();
   __syncthreads();
+  if constexpr (HAS_BIAS) {   // this CTA's share of the table gradient (every shared-memory atomic above is behind the barrier)
+    float* dst = a.dbias + static_cast<size_t>(h) * a.T;
+    for (int i = threadIdx.x; i < a.T; i += kAbtThreads) {
+      const float v = sGrad[i];
+      if (v != 0.f) atomicAdd(dst + i, v);
+    }
+  }
   if (warp == 1) tmem_dealloc(tmem_base, kAbtTmemCols);
 }
 

@@ -1352,9 +1352,12 @@ int ldit_attention_bwd(const void* qkv, const void* dctx, void* dqkv, int B, int
 }
 
 int ldit_attention_bwd_flash(const void* qkv, const void* ctx, const void* lse, const void* dctx, void* dqkv, void* dq_acc, void* delta,
-                             int B, int N, int heads, void* stream) {
+                             const void* bias_table, void* dbias, int B, int N, int heads, int Gh, int Gw, void* stream) {
   if (!qkv || !ctx || !lse || !dctx || !dqkv || !dq_acc || !delta) return LDIT_E_NULL;
   if (B <= 0 || heads <= 0 || N <= 0 || B * heads > 65535) return LDIT_E_SHAPE;
+  if ((bias_table != nullptr) != (dbias != nullptr)) return LDIT_E_NULL;
+  if (bias_table && (Gh <= 0 || Gw <= 0 || N != Gh * Gw + 1)) return LDIT_E_SHAPE;
+  if (!aligned16(bias_table) || !aligned16(dbias)) return LDIT_E_ALIGN;
   if (!aligned16(qkv) || !aligned16(ctx) || !aligned16(lse) || !aligned16(dctx) || !aligned16(dqkv) || !aligned16(dq_acc) || !aligned16(delta))
     return LDIT_E_ALIGN;
   cudaStream_t st = static_cast<cudaStream_t>(stream);
@@ -1380,10 +1383,21 @@ int ldit_attention_bwd_flash(const void* qkv, const void* ctx, const void* lse, 
   if (rc) return rc;
   rc = make_tmap_rows_3d(&tmDO, dctx, B, N, D, 128);
   if (rc) return rc;
-  const size_t smem = 1024 + kAbfSmemTiles + 64;
-  e = ensure_smem(attention_bwd_flash_kernel, smem, false);
-  if (e != cudaSuccess) return static_cast<int>(e);
-  attention_bwd_flash_kernel<<<dim3(a.nqt, B * heads), kAbtThreads, smem, st>>>(tmQKV, tmDO, a);
+  size_t smem = 1024 + kAbfSmemTiles + 64;
+  if (bias_table) {
+    a.bias_table = static_cast<const float*>(bias_table);
+    a.dbias = static_cast<float*>(dbias);
+    a.Gh = Gh; a.Gw = Gw; a.T = (2 * Gh - 1) * (2 * Gw - 1) + 3;
+    smem += (2 * static_cast<size_t>(a.T) + 128) * 4;
+    if (smem > 227 * 1024) return LDIT_E_SHAPE;
+    e = ensure_smem(attention_bwd_flash_kernel<true>, smem, false);
+    if (e != cudaSuccess) return static_cast<int>(e);
+    attention_bwd_flash_kernel<true><<<dim3(a.nqt, B * heads), kAbtThreads, smem, st>>>(tmQKV, tmDO, a);
+  } else {
+    e = ensure_smem(attention_bwd_flash_kernel<false>, smem, false);
+    if (e != cudaSuccess) return static_cast<int>(e);
+    attention_bwd_flash_kernel<false><<<dim3(a.nqt, B * heads), kAbtThreads, smem, st>>>(tmQKV, tmDO, a);
+  }
   rc = check_launch();
   if (rc) return rc;
   dq_cast_kernel<<<static_cast<unsigned>((rows * (D / 8) + 255) / 256), 256, 0, st>>>(static_cast<const float*>(dq_acc), static_cast<__nv_bfloat16*>(dqkv), rows, D);

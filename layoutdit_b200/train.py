@@ -6,8 +6,8 @@ What the reference does here: ``LayoutDetectionModel`` is trained with ``torch.a
 (HF:469-508) under autocast, ``scaler.scale(loss).backward()`` (R:src/layoutdit/training/trainer.py:164-183); it has no
 distributed code (R:README.md:59) -- BASELINE config 5 asks for DDP with an NCCL gradient all-reduce, which is new.
 
-Scope (the rest is listed in DESIGN.md "next"): absolute-position configurations (no relative-position
-bias: its table gradient is not written yet).  Drop-path (HF's training-mode stochastic depth, HF:61-73: a per-image
+Scope (the rest is listed in DESIGN.md "next"): every configuration the forward covers; relative-position tables
+(per layer or shared) train at their native window, through the flash-style attention backward.  Drop-path (HF's training-mode stochastic depth, HF:61-73: a per-image
 Bernoulli scaling of the two branches) is a constructor argument, active in ``train()`` mode.  The attention backward is a tcgen05 kernel: up to 256 tokens (224 x 224
 pages have 197) one self-contained CTA per (image, head); beyond that a flash-style kernel over key tiles that recomputes P
 from the row statistics the forward writes (``ldit_attention_lse``).  The eight GEMMs of a layer's backward run on the
@@ -89,21 +89,25 @@ class _K:
         _lib.check(self.lib.ldit_attention_bwd(qkv.data_ptr(), dctx.data_ptr(), dqkv.data_ptr(), B, N, heads, _st(self.dev)), "ldit_attention_bwd")
         return dqkv
 
-    def attention_lse(self, qkv, B, N, heads, Gh, Gw):
+    def attention_lse(self, qkv, B, N, heads, Gh, Gw, table=None):
+        """Forward attention that also returns the rows' log2-sum-exp; ``table``: f32 [heads, T] relative-position table or None."""
         D = heads * 64
         ctx = torch.empty(B * N, D, device=self.dev, dtype=_BF)
         lse = torch.empty(B, heads, N, device=self.dev, dtype=torch.float32)
-        _lib.check(self.lib.ldit_attention_lse(qkv.data_ptr(), ctx.data_ptr(), None, lse.data_ptr(), B, N, heads, Gh, Gw, _st(self.dev)), "ldit_attention_lse")
+        _lib.check(self.lib.ldit_attention_lse(qkv.data_ptr(), ctx.data_ptr(), _p(table), lse.data_ptr(), B, N, heads, Gh, Gw, _st(self.dev)),
+                   "ldit_attention_lse")
         return ctx, lse
 
-    def attention_bwd_flash(self, qkv, ctx, lse, dctx, B, N, heads):
-        """Any sequence length: key-tile CTAs, P recomputed from the forward's row statistics."""
+    def attention_bwd_flash(self, qkv, ctx, lse, dctx, B, N, heads, Gh, Gw, table=None, dtable=None):
+        """Any sequence length: key-tile CTAs, P recomputed from the forward's row statistics; with ``table`` also
+        ``dtable`` f32 [heads, T] += the table's gradient."""
         D = heads * 64
         dqkv = torch.empty_like(qkv)
         dq_acc = torch.empty(B * N, D, device=self.dev, dtype=torch.float32)
         delta = torch.empty(B * heads * N, device=self.dev, dtype=torch.float32)
         _lib.check(self.lib.ldit_attention_bwd_flash(qkv.data_ptr(), ctx.data_ptr(), lse.data_ptr(), dctx.data_ptr(), dqkv.data_ptr(),
-                                                     dq_acc.data_ptr(), delta.data_ptr(), B, N, heads, _st(self.dev)), "ldit_attention_bwd_flash")
+                                                     dq_acc.data_ptr(), delta.data_ptr(), _p(table), _p(dtable), B, N, heads, Gh, Gw,
+                                                     _st(self.dev)), "ldit_attention_bwd_flash")
         return dqkv
 
     def transpose(self, t):
@@ -150,11 +154,20 @@ class _K:
 
 
 # order of the parameter tensors handed to BeitLayerFunction (lambda_1 / lambda_2 may be None)
-PARAM_NAMES = ("ln1_w", "ln1_b", "wq", "bq", "wk", "wv", "bv", "wo", "bo", "lam1", "ln2_w", "ln2_b", "w1", "b1", "w2", "b2", "lam2")
+PARAM_NAMES = ("ln1_w", "ln1_b", "wq", "bq", "wk", "wv", "bv", "wo", "bo", "lam1", "ln2_w", "ln2_b", "w1", "b1", "w2", "b2", "lam2",
+               "rel_table")     # relative_position_bias_table [T, heads] (the layer's own or the shared one) or None
 
 
-def layer_params(layer) -> tuple:
-    """The 17 tensors of a ``dit_params._Layer`` (HF names) in ``PARAM_NAMES`` order."""
+def layer_params(layer, shared_table=None) -> tuple:
+    """The tensors of a ``dit_params._Layer`` (HF names) in ``PARAM_NAMES`` order; ``shared_table``: the encoder's shared
+    relative-position table when the configuration has one (HF:598-600)."""
+    at = layer.attention.attention
+    own = getattr(at, "relative_position_bias", None)
+    table = own.relative_position_bias_table if own is not None else shared_table
+    return _layer_params17(layer) + (table,)
+
+
+def _layer_params17(layer) -> tuple:
     at = layer.attention.attention
     return (layer.layernorm_before.weight, layer.layernorm_before.bias, at.query.weight, at.query.bias, at.key.weight, at.value.weight,
             at.value.bias, layer.attention.output.dense.weight, layer.attention.output.dense.bias, layer.lambda_1,
@@ -188,8 +201,15 @@ class BeitLayerFunction(torch.autograd.Function):
         lam1, lam2 = f32(p["lam1"]), f32(p["lam2"])
         a1 = k.layernorm(x, f32(p["ln1_w"]), f32(p["ln1_b"]), eps)
         qkv = k.gemm(a1, wqkv, bqkv)
-        if N > 256:     # the self-contained backward kernel covers two 128-row tiles; beyond that keep the row statistics
-            att, lse = k.attention_lse(qkv, B, N, heads, Gh, Gw)
+        table = None
+        if p["rel_table"] is not None:
+            T = (2 * Gh - 1) * (2 * Gw - 1) + 3
+            if p["rel_table"].shape[0] != T:
+                raise NotImplementedError("training with a relative-position table runs at the table's native window "
+                                          "(the bilinear window resize, HF:556-571, has no backward yet)")
+            table = p["rel_table"].detach().to(dev, torch.float32).t().contiguous()     # [heads, T] as the kernels take it
+        if N > 256 or table is not None:     # the self-contained backward kernel covers two 128-row tiles without a table;
+            att, lse = k.attention_lse(qkv, B, N, heads, Gh, Gw, table)                 # otherwise keep the row statistics
         else:
             att, lse = k.attention(qkv, B, N, heads, Gh, Gw), x.new_empty(0)
         br1 = k.gemm(att, wo, f32(p["bo"]))
@@ -202,6 +222,7 @@ class BeitLayerFunction(torch.autograd.Function):
         ctx.geom = geom
         ctx.has_lam = (p["lam1"] is not None, p["lam2"] is not None)
         ctx.drop = drop
+        ctx.table = table
         ctx.save_for_backward(lse, x, xm, a1, qkv, att, br1, a2, pre, h, br2, wqkv, wo, w1, w2,
                               f32(p["ln1_w"]), f32(p["ln2_w"]), lam1 if lam1 is not None else x.new_empty(0),
                               lam2 if lam2 is not None else x.new_empty(0))
@@ -240,7 +261,15 @@ class BeitLayerFunction(torch.autograd.Function):
         dbo = z(D); k.colsum(g1, dbo)
         dwo = z(D, D); k.wgrad(g1, att, dwo)
         datt = k.dgrad(g1, wo)
-        dqkv = k.attention_bwd(qkv, datt, B, N, heads) if N <= 256 else k.attention_bwd_flash(qkv, att, lse, datt, B, N, heads)
+        dtable = None
+        if ctx.table is not None:
+            dtab = torch.zeros_like(ctx.table)
+            dqkv = k.attention_bwd_flash(qkv, att, lse, datt, B, N, heads, Gh, Gw, ctx.table, dtab)
+            dtable = dtab.t()                                              # back to HF's [T, heads]
+        elif N <= 256:
+            dqkv = k.attention_bwd(qkv, datt, B, N, heads)
+        else:
+            dqkv = k.attention_bwd_flash(qkv, att, lse, datt, B, N, heads, Gh, Gw)
         dbqkv = z(3 * D); k.colsum(dqkv, dbqkv)
         dwqkv = z(3 * D, D); k.wgrad(dqkv, a1, dwqkv)
         da1 = k.dgrad(dqkv, wqkv)
@@ -248,7 +277,7 @@ class BeitLayerFunction(torch.autograd.Function):
         dx = k.layernorm_bwd(x, g1w, da1, dxm, dg1, dbt1, eps)
 
         grads = dict(ln1_w=dg1, ln1_b=dbt1, wq=dwqkv[:D], bq=dbqkv[:D], wk=dwqkv[D:2 * D], wv=dwqkv[2 * D:], bv=dbqkv[2 * D:],
-                     wo=dwo, bo=dbo, lam1=dlam1, ln2_w=dg2, ln2_b=dbt2, w1=dw1, b1=db1, w2=dw2, b2=db2, lam2=dlam2)
+                     wo=dwo, bo=dbo, lam1=dlam1, ln2_w=dg2, ln2_b=dbt2, w1=dw1, b1=db1, w2=dw2, b2=db2, lam2=dlam2, rel_table=dtable)
         return (dx, None, None) + tuple(grads[n] for n in PARAM_NAMES)
 
 
@@ -258,14 +287,17 @@ class TrainableEncoder(nn.Module):
 
     def __init__(self, params: DiTParameters, cfg: DiTConfig, drop_path_rate: float = 0.0):
         super().__init__()
-        if cfg.use_relative_position_bias or cfg.use_shared_relative_position_bias:
-            raise NotImplementedError("the backward slice covers absolute-position configurations (no relative-position bias yet)")
         if not 0.0 <= drop_path_rate < 1.0:
             raise ValueError("drop_path_rate must be in [0, 1)")
         self.params_tree, self.cfg = params, cfg
         # stochastic depth as HF builds it: rate i of L grows linearly from 0 to drop_path_rate (HF:602-604), active in train()
         L = cfg.num_hidden_layers
         self.drop_rates = [drop_path_rate * i / max(L - 1, 1) for i in range(L)]
+
+    def shared_table(self):
+        """The encoder-level relative-position table (HF:598-600) or None."""
+        rp = getattr(self.params_tree.encoder, "relative_position_bias", None)
+        return None if rp is None else rp.relative_position_bias_table
 
     def drop_factors(self, i: int, B: int, device):
         """f32 [2, B] drop-path factors of layer i for this step (HF:61-73: floor(keep + U[0,1)) / keep), or None."""
@@ -284,7 +316,7 @@ class TrainableEncoder(nn.Module):
         geom = (B, N, self.cfg.num_attention_heads, Gh, Gw, float(self.cfg.layer_norm_eps))
         x = hidden.reshape(B * N, D).float()
         for i, layer in enumerate(self.params_tree.encoder.layer):
-            x = BeitLayerFunction.apply(x, geom, self.drop_factors(i, B, x.device), *layer_params(layer))
+            x = BeitLayerFunction.apply(x, geom, self.drop_factors(i, B, x.device), *layer_params(layer, self.shared_table()))
         return x.reshape(B, N, D)
 
 
@@ -417,7 +449,7 @@ class TrainableBackbone(nn.Module):
         geom = (B, Gh * Gw + 1, cfg.num_attention_heads, Gh, Gw, float(cfg.layer_norm_eps))
         taps = {}
         for i, layer in enumerate(self.params_tree.encoder.layer, start=1):
-            x = BeitLayerFunction.apply(x, geom, self.encoder.drop_factors(i - 1, B, x.device), *layer_params(layer))
+            x = BeitLayerFunction.apply(x, geom, self.encoder.drop_factors(i - 1, B, x.device), *layer_params(layer, self.encoder.shared_table()))
             for j, idx in enumerate(self.layer_idxs):          # shallow models tap one layer more than once
                 if idx == i:
                     taps[j] = TapFunction.apply(x, (B, Gh, Gw, D, self.SCALES[j]))

@@ -302,7 +302,7 @@ def test_attention_backward_any_length(lib, B, heads, Gh, Gw):
     dq_acc = torch.empty(B * N, D, device="cuda")
     delta = torch.empty(B * heads * N, device="cuda")
     _lib.check(lib.ldit_attention_bwd_flash(qkv.data_ptr(), ctx.data_ptr(), lse.data_ptr(), dctx.data_ptr(), dqkv.data_ptr(), dq_acc.data_ptr(),
-                                            delta.data_ptr(), B, N, heads, _st()), "attn_bwd_flash")
+                                            delta.data_ptr(), None, None, B, N, heads, Gh, Gw, _st()), "attn_bwd_flash")
     assert torch.isfinite(dqkv.float()).all()
     assert _rel(dqkv.float(), x.grad) < 8e-3
     if N <= 256:   # agrees with the self-contained two-tile kernel
@@ -346,3 +346,73 @@ def test_drop_path_scales_the_branches_per_image(cuda_device):
     enc.train()
     f = enc.drop_factors(3, 4096, "cuda")
     assert f.shape == (2, 4096) and bool(((f == 0) | ((f - 1.0 / 0.7).abs() < 1e-5)).all()) and 0.6 < (f > 0).float().mean() < 0.8
+
+
+@pytest.mark.parametrize("B,heads,Gh,Gw", [(2, 2, 4, 4), (1, 3, 14, 14), (1, 2, 20, 13)])
+def test_attention_backward_with_relative_position_table(lib, B, heads, Gh, Gw):
+    """Flash backward with the forward's relative-position table: dQKV and the table gradient (scatter of dS through the
+    HF:522-544 index rule) against fp64 autograd."""
+    N, D = Gh * Gw + 1, heads * 64
+    T = (2 * Gh - 1) * (2 * Gw - 1) + 3
+    g = torch.Generator(device="cuda").manual_seed(N + heads)
+    qkv = torch.randn(B * N, 3 * D, device="cuda", generator=g).to(torch.bfloat16)
+    dctx = torch.randn(B * N, D, device="cuda", generator=g).to(torch.bfloat16)
+    table = torch.randn(heads, T, device="cuda", generator=g)
+    ctx = torch.empty(B * N, D, device="cuda", dtype=torch.bfloat16)
+    lse = torch.empty(B, heads, N, device="cuda")
+    _lib.check(lib.ldit_attention_lse(qkv.data_ptr(), ctx.data_ptr(), table.data_ptr(), lse.data_ptr(), B, N, heads, Gh, Gw, _st()), "attn_lse")
+    dqkv = torch.full_like(qkv, float("nan"))
+    dtab = torch.zeros_like(table)
+    dq_acc, delta = torch.empty(B * N, D, device="cuda"), torch.empty(B * heads * N, device="cuda")
+    _lib.check(lib.ldit_attention_bwd_flash(qkv.data_ptr(), ctx.data_ptr(), lse.data_ptr(), dctx.data_ptr(), dqkv.data_ptr(), dq_acc.data_ptr(),
+                                            delta.data_ptr(), table.data_ptr(), dtab.data_ptr(), B, N, heads, Gh, Gw, _st()), "attn_bwd_flash")
+    x = qkv.double().requires_grad_(True)
+    t64 = table.double().requires_grad_(True)
+    idx = dit_oracle.relative_position_index(Gh, Gw).to("cuda")
+    bias = t64[:, idx.reshape(-1)].reshape(1, heads, N, N)
+    q, k, v = x.reshape(B, N, 3, heads, 64).permute(2, 0, 3, 1, 4)
+    s = q @ k.transpose(-1, -2) / 8.0 + bias
+    (torch.softmax(s, dim=-1) @ v).transpose(1, 2).reshape(B * N, D).backward(dctx.double())
+    assert torch.isfinite(dqkv.float()).all() and torch.isfinite(dtab).all()
+    assert _rel(dqkv.float(), x.grad) < 8e-3
+    assert _rel(dtab, t64.grad) < 8e-3
+
+
+@pytest.mark.parametrize("shared", [False, True])
+def test_encoder_gradients_with_relative_position_bias(cuda_device, shared):
+    """Two layers of a BEiT configuration with relative-position bias (per layer / shared): every gradient, the tables'
+    included, against the fp64 oracle's autograd."""
+    B, G = 2, 5
+    cfg = DiTConfig(hidden_size=128, num_hidden_layers=2, num_attention_heads=2, intermediate_size=256, image_size=G * 16,
+                    use_absolute_position_embeddings=False, use_relative_position_bias=not shared, use_shared_relative_position_bias=shared)
+    sd = make_state_dict(cfg, 83, True)
+    N, D = G * G + 1, cfg.hidden_size
+    gen = torch.Generator().manual_seed(11)
+    h0, wgt = torch.randn(B, N, D, generator=gen), torch.randn(B, N, D, generator=gen)
+    tree = DiTParameters(cfg)
+    tree.load_state_dict(sd)
+    tree = tree.cuda()
+    hin = h0.cuda().requires_grad_(True)
+    out = TrainableEncoder(tree, cfg)(hin, G, G)
+    (out * wgt.cuda()).sum().backward()
+    sd64 = {k: (v.double().requires_grad_(True) if v.is_floating_point() else v) for k, v in sd.items()}
+    cd = cfg.to_dict()
+    shared_bias = None
+    skey = "encoder.relative_position_bias.relative_position_bias_table"
+    if skey in sd64:
+        shared_bias = dit_oracle.relative_position_bias(sd64[skey], G, G, G)
+    x = h0.double().requires_grad_(True)
+    y = x
+    for i in range(2):
+        y = dit_oracle.beit_layer(sd64, cd, i, y, shared_bias, G, G)
+    (y * wgt.double()).sum().backward()
+    assert _rel(out.detach(), y.detach()) < 1e-2
+    assert _rel(hin.grad, x.grad) < GRAD_TOL
+    tables = 0
+    for name, p in tree.named_parameters():
+        if name.startswith("encoder.") and name in sd64 and sd64[name].grad is not None:
+            assert p.grad is not None, name
+            e = _rel(p.grad, sd64[name].grad)
+            assert e < GRAD_TOL, f"{name}: {e:.3e}"
+            tables += name.endswith("relative_position_bias_table")
+    assert tables == (1 if shared else 2)
