@@ -306,6 +306,10 @@ struct AttnBwdFlashArgs {
   int Gh, Gw, T;
 };
 constexpr int kAbfSmemTiles = 12 * kAbtTile;   // K, V, Q[2], dO[2], P^T (2 atoms), dS^T (2), dS (2)
+#ifndef LDIT_ABF_THREADS
+#define LDIT_ABF_THREADS 512
+#endif
+constexpr int kAbfThreads = LDIT_ABF_THREADS;   // 16 warps: the element-wise phase between the MMAs is what a block costs
 
 __device__ __forceinline__ void red_add_v4(float* addr, float a, float b, float c, float d) {
   asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(addr), "f"(a), "f"(b), "f"(c), "f"(d) : "memory");
@@ -351,7 +355,7 @@ dq_cast_kernel(const float* __restrict__ dq_acc, __nv_bfloat16* __restrict__ dqk
 }
 
 template <bool HAS_BIAS>
-__global__ void __launch_bounds__(kAbtThreads, 1)
+__global__ void __launch_bounds__(kAbfThreads, 1)
 attention_bwd_flash_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_constant__ CUtensorMap tmDO, const AttnBwdFlashArgs a) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
@@ -373,7 +377,7 @@ attention_bwd_flash_kernel(const __grid_constant__ CUtensorMap tmQKV, const __gr
   int* sColK = reinterpret_cast<int*>(sGrad + (HAS_BIAS ? a.T : 0));
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int quarter = warp & 3, half = warp >> 2;
+  const int quarter = warp & 3, half = warp >> 2;     // 16 warps: four per TMEM lane quarter, each takes every fourth 16-column chunk
   const int row = quarter * 32 + lane;
   const int kh = blockIdx.x;
   const int b = blockIdx.y / a.heads, h = blockIdx.y % a.heads;
@@ -411,7 +415,7 @@ attention_bwd_flash_kernel(const __grid_constant__ CUtensorMap tmQKV, const __gr
   }
   if constexpr (HAS_BIAS) {
     const float* tab = a.bias_table + static_cast<size_t>(h) * a.T;
-    for (int i = threadIdx.x; i < a.T; i += kAbtThreads) { sTab[i] = tab[i] * 1.4426950408889634f; sGrad[i] = 0.f; }
+    for (int i = threadIdx.x; i < a.T; i += kAbfThreads) { sTab[i] = tab[i] * 1.4426950408889634f; sGrad[i] = 0.f; }
     if (threadIdx.x < 128) {
       const int key = kh * 128 + threadIdx.x, p = key - 1;
       sColK[threadIdx.x] = (key == 0 || key >= a.N) ? 0 : (p / a.Gw) * (2 * a.Gw - 1) + (p % a.Gw);
@@ -456,7 +460,7 @@ attention_bwd_flash_kernel(const __grid_constant__ CUtensorMap tmQKV, const __gr
       if (qrow >= 1 && qrow < a.N) { const int pp = qrow - 1; rowterm = (pp / a.Gw + a.Gh - 1) * (2 * a.Gw - 1) + (pp % a.Gw) + a.Gw - 1; }
     }
     wait_mma();
-    for (int c = half; c < 8; c += 2) {
+    for (int c = half; c < 8; c += kAbfThreads / 128) {
       uint32_t r[16], q[16];
       tmem_ld_32x32b_x16(lane_addr + c * 16, r);
       tmem_ld_32x32b_x16(lane_addr + 128 + c * 16, q);
@@ -515,7 +519,7 @@ attention_bwd_flash_kernel(const __grid_constant__ CUtensorMap tmQKV, const __gr
     }
     wait_mma();
     // dQ block -> fp32 reductions into dq_acc (this warp's half of the 64 columns)
-    for (int c = half; c < 4; c += 2) {
+    for (int c = half; c < 4; c += kAbfThreads / 128) {
       uint32_t r[16];
       tmem_ld_32x32b_x16(lane_addr + 384 + c * 16, r);
       tmem_wait_ld16(r);
@@ -532,7 +536,7 @@ attention_bwd_flash_kernel(const __grid_constant__ CUtensorMap tmQKV, const __gr
   // dV, dK of this key tile: thread <-> key row (every MMA completed: the last wait above)
   {
     const int key = kh * 128 + row;
-    for (int c = half; c < 8; c += 2) {
+    for (int c = half; c < 8; c += kAbfThreads / 128) {
       uint32_t r[16];
       tmem_ld_32x32b_x16(lane_addr + 256 + c * 16, r);
       tmem_wait_ld16(r);
@@ -553,7 +557,7 @@ attention_bwd_flash_kernel(const __grid_constant__ CUtensorMap tmQKV, const __gr
   __syncthreads();
   if constexpr (HAS_BIAS) {   // this CTA's share of the table gradient (every shared-memory atomic above is behind the barrier)
     float* dst = a.dbias + static_cast<size_t>(h) * a.T;
-    for (int i = threadIdx.x; i < a.T; i += kAbtThreads) {
+    for (int i = threadIdx.x; i < a.T; i += kAbfThreads) {
       const float v = sGrad[i];
       if (v != 0.f) atomicAdd(dst + i, v);
     }

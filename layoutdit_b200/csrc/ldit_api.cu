@@ -1392,11 +1392,11 @@ int ldit_attention_bwd_flash(const void* qkv, const void* ctx, const void* lse, 
     if (smem > 227 * 1024) return LDIT_E_SHAPE;
     e = ensure_smem(attention_bwd_flash_kernel<true>, smem, false);
     if (e != cudaSuccess) return static_cast<int>(e);
-    attention_bwd_flash_kernel<true><<<dim3(a.nqt, B * heads), kAbtThreads, smem, st>>>(tmQKV, tmDO, a);
+    attention_bwd_flash_kernel<true><<<dim3(a.nqt, B * heads), kAbfThreads, smem, st>>>(tmQKV, tmDO, a);
   } else {
     e = ensure_smem(attention_bwd_flash_kernel<false>, smem, false);
     if (e != cudaSuccess) return static_cast<int>(e);
-    attention_bwd_flash_kernel<false><<<dim3(a.nqt, B * heads), kAbtThreads, smem, st>>>(tmQKV, tmDO, a);
+    attention_bwd_flash_kernel<false><<<dim3(a.nqt, B * heads), kAbfThreads, smem, st>>>(tmQKV, tmDO, a);
   }
   rc = check_launch();
   if (rc) return rc;

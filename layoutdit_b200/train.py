@@ -28,6 +28,9 @@ from .config import DiTConfig
 from .dit_params import DiTParameters
 
 _BF = torch.bfloat16
+# sequences longer than this take the flash-style attention backward (the self-contained kernel stops at 256 tokens);
+# LDIT_BWD_FLASH_ABOVE=0 sends every length through it (A/B knob)
+_FLASH_ABOVE = min(256, int(__import__("os").environ.get("LDIT_BWD_FLASH_ABOVE", "256")))
 
 
 def _st(dev):
@@ -208,7 +211,7 @@ class BeitLayerFunction(torch.autograd.Function):
                 raise NotImplementedError("training with a relative-position table runs at the table's native window "
                                           "(the bilinear window resize, HF:556-571, has no backward yet)")
             table = p["rel_table"].detach().to(dev, torch.float32).t().contiguous()     # [heads, T] as the kernels take it
-        if N > 256 or table is not None:     # the self-contained backward kernel covers two 128-row tiles without a table;
+        if N > _FLASH_ABOVE or table is not None:     # the self-contained backward kernel covers two 128-row tiles without a table;
             att, lse = k.attention_lse(qkv, B, N, heads, Gh, Gw, table)                 # otherwise keep the row statistics
         else:
             att, lse = k.attention(qkv, B, N, heads, Gh, Gw), x.new_empty(0)
@@ -266,7 +269,7 @@ class BeitLayerFunction(torch.autograd.Function):
             dtab = torch.zeros_like(ctx.table)
             dqkv = k.attention_bwd_flash(qkv, att, lse, datt, B, N, heads, Gh, Gw, ctx.table, dtab)
             dtable = dtab.t()                                              # back to HF's [T, heads]
-        elif N <= 256:
+        elif N <= _FLASH_ABOVE:
             dqkv = k.attention_bwd(qkv, datt, B, N, heads)
         else:
             dqkv = k.attention_bwd_flash(qkv, att, lse, datt, B, N, heads, Gh, Gw)
