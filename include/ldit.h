@@ -179,13 +179,13 @@ int ldit_subsample2_f32(const void* in, void* out, int B, int H, int W, int C, v
  * Equal sizes copy exactly.  Not part of the per-forward launch sequence. */
 int ldit_resize_rows(const void* src, void* dst, const void* add, int h, int w, int oh, int ow, int C, int bicubic, void* stream);
 
-/* ---- Backward of one BeitLayer (first vertical slice; host side: layoutdit_b200/train.py).
- * The reference trains through torch.autograd over HF BeitLayer (R:src/layoutdit/training/trainer.py:164-183, HF:469-508).
- * The eight GEMMs of a layer's backward run on the forward entry points: dgrad dA = dY W is ldit_gemm_bias(dY, W^T),
- * wgrad dW += dY^T A is ldit_gemm_bias_scale_residual(dY^T, A^T) accumulating into an fp32 dW; the rest is below.
- * bf16 activations / gradients, fp32 residual-stream gradients and parameter gradients (ACCUMULATED into, like .grad). */
-/* out bf16 [C, ld_out] (ld_out >= R) = in bf16 [R, C]^T  (operands of the wgrad GEMMs; pad ld_out to a multiple of 8
- * and zero the padding: a TMA operand's row pitch must be a multiple of 16 bytes) */
+/* ---- Backward of the backbone (host side: layoutdit_b200/train.py).
+ * The reference trains through torch.autograd over HF BeitModel (R:src/layoutdit/training/trainer.py:164-183, HF:469-508).
+ * The eight GEMMs of a layer's backward are ldit_gemm_dgrad (dA = dY W) and ldit_gemm_wgrad (dW += dY^T A) below: the
+ * forward's tcgen05 GEMM with MN-major operands, no transposed copies.  bf16 activations / gradients, fp32
+ * residual-stream gradients and parameter gradients (ACCUMULATED into, like .grad). */
+/* out bf16 [C, ld_out] (ld_out >= R) = in bf16 [R, C]^T  (utility: the first wgrad path used it; pad ld_out to a multiple
+ * of 8 and zero the padding: a TMA operand's row pitch must be a multiple of 16 bytes) */
 int ldit_transpose_bf16(const void* in, void* out, int R, int C, int ld_out, void* stream);
 /* out f32 [C] += column sums of in bf16 [R, ld] over columns [0, C)  (bias gradients; C, ld even) */
 int ldit_colsum_bf16(const void* in, void* out, int R, int C, int ld, void* stream);
