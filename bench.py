@@ -243,6 +243,7 @@ def run_train_line(args, cfg, fac, B, H, W, dev, rank, world, peaks):
     from layoutdit_b200.dit_params import DiTParameters
     from layoutdit_b200.synth import make_state_dict, synthetic_pages
     from layoutdit_b200.train import GradientBuckets, TrainableBackbone
+    from layoutdit_b200 import _lib as _lib_mod
     sd = make_state_dict(cfg, 0, False)
     pages = synthetic_pages(B, H, W, 1234 + rank).to(dev)
 
@@ -283,6 +284,10 @@ def run_train_line(args, cfg, fac, B, H, W, dev, rank, world, peaks):
         buckets.all_reduce()
         opt.step()
     ms_ours = timed(ours)
+    lib = _lib_mod.load()
+    lib.ldit_reset_launch_count()
+    ours()
+    launches = int(lib.ldit_launch_count())
     del model, opt, buckets, tree
     torch.cuda.empty_cache()
 
@@ -314,6 +319,7 @@ def run_train_line(args, cfg, fac, B, H, W, dev, rank, world, peaks):
                                                else "bucketed NCCL all-reduce after the backward") if world > 1 else "none",
                        "timing": "stream launches (no CUDA graph), CUDA events around all steps, max over ranks, no L2 flush"},
             "model_tflops": round(fl * value / 1e12, 1), "model_frac_of_peak": round(fl * value / 1e12 / (world * peaks["bf16_tflops"]), 4),
+            "gpu_launches": launches * args.steps, "launches_per_step": launches,
             "gpu_library_baseline": {"value": round(world * B / (ms_hf / 1e3), 1), "unit": "images/s", "ms_per_step": round(ms_hf, 3),
                                      "ours_over_library": round(ms_hf / ms_ours, 3),
                                      "what": "HF BeitModel wrapped as R:dit_backbone.py:38-62, torch autocast bf16 + autograd"
