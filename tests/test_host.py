@@ -213,3 +213,28 @@ def test_argument_validation_of_the_widened_entry_points_without_gpu():
     up = lambda v: (v + 1023) // 1024 * 1024
     assert lib.ldit_workspace_bytes(64, 224, 224, 768, 3072) == up(M * 768 * 4) + up(M * 768 * 2) + up(M * 3072 * 2)
     assert lib.ldit_workspace_bytes(0, 224, 224, 768, 3072) == 0
+
+
+def test_argument_validation_of_the_backward_entry_points_without_gpu():
+    """Every training entry point rejects null / misaligned pointers and impossible shapes before touching the device."""
+    lib = _lib.load()
+    buf = ctypes.create_string_buffer(256)
+    p16 = (ctypes.addressof(buf) + 15) & ~15
+    assert lib.ldit_gemm_dgrad(None, p16, p16, 128, 768, 768, None) == -1
+    assert lib.ldit_gemm_dgrad(p16, p16, p16, 128, 770, 768, None) == -2           # N_out not a multiple of 8
+    assert lib.ldit_gemm_dgrad(p16, p16 + 2, p16, 128, 768, 768, None) == -3
+    assert lib.ldit_gemm_wgrad(p16, None, p16, 128, 768, 768, None) == -1
+    assert lib.ldit_gemm_wgrad(p16, p16, p16, 0, 768, 768, None) == -2
+    assert lib.ldit_gemm_wgrad(p16, p16, p16 + 4, 128, 768, 768, None) == -3
+    assert lib.ldit_attention_lse(p16, p16, None, None, 1, 197, 12, 14, 14, None) == -1      # the statistics buffer is required
+    assert lib.ldit_attention_lse(p16, p16, None, p16, 1, 100, 12, 14, 14, None) == -2       # N != Gh*Gw + 1
+    assert lib.ldit_attention_bwd(p16, p16, p16, 1, 257, 12, None) == -6                     # beyond two query tiles
+    assert lib.ldit_attention_bwd_flash(p16, p16, None, p16, p16, p16, p16, None, None, 1, 197, 12, 14, 14, None) == -1
+    assert lib.ldit_attention_bwd_flash(p16, p16, p16, p16, p16, p16, p16, p16, None, 1, 197, 12, 14, 14, None) == -1   # table without gradient
+    assert lib.ldit_attention_bwd_flash(p16, p16, p16, p16, p16, p16, p16, p16, p16, 1, 100, 12, 14, 14, None) == -2    # table and N != Gh*Gw + 1
+    assert lib.ldit_scale_residual_rows(p16, p16, None, p16, 0, p16, 8, 128, None) == -2     # row scales need rows_per_image
+    assert lib.ldit_scale_residual_rows_bwd(None, p16, None, None, 1, p16, None, 8, 128, None) == -1
+    assert lib.ldit_resample_taps_bwd(p16, None, 1, 14, 14, 768, 2.0, None) == -1
+    assert lib.ldit_resample_taps_bwd(p16, p16, 1, 14, 14, 770, 2.0, None) == -2
+    assert lib.ldit_batch_sum(p16, p16, 4, 6, None) == -2                                     # R % 4
+    assert lib.ldit_layernorm_bwd(p16, p16, p16, None, p16, p16, p16, 4, 100, 1e-12, None) == -2
